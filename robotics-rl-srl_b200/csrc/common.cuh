@@ -1,0 +1,68 @@
+// Internal declarations shared by the translation units of libsrl_sim_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/srl_sim.h"
+
+void srl_set_error(const char* fmt, ...);
+
+#define SRL_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            srl_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,              \
+                          cudaGetErrorString(_e));                                          \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+// ---- MobileRobot family: structure-of-arrays state in HBM, 16-byte records per field -----
+struct MobileDev {
+    double2* pos;   // [N] robot_pos (x, y); z is identically 0 (mobile_robot_env.py:170)
+    double2* tgt0;  // [N] target_pos (x, y)
+    double2* tgt1;  // [N] second target (2-target variant only)
+    int4*    meta;  // [N] {_env_step_counter, current_target | has_bumped << 8, episode, total_steps}
+    double2* ep;    // [N] {running episode return, running episode length}
+};
+
+struct KukaDev;  // kuka.cuh
+
+struct srl_sim {
+    int kind;
+    int n;
+    int device;
+    srl_cfg cfg;
+    uint64_t seed;
+    int auto_reset;
+    int max_steps;
+    MobileDev mob;
+    KukaDev* kuka;
+    uint64_t launches;
+    cudaEvent_t ev0, ev1;
+    bool ev_valid;
+    // device staging buffers for the *_host entry points (grown on demand)
+    void* stage[5];
+    size_t stage_cap[5];
+};
+
+static inline bool srl_is_mobile(int kind) { return kind >= SRL_ENV_MOBILE && kind <= SRL_ENV_MOBILE_LINE_TARGET; }
+static inline bool srl_is_kuka(int kind) { return kind >= SRL_ENV_KUKA_BUTTON && kind <= SRL_ENV_KUKA_MOVING_BUTTON; }
+
+// ---- launchers (mobile_kernels.cu) -------------------------------------------------------
+int mobile_alloc(srl_sim* s);
+void mobile_free(srl_sim* s);
+int mobile_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st);
+int mobile_launch_rollout(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew,
+                          uint8_t* done, float* ep_ret, int32_t* ep_len, cudaStream_t st);
+int mobile_get_state(srl_sim* s, int field, void* dst, size_t bytes);
+int mobile_set_state(srl_sim* s, int field, const void* src, size_t bytes);
+
+// ---- launchers (kuka_kernels.cu) ---------------------------------------------------------
+int kuka_alloc(srl_sim* s, const void* blob, size_t bytes);
+void kuka_free(srl_sim* s);
+int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st);
+int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew,
+                        uint8_t* done, float* ep_ret, int32_t* ep_len, cudaStream_t st);
+int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes);
+int kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes);
