@@ -1,0 +1,589 @@
+// Kuka button-push physics, device side (sm_100a), one thread per environment.
+//
+// One call of kuka_physics_step() == Kuka.applyAction's IK + 12 motor set-points
+// (environments/kuka_gym/kuka.py:142-187) followed by one p.stepSimulation()
+// (environments/kuka_gym/kuka_button_gym_env.py:351) of the reference, restated as:
+//
+//   FK in the world frame  ->  sphere contacts (flags + rows)  ->  DLS inverse kinematics
+//   -> composite-rigid-body mass matrix M(q) and recursive Newton-Euler bias in WORLD coordinates
+//      about the world origin (sub-tree wrenches and composite inertias accumulate by plain sums)
+//   -> Cholesky M = L L^T, A = M^-1 = L^-T L^-1 held in REGISTERS (78 unique entries)
+//   -> 150 projected Gauss-Seidel sweeps over [motor | limit | contact | friction] rows; the 12 motor
+//      rows have unit Jacobians, so a row is  v += A[:,i] * delta  (12 FMAs, no memory traffic)
+//   -> semi-implicit Euler.
+//
+// The formulation is deliberately different from the CPU oracle (ABA + per-row impulse responses in
+// double precision); the two must agree to fp32 tolerance.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "kuka_params.cuh"
+#include "philox.cuh"
+
+#define KK_DEV __device__ __forceinline__
+
+struct f3 { float x, y, z; };
+KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+KK_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+KK_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+KK_DEV f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+KK_DEV float dot3(f3 a, f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+KK_DEV f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+KK_DEV float norm3(f3 a) { return sqrtf(dot3(a, a)); }
+// symmetric 3x3 (xx xy xz yy yz zz) times vector
+KK_DEV f3 symv(const float* I, f3 v) {
+    return mk3(I[0] * v.x + I[1] * v.y + I[2] * v.z, I[1] * v.x + I[3] * v.y + I[4] * v.z, I[2] * v.x + I[4] * v.y + I[5] * v.z);
+}
+
+// parent of each body: chain 0..7, fingers 8->9 and 10->11 hanging off the gripper base (7)
+__device__ __constant__ const int KK_PARENT[KK_NB] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 7, 10};
+#define KK_PAR(i) ((i) == 0 ? -1 : (i) == 10 ? 7 : (i) - 1)
+
+// ---- per-env dynamic state, register resident across the steps of a fused rollout ----
+struct KukaEnv {
+    float q[KK_NB], qd[KK_NB];
+    float qb, qdb;           // button glider
+    float ee[3];             // commanded end-effector position (kuka.py:73,134-139)
+    float bbx, bby;          // button base x, y (z is a model constant)
+    float tgt[3];            // button_pos: target frozen at reset (:273-274)
+    float grip[3], eepos[3]; // link states after the last step
+    int counter, n_contacts, n_outside, terminated;
+    int cbutton, ctable;     // manifold flags of the last stepSimulation
+    uint32_t episode, total_steps;
+    float ep_ret; int ep_len;
+};
+
+struct KukaKin {             // kinematics of the current configuration
+    f3 a[KK_NB];             // joint axes, world
+    f3 p[KK_NB];             // joint frame origins, world
+    f3 c[KK_NB];             // centres of mass, world
+    float Iw[KK_NB][6];      // rotational inertia about the COM, world axes
+    float R6[9];             // rotation of the IK link (body 6)
+};
+
+struct KukaContacts {        // contact rows of this step (rare; lives in local memory)
+    int n;
+    int body[KK_MAXC], shape[KK_MAXC];
+    float dist[KK_MAXC];
+    f3 nrm[KK_MAXC], pt[KK_MAXC];
+};
+
+// sphere vs upright finite cylinder (axis +z through (cx, cy), z in [z0, z1], radius R)
+KK_DEV void sphere_cylinder(f3 s, float r, float cx, float cy, float z0, float z1, float R, float& dist, f3& n) {
+    const float dx = s.x - cx, dy = s.y - cy;
+    const float rho = sqrtf(dx * dx + dy * dy);
+    const f3 radial = rho > 1e-12f ? mk3(dx / rho, dy / rho, 0.f) : mk3(1.f, 0.f, 0.f);
+    float d;
+    if (s.z >= z1 || s.z <= z0) {
+        const float zf = s.z >= z1 ? z1 : z0;
+        if (rho <= R) { d = fabsf(s.z - zf); n = mk3(0.f, 0.f, s.z >= z1 ? 1.f : -1.f); }
+        else { const f3 vec = mk3(dx - radial.x * R, dy - radial.y * R, s.z - zf); d = norm3(vec); n = (1.0f / d) * vec; }
+    } else if (rho > R) {
+        d = rho - R; n = radial;
+    } else {
+        const float d_top = z1 - s.z, d_side = R - rho;
+        if (d_top <= d_side) { d = -d_top; n = mk3(0.f, 0.f, 1.f); } else { d = -d_side; n = radial; }
+    }
+    dist = d - r;
+}
+
+// Forward kinematics + link states + collision detection against table / button disc / button stack.
+template <bool WITH_CONTACTS>
+KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& ct) {
+    float R[9], R7[9];
+    float Rall[WITH_CONTACTS ? KK_NB : 1][9];  // per-body rotations for the sphere loop (local memory)
+    f3 p = mk3(P.base[0], P.base[1], P.base[2]), p7 = p;
+    R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+    int cbutton = 0, ctable = 0;
+    if (WITH_CONTACTS) ct.n = 0;
+    const float bz = P.btn_base[2];
+    const float disc0 = bz + P.glider_z + e.qb + P.disc_z0, disc1 = bz + P.glider_z + e.qb + P.disc_z1;
+    const float zmax_shapes = fmaxf(disc1, fmaxf(bz + P.stack_top, P.table_z));
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        if (i == 10) {  // second finger restarts from the gripper base
+#pragma unroll
+            for (int t = 0; t < 9; ++t) R[t] = R7[t];
+            p = p7;
+        }
+        // child frame: p_i = p_parent + R_parent * origin ; R_i = R_parent * rot * Rodrigues(axis, q)
+        p = mk3(p.x + R[0] * P.org[i][0] + R[1] * P.org[i][1] + R[2] * P.org[i][2],
+                p.y + R[3] * P.org[i][0] + R[4] * P.org[i][1] + R[5] * P.org[i][2],
+                p.z + R[6] * P.org[i][0] + R[7] * P.org[i][1] + R[8] * P.org[i][2]);
+        float s, c;
+        sincosf(e.q[i], &s, &c);
+        const float t = 1.f - c, ax = P.axis[i][0], ay = P.axis[i][1], az = P.axis[i][2];
+        const float Q[9] = {c + t * ax * ax, t * ax * ay - s * az, t * ax * az + s * ay,
+                            t * ax * ay + s * az, c + t * ay * ay, t * ay * az - s * ax,
+                            t * ax * az - s * ay, t * ay * az + s * ax, c + t * az * az};
+        float B[9], Rn[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                B[3 * r + cc] = P.rot[i][3 * r] * Q[cc] + P.rot[i][3 * r + 1] * Q[3 + cc] + P.rot[i][3 * r + 2] * Q[6 + cc];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                Rn[3 * r + cc] = R[3 * r] * B[cc] + R[3 * r + 1] * B[3 + cc] + R[3 * r + 2] * B[6 + cc];
+#pragma unroll
+        for (int t2 = 0; t2 < 9; ++t2) R[t2] = Rn[t2];
+        k.p[i] = p;
+        k.a[i] = mk3(R[0] * ax + R[1] * ay + R[2] * az, R[3] * ax + R[4] * ay + R[5] * az, R[6] * ax + R[7] * ay + R[8] * az);
+        k.c[i] = mk3(p.x + R[0] * P.com[i][0] + R[1] * P.com[i][1] + R[2] * P.com[i][2],
+                     p.y + R[3] * P.com[i][0] + R[4] * P.com[i][1] + R[5] * P.com[i][2],
+                     p.z + R[6] * P.com[i][0] + R[7] * P.com[i][1] + R[8] * P.com[i][2]);
+        {   // Iw = R Ic R^T
+            const float* I = P.Ic[i];
+            float T[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                T[3 * r + 0] = R[3 * r] * I[0] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[2];
+                T[3 * r + 1] = R[3 * r] * I[1] + R[3 * r + 1] * I[3] + R[3 * r + 2] * I[4];
+                T[3 * r + 2] = R[3 * r] * I[2] + R[3 * r + 1] * I[4] + R[3 * r + 2] * I[5];
+            }
+            k.Iw[i][0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+            k.Iw[i][1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+            k.Iw[i][2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+            k.Iw[i][3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+            k.Iw[i][4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+            k.Iw[i][5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+        }
+        if (i == 6) {
+#pragma unroll
+            for (int t2 = 0; t2 < 9; ++t2) k.R6[t2] = R[t2];
+        }
+        if (i == 7) {
+#pragma unroll
+            for (int t2 = 0; t2 < 9; ++t2) R7[t2] = R[t2];
+            p7 = p;
+        }
+        if (WITH_CONTACTS) {
+#pragma unroll
+            for (int t2 = 0; t2 < 9; ++t2) Rall[i][t2] = R[t2];
+        }
+    }
+    if (WITH_CONTACTS) {
+        // collision detection: ONE copy of the sphere-vs-shape code, runtime loop over the spheres
+#pragma unroll 1
+        for (int sidx = 0; sidx < P.nsph; ++sidx) {
+            const int b = P.sph_body[sidx];
+            const float* Rb = Rall[b];
+            const f3 pb = k.p[b];
+            const f3 sc = mk3(pb.x + Rb[0] * P.sph_c[sidx][0] + Rb[1] * P.sph_c[sidx][1] + Rb[2] * P.sph_c[sidx][2],
+                              pb.y + Rb[3] * P.sph_c[sidx][0] + Rb[4] * P.sph_c[sidx][1] + Rb[5] * P.sph_c[sidx][2],
+                              pb.z + Rb[6] * P.sph_c[sidx][0] + Rb[7] * P.sph_c[sidx][1] + Rb[8] * P.sph_c[sidx][2]);
+            const float r = P.sph_r[sidx];
+            if (sc.z - r - zmax_shapes > P.cdist) continue;  // cheap reject: well above every shape
+#pragma unroll 1
+            for (int shape = 0; shape < 3; ++shape) {
+                float dist; f3 nn;
+                if (shape == 0) {
+                    if (sc.x < P.txmin || sc.x > P.txmax || sc.y < P.tymin || sc.y > P.tymax) continue;
+                    dist = sc.z - P.table_z - r; nn = mk3(0.f, 0.f, 1.f);
+                } else {
+                    const float z0 = shape == 1 ? disc0 : bz, z1 = shape == 1 ? disc1 : bz + P.stack_top;
+                    sphere_cylinder(sc, r, e.bbx, e.bby, z0, z1, shape == 1 ? P.disc_r : P.stack_r, dist, nn);
+                }
+                if (dist > P.cdist) continue;
+                if (shape == 0) ctable = 1;
+                if (shape == 1) cbutton = 1;
+                if (ct.n < P.max_contacts && ct.n < KK_MAXC) {
+                    const int n = ct.n;
+                    ct.body[n] = b; ct.shape[n] = shape; ct.dist[n] = dist; ct.nrm[n] = nn;
+                    ct.pt[n] = sc - r * nn;
+                    ct.n = n + 1;
+                }
+            }
+        }
+    }
+    if (WITH_CONTACTS) { e.cbutton = cbutton; e.ctable = ctable; }
+    e.grip[0] = k.c[8].x; e.grip[1] = k.c[8].y; e.grip[2] = k.c[8].z;   // getLinkState(kuka, 8)[0]: COM of link 8
+    e.eepos[0] = k.p[6].x; e.eepos[1] = k.p[6].y; e.eepos[2] = k.p[6].z;
+}
+
+// (x, y, z, w) of a rotation matrix, branch on the largest diagonal term
+KK_DEV void quat_from_matrix(const float* R, float* q) {
+    const float tr = R[0] + R[4] + R[8];
+    if (tr > 0.f) {
+        const float s = sqrtf(tr + 1.0f) * 2.f;
+        q[3] = 0.25f * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        const float s = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f;
+        q[3] = (R[7] - R[5]) / s; q[0] = 0.25f * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s;
+    } else if (R[4] > R[8]) {
+        const float s = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f;
+        q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25f * s; q[2] = (R[5] + R[7]) / s;
+    } else {
+        const float s = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f;
+        q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25f * s;
+    }
+}
+
+// One damped-least-squares IK iteration at the current joint state (pybullet 1.8.6 / BussIK DLS):
+// dtheta = (J^T J + lambda I)^-1 J^T e over the 7 arm joints.  The 7x7 normal equations are formed and
+// solved in float64: they square the Jacobian's condition number, which float32 cannot afford.
+KK_DEV void kuka_ik(const KukaParams& P, const KukaEnv& e, const KukaKin& k, float* q_ik) {
+    constexpr int n = 7;
+    float J[6][n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        const f3 l = cross3(k.a[j], k.p[6] - k.p[j]);
+        J[0][j] = l.x; J[1][j] = l.y; J[2][j] = l.z; J[3][j] = k.a[j].x; J[4][j] = k.a[j].y; J[5][j] = k.a[j].z;
+    }
+    float err[6];
+    err[0] = e.ee[0] - k.p[6].x; err[1] = e.ee[1] - k.p[6].y; err[2] = e.ee[2] - k.p[6].z;
+    float qc[4];
+    quat_from_matrix(k.R6, qc);
+    const float cx = -qc[0], cy = -qc[1], cz = -qc[2], cw = qc[3];
+    const float dx = P.ikq[3] * cx + P.ikq[0] * cw + P.ikq[1] * cz - P.ikq[2] * cy;
+    const float dy = P.ikq[3] * cy - P.ikq[0] * cz + P.ikq[1] * cw + P.ikq[2] * cx;
+    const float dz = P.ikq[3] * cz + P.ikq[0] * cy - P.ikq[1] * cx + P.ikq[2] * cw;
+    const float dw = P.ikq[3] * cw - P.ikq[0] * cx - P.ikq[1] * cy - P.ikq[2] * cz;
+    const float vn = sqrtf(dx * dx + dy * dy + dz * dz);
+    // angle = 2 atan2(|v|, w) (== btQuaternion::getAngle, but well conditioned for small angles in fp32)
+    float angle = 2.0f * atan2f(vn, dw);
+    if (angle > 3.14159265358979f) angle -= 6.28318530717959f;
+    if (vn > 1e-12f) { const float s = angle / vn; err[3] = s * dx; err[4] = s * dy; err[5] = s * dz; }
+    else { err[3] = err[4] = err[5] = 0.f; }
+    double A[n][n], b[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) s = fma((double)J[r][i], (double)J[r][j], s);
+            A[i][j] = s;
+        }
+        A[i][i] += P.ik_damp;
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s = fma((double)J[r][i], (double)err[r], s);
+        b[i] = s;
+    }
+    // Cholesky A = L L^T (A is SPD thanks to the damping), forward/back substitution
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        double d = A[j][j];
+#pragma unroll
+        for (int kk = 0; kk < j; ++kk) d -= A[j][kk] * A[j][kk];
+        const double inv = rsqrt(d);
+        A[j][j] = inv;  // store 1 / L_jj
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[i][j];
+#pragma unroll
+            for (int kk = 0; kk < j; ++kk) s -= A[i][kk] * A[j][kk];
+            A[i][j] = s * inv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) s -= A[i][kk] * b[kk];
+        b[i] = s * A[i][i];
+    }
+#pragma unroll
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+#pragma unroll
+        for (int kk = i + 1; kk < n; ++kk) s -= A[kk][i] * b[kk];
+        b[i] = s * A[i][i];
+    }
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(b[i]));
+    const double max_angle = 0.78539816339744830962;  // BussIK MaxAngleDLS = 45 degrees
+    const double scale = mx > max_angle ? max_angle / mx : 1.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) q_ik[i] = e.q[i] + (float)(scale * b[i]);
+}
+
+// Mass matrix (lower triangle, m[i][j], j <= i) by the composite-rigid-body algorithm and bias torques
+// (gravity, velocity products, Bullet link damping) by recursive Newton-Euler, both in world coordinates
+// about the world origin: sub-tree quantities accumulate by plain addition.
+KK_DEV void kuka_dynamics(const KukaParams& P, const KukaEnv& e, const KukaKin& k, float (&M)[KK_NB][KK_NB], float* bias) {
+    f3 pv[KK_NB];  // linear part of the joint motion vector about the origin: p x a
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) pv[i] = cross3(k.p[i], k.a[i]);
+
+    // ---- RNEA forward pass + body wrenches ----
+    f3 w[KK_NB], vO[KK_NB], aw[KK_NB], av[KK_NB], nn[KK_NB], ff[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        const int pa = KK_PAR(i);
+        const f3 wp = pa < 0 ? mk3(0.f, 0.f, 0.f) : w[pa];
+        const f3 vp = pa < 0 ? mk3(0.f, 0.f, 0.f) : vO[pa];
+        const f3 awp = pa < 0 ? mk3(0.f, 0.f, 0.f) : aw[pa];
+        const f3 avp = pa < 0 ? mk3(0.f, 0.f, -P.gz) : av[pa];  // gravity as a fictitious base acceleration
+        const float qd = e.qd[i];
+        w[i] = wp + qd * k.a[i];
+        vO[i] = vp + qd * pv[i];
+        aw[i] = awp + qd * cross3(wp, k.a[i]);
+        av[i] = avp + qd * (cross3(wp, pv[i]) + cross3(vp, k.a[i]));
+        // spatial inertia about the origin: m, h = m c, I_O = Iw + m (|c|^2 1 - c c^T)
+        const float m = P.mass[i];
+        const f3 c = k.c[i];
+        const f3 h = m * c;
+        float IO[6];
+        IO[0] = k.Iw[i][0] + m * (c.y * c.y + c.z * c.z);
+        IO[1] = k.Iw[i][1] - m * c.x * c.y;
+        IO[2] = k.Iw[i][2] - m * c.x * c.z;
+        IO[3] = k.Iw[i][3] + m * (c.x * c.x + c.z * c.z);
+        IO[4] = k.Iw[i][4] - m * c.y * c.z;
+        IO[5] = k.Iw[i][5] + m * (c.x * c.x + c.y * c.y);
+        const f3 Lv = symv(IO, w[i]) + cross3(h, vO[i]);
+        const f3 Pv = m * vO[i] + cross3(w[i], h);
+        const f3 La = symv(IO, aw[i]) + cross3(h, av[i]);
+        const f3 Pa = m * av[i] + cross3(aw[i], h);
+        f3 n = La + cross3(w[i], Lv) + cross3(vO[i], Pv);
+        f3 f = Pa + cross3(w[i], Pv);
+        // btMultiBody link damping (linear/angular 0.04, K1 = K2): resisting wrench added to the bias
+        const f3 vc = vO[i] + cross3(w[i], c);
+        const f3 F = (P.kl * m * (1.0f + norm3(vc))) * vc;
+        const f3 T = (P.ka * (1.0f + norm3(w[i]))) * symv(k.Iw[i], w[i]);
+        n = n + T + cross3(c, F);
+        f = f + F;
+        nn[i] = n; ff[i] = f;
+    }
+    // ---- RNEA backward pass: bias_i = s_i . (wrench of the sub-tree) ----
+#pragma unroll
+    for (int i = KK_NB - 1; i >= 0; --i) {
+        bias[i] = dot3(k.a[i], nn[i]) + dot3(pv[i], ff[i]);
+        const int pa = KK_PAR(i);
+        if (pa >= 0) { nn[pa] = nn[pa] + nn[i]; ff[pa] = ff[pa] + ff[i]; }
+    }
+    // ---- CRBA: composite inertias from the leaves, M_ij = s_i . (I^c_j s_j) for i ancestor-or-self of j ----
+    float cm[KK_NB]; f3 ch[KK_NB]; float cI[KK_NB][6];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        const float m = P.mass[i];
+        const f3 c = k.c[i];
+        cm[i] = m; ch[i] = m * c;
+        cI[i][0] = k.Iw[i][0] + m * (c.y * c.y + c.z * c.z);
+        cI[i][1] = k.Iw[i][1] - m * c.x * c.y;
+        cI[i][2] = k.Iw[i][2] - m * c.x * c.z;
+        cI[i][3] = k.Iw[i][3] + m * (c.x * c.x + c.z * c.z);
+        cI[i][4] = k.Iw[i][4] - m * c.y * c.z;
+        cI[i][5] = k.Iw[i][5] + m * (c.x * c.x + c.y * c.y);
+    }
+#pragma unroll
+    for (int j = KK_NB - 1; j >= 0; --j) {
+        const f3 Pm = cm[j] * pv[j] + cross3(k.a[j], ch[j]);             // linear momentum of the composite
+        const f3 Lm = symv(cI[j], k.a[j]) + cross3(ch[j], pv[j]);        // angular momentum about the origin
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {
+            // i ancestor-or-self of j  (chain 0..7 precedes everything; 8 -> 9; 10 -> 11)
+            const bool anc = (i == j) || (i <= 7 && i < j) || (i == 8 && j == 9) || (i == 10 && j == 11);
+            if (i <= j) {
+                if (anc) M[j][i] = dot3(k.a[i], Lm) + dot3(pv[i], Pm);
+                else M[j][i] = 0.f;
+            }
+        }
+        const int pa = KK_PAR(j);
+        if (pa >= 0) {
+            cm[pa] += cm[j]; ch[pa] = ch[pa] + ch[j];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) cI[pa][t] += cI[j][t];
+        }
+    }
+}
+
+// In-place: M (lower) -> A = M^-1 (lower triangle valid), via Cholesky and triangular inverse.
+KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
+    constexpr int n = KK_NB;
+    float dinv[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        float d = M[j][j];
+#pragma unroll
+        for (int kk = 0; kk < j; ++kk) d = fmaf(-M[j][kk], M[j][kk], d);
+        const float inv = rsqrtf(d);
+        dinv[j] = inv;
+        M[j][j] = d * inv;
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            float s = M[i][j];
+#pragma unroll
+            for (int kk = 0; kk < j; ++kk) s = fmaf(-M[i][kk], M[j][kk], s);
+            M[i][j] = s * inv;
+        }
+    }
+    // X = L^-1 (lower), in place column by column
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        M[j][j] = dinv[j];
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int kk = j; kk < i; ++kk) s = fmaf(M[i][kk], M[kk][j], s);
+            M[i][j] = -s * dinv[i];
+        }
+    }
+    // A = X^T X : A[i][j] = sum_{k >= i} X[k][i] X[k][j]   (i >= j); rows ascending keeps inputs intact
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int kk = i; kk < n; ++kk) s = fmaf(M[kk][i], M[kk][j], s);
+            M[i][j] = s;
+        }
+    }
+}
+
+#define KK_A(i, j) ((i) >= (j) ? A[i][j] : A[j][i])
+
+// One applyAction + stepSimulation.  `k`/`ct` hold the kinematics / contacts of the CURRENT configuration
+// (computed by the caller with kuka_fk<true>); on return q, qd, qb, qdb are advanced by one time step.
+KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed) {
+    // ---- applyAction: IK + motor set-points (kuka.py:142-187) ----
+    float q_ik[7];
+    kuka_ik(P, e, k, q_ik);
+    // ---- dynamics ----
+    float A[KK_NB][KK_NB], bias[KK_NB];
+    kuka_dynamics(P, e, k, A, bias);
+    kuka_spd_inverse(A);
+    float v[KK_ND];
+    {
+        float rhs[KK_NB];
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) rhs[i] = -P.damping[i] * e.qd[i] - bias[i];
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < KK_NB; ++j) s = fmaf(KK_A(i, j), rhs[j], s);
+            v[i] = fmaf(P.dt, s, e.qd[i]);
+        }
+        const float vb = e.qdb;
+        v[KK_NB] = fmaf(P.dt, P.gz - P.kl * vb * (1.0f + fabsf(vb)), vb);
+    }
+    // ---- motor rows: target velocity, impulse bound (btMultiBodyJointMotor) ----
+    float tgt[KK_NB], lam[KK_NB], invd[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        const float qdes = (P.tmode[i] == 0 && i < 7) ? q_ik[i < 7 ? i : 0] : 0.f;
+        float t = fmaf(P.kp_dt[i], qdes - e.q[i], v[i]) - P.kd[i] * v[i];
+        if (P.maxvel[i] > 0.f) t = fminf(fmaxf(t, -P.maxvel[i]), P.maxvel[i]);
+        tgt[i] = t; lam[i] = 0.f; invd[i] = 1.0f / A[i][i];
+    }
+    float b_tgt, b_hi, b_lam = 0.f;
+    if (button_armed) { b_tgt = fmaf(P.btn_kp_dt, P.btn_target - e.qb, v[KK_NB]) - P.btn_kd * v[KK_NB]; b_hi = P.btn_maximp; }
+    else { b_tgt = 0.f; b_hi = P.btn_idle_imp; }
+    const float b_invd = 1.0f / P.btn_minv;
+    // ---- limit rows (active while the joint is on / beyond the limit) ----
+    const bool bl_lo = (e.qb - P.gl_lo) <= P.lim_eps, bl_hi = (P.gl_hi - e.qb) <= P.lim_eps;
+    const float bl_lo_t = -P.erp * (e.qb - P.gl_lo) * P.inv_dt, bl_hi_t = -P.erp * (P.gl_hi - e.qb) * P.inv_dt;
+    float bl_lo_lam = 0.f, bl_hi_lam = 0.f;
+    unsigned lim_lo_mask = 0u, lim_hi_mask = 0u;
+    float lim_lam_lo[KK_NB], lim_lam_hi[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        if ((e.q[i] - P.lower[i]) <= P.lim_eps) lim_lo_mask |= 1u << i;
+        if ((P.upper[i] - e.q[i]) <= P.lim_eps) lim_hi_mask |= 1u << i;
+        lim_lam_lo[i] = 0.f; lim_lam_hi[i] = 0.f;
+    }
+    // ---- contact rows: J, W = M^-1 J^T, 1/D, target; two friction rows each (rare path, local memory) ----
+    const int nc = ct.n;
+    float cJ[3 * KK_MAXC][KK_ND], cW[3 * KK_MAXC][KK_ND], c_invd[3 * KK_MAXC], c_tgt[3 * KK_MAXC], c_lam[3 * KK_MAXC];
+    if (nc > 0) {
+        for (int r = 0; r < 3 * nc; ++r) {
+            const int c = r < nc ? r : (r - nc) >> 1;
+            f3 dir = ct.nrm[c];
+            if (r >= nc) {  // btPlaneSpace1 tangents
+                const f3 n = ct.nrm[c];
+                f3 t1, t2;
+                if (fabsf(n.z) > 0.70710678f) {
+                    const float a = n.y * n.y + n.z * n.z, kk = rsqrtf(a);
+                    t1 = mk3(0.f, -n.z * kk, n.y * kk); t2 = mk3(a * kk, -n.x * t1.z, n.x * t1.y);
+                } else {
+                    const float a = n.x * n.x + n.y * n.y, kk = rsqrtf(a);
+                    t1 = mk3(-n.y * kk, n.x * kk, 0.f); t2 = mk3(-n.z * t1.y, n.z * t1.x, a * kk);
+                }
+                dir = ((r - nc) & 1) ? t2 : t1;
+            }
+            const int body = ct.body[c];
+#pragma unroll
+            for (int j = 0; j < KK_NB; ++j) {
+                const bool anc = (j == body) || (j <= 7 && j < body) || (j == 8 && body == 9) || (j == 10 && body == 11);
+                cJ[r][j] = anc ? dot3(dir, cross3(k.a[j], ct.pt[c] - k.p[j])) : 0.f;
+            }
+            cJ[r][KK_NB] = ct.shape[c] == 1 ? -dir.z : 0.f;
+            float D = 0.f;
+#pragma unroll
+            for (int i = 0; i < KK_NB; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < KK_NB; ++j) s = fmaf(KK_A(i, j), cJ[r][j], s);
+                cW[r][i] = s; D = fmaf(cJ[r][i], s, D);
+            }
+            cW[r][KK_NB] = cJ[r][KK_NB] * P.btn_minv;
+            D = fmaf(cJ[r][KK_NB], cW[r][KK_NB], D);
+            c_invd[r] = 1.0f / D;
+            c_lam[r] = 0.f;
+            if (r < nc) { const float pen = ct.dist[c]; c_tgt[r] = pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt; }
+            else c_tgt[r] = 0.f;
+        }
+    }
+    // ---- projected Gauss-Seidel: row order = motors (button first), limits (button first), contact normals, friction ----
+    for (int it = 0; it < P.iters; ++it) {
+        {   // button motor
+            const float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
+            v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
+        }
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {  // arm motors: unit Jacobian, W = A[:, i]
+            const float s = fminf(fmaxf(fmaf(tgt[i] - v[i], invd[i], lam[i]), -P.maximp[i]), P.maximp[i]);
+            const float d = s - lam[i];
+            lam[i] = s;
+#pragma unroll
+            for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
+        }
+        if (bl_lo) { const float s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), P.lim_maximp);
+                     v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s; }
+        if (bl_hi) { const float s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), P.lim_maximp);
+                     v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s; }
+        if (lim_lo_mask | lim_hi_mask) {
+#pragma unroll
+            for (int i = 0; i < KK_NB; ++i) {
+                if (lim_lo_mask & (1u << i)) {  // J = +e_i
+                    const float t = -P.erp * (e.q[i] - P.lower[i]) * P.inv_dt;
+                    const float s = fminf(fmaxf(fmaf(t - v[i], invd[i], lim_lam_lo[i]), 0.f), P.lim_maximp);
+                    const float d = s - lim_lam_lo[i]; lim_lam_lo[i] = s;
+#pragma unroll
+                    for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
+                }
+                if (lim_hi_mask & (1u << i)) {  // J = -e_i
+                    const float t = -P.erp * (P.upper[i] - e.q[i]) * P.inv_dt;
+                    const float s = fminf(fmaxf(fmaf(t + v[i], invd[i], lim_lam_hi[i]), 0.f), P.lim_maximp);
+                    const float d = s - lim_lam_hi[i]; lim_lam_hi[i] = s;
+#pragma unroll
+                    for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(-KK_A(j, i), d, v[j]);
+                }
+            }
+        }
+        if (nc > 0) {
+            for (int r = 0; r < 3 * nc; ++r) {
+                float jv = 0.f;
+#pragma unroll
+                for (int j = 0; j < KK_ND; ++j) jv = fmaf(cJ[r][j], v[j], jv);
+                float lo = 0.f, hi = 1e10f;
+                if (r >= nc) { hi = P.mu * c_lam[(r - nc) >> 1]; lo = -hi; }
+                const float s = fminf(fmaxf(fmaf(c_tgt[r] - jv, c_invd[r], c_lam[r]), lo), hi);
+                const float d = s - c_lam[r]; c_lam[r] = s;
+#pragma unroll
+                for (int j = 0; j < KK_ND; ++j) v[j] = fmaf(cW[r][j], d, v[j]);
+            }
+        }
+    }
+    // ---- semi-implicit Euler ----
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) { e.qd[i] = v[i]; e.q[i] = fmaf(P.dt, v[i], e.q[i]); }
+    e.qdb = v[KK_NB]; e.qb = fmaf(P.dt, v[KK_NB], e.qb);
+}

@@ -1,8 +1,554 @@
-// placeholder until the Kuka kernels land
+// Kuka button-push family -- kernels and host launchers (sm_100a).
+//
+// Replaces, for thousands of envs in lockstep, KukaButtonGymEnv.reset/step/step2/_reward/_termination
+// (environments/kuka_gym/kuka_button_gym_env.py:214-281,293-368,422-463), Kuka.applyAction
+// (environments/kuka_gym/kuka.py:118-187) and the PyBullet calls behind them.
+//
+// Mapping: ONE THREAD PER ENV, all dynamic state in registers for the whole fused rollout.  The projected
+// Gauss-Seidel solve (150 sweeps x >= 13 strictly sequential rows) is a dependency chain that no amount of
+// intra-env parallelism shortens, so lanes are not spent on it; instead `envs_per_warp` < 32 spreads a small
+// batch over all 592 warp schedulers (4096 envs -> ~600 warps of 7 live lanes), which also bounds the cost of
+// the divergent 5-step reset to the few envs sharing a warp.  The robot model arrives as a __grid_constant__
+// parameter block (constant bank, folded into FFMA operands).  HBM traffic is the SoA state once per launch
+// (float4 / int4 records, coalesced) plus action + noise in and obs + reward + done out per step.
+#include <stdio.h>
+#include <string.h>
+#include <vector>
 #include "common.cuh"
-int kuka_alloc(srl_sim*, const void*, size_t) { srl_set_error("kuka kernels not built yet"); return 1; }
-void kuka_free(srl_sim*) {}
-int kuka_launch_reset(srl_sim*, const uint8_t*, const double*, float*, cudaStream_t) { return 1; }
-int kuka_launch_rollout(srl_sim*, int, const void*, const float*, float*, float*, uint8_t*, float*, int32_t*, cudaStream_t) { return 1; }
-int kuka_get_state(srl_sim*, int, void*, size_t) { return 1; }
-int kuka_set_state(srl_sim*, int, const void*, size_t) { return 1; }
+#include "kuka_device.cuh"
+
+struct KukaDev {
+    float4* q[3];    // [N] joint positions  (12 floats as 3 x float4)
+    float4* qd[3];   // [N] joint velocities
+    float4* misc0;   // ee.x ee.y ee.z qb
+    float4* misc1;   // qdb btn_base.x btn_base.y ep_ret
+    float4* tgt;     // button_pos.xyz, -
+    float4* grip;    // gripper_pos.xyz, -
+    float4* eepos;   // link-6 origin xyz, -
+    int4*   cnt;     // counter, n_contacts, n_outside, terminated | cbutton << 1 | ctable << 2
+    int4*   cnt2;    // episode, total_steps, ep_len, -
+    KukaParams P;
+    int epw;         // live lanes per warp
+};
+
+namespace {
+
+constexpr float DELTA_V = 0.03f, DELTA_V_CONTINUOUS = 0.0035f;            // kuka_button_gym_env.py:27-28
+constexpr double NOISE_STD = 0.01, NOISE_STD_CONTINUOUS = 0.0001;          // :31-32
+constexpr int N_CONTACTS_BEFORE_TERMINATION = 5, N_STEPS_OUTSIDE_SAFETY_SPHERE = 5000, N_RANDOM_ACTIONS_AT_INIT = 5;
+
+KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 a = d.q[k][i], b = d.qd[k][i];
+        e.q[4 * k] = a.x; e.q[4 * k + 1] = a.y; e.q[4 * k + 2] = a.z; e.q[4 * k + 3] = a.w;
+        e.qd[4 * k] = b.x; e.qd[4 * k + 1] = b.y; e.qd[4 * k + 2] = b.z; e.qd[4 * k + 3] = b.w;
+    }
+    const float4 m0 = d.misc0[i], m1 = d.misc1[i], tg = d.tgt[i], gr = d.grip[i], ep = d.eepos[i];
+    const int4 c = d.cnt[i], c2 = d.cnt2[i];
+    e.ee[0] = m0.x; e.ee[1] = m0.y; e.ee[2] = m0.z; e.qb = m0.w;
+    e.qdb = m1.x; e.bbx = m1.y; e.bby = m1.z; e.ep_ret = m1.w;
+    e.tgt[0] = tg.x; e.tgt[1] = tg.y; e.tgt[2] = tg.z;
+    e.grip[0] = gr.x; e.grip[1] = gr.y; e.grip[2] = gr.z;
+    e.eepos[0] = ep.x; e.eepos[1] = ep.y; e.eepos[2] = ep.z;
+    e.counter = c.x; e.n_contacts = c.y; e.n_outside = c.z;
+    e.terminated = c.w & 1; e.cbutton = (c.w >> 1) & 1; e.ctable = (c.w >> 2) & 1;
+    e.episode = (uint32_t)c2.x; e.total_steps = (uint32_t)c2.y; e.ep_len = c2.z;
+}
+
+KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        d.q[k][i] = make_float4(e.q[4 * k], e.q[4 * k + 1], e.q[4 * k + 2], e.q[4 * k + 3]);
+        d.qd[k][i] = make_float4(e.qd[4 * k], e.qd[4 * k + 1], e.qd[4 * k + 2], e.qd[4 * k + 3]);
+    }
+    d.misc0[i] = make_float4(e.ee[0], e.ee[1], e.ee[2], e.qb);
+    d.misc1[i] = make_float4(e.qdb, e.bbx, e.bby, e.ep_ret);
+    d.tgt[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], 0.f);
+    d.grip[i] = make_float4(e.grip[0], e.grip[1], e.grip[2], 0.f);
+    d.eepos[i] = make_float4(e.eepos[0], e.eepos[1], e.eepos[2], 0.f);
+    d.cnt[i] = make_int4(e.counter, e.n_contacts, e.n_outside, e.terminated | (e.cbutton << 1) | (e.ctable << 2));
+    d.cnt2[i] = make_int4((int)e.episode, (int)e.total_steps, e.ep_len, 0);
+}
+
+// Kuka.applyAction's accumulate + clip of the commanded end-effector position (kuka.py:134-139)
+KK_DEV void apply_ee_delta(const KukaParams& P, KukaEnv& e, float dx, float dy, float dz) {
+    e.ee[0] = fminf(fmaxf(e.ee[0] + dx, P.box[0]), P.box[1]);
+    e.ee[1] = fminf(fmaxf(e.ee[1] + dy, P.box[2]), P.box[3]);
+    e.ee[2] = fminf(fmaxf(e.ee[2] + dz, P.box[4]), P.box[5]);
+}
+
+// Decode the reference's random initial action k of reset() (:250-268) from host draws or the env's stream.
+KK_DEV void reset_action(const KukaParams& P, const double* __restrict__ d17, uint64_t genv, uint32_t episode, int s,
+                         float& dx, float& dy, float& dz) {
+    dx = dy = dz = 0.f;
+    if (d17) { dx = (float)d17[2 + 3 * s]; dy = (float)d17[3 + 3 * s]; dz = (float)d17[4 + 3 * s]; return; }
+    const uint4 r = philox4x32_10(P.seed, genv, episode, PHILOX_PURPOSE_RESET0 + 1 + s);
+    if (P.is_discrete) {
+        const float sign = philox_u01(r.x, r.y) > 0.5 ? 1.f : -1.f;     // np_random.rand() > 0.5
+        const uint32_t idx = __umulhi(r.z, 3u);                          // np_random.randint(3)
+        dx = idx == 0 ? sign * DELTA_V : 0.f; dy = idx == 1 ? sign * DELTA_V : 0.f; dz = idx == 2 ? sign * DELTA_V : 0.f;
+    } else {
+        // np_random.normal((3,)) is ONE draw from N(loc=3, 1); normalised it is +-1 on all three axes (:263-266)
+        const double u1 = philox_u01(r.x, r.y), u2 = philox_u01(r.z, r.w);
+        const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
+        const float sign = (3.0 + z) >= 0.0 ? 1.f : -1.f;
+        dx = dy = dz = sign * DELTA_V_CONTINUOUS;
+    }
+}
+
+// reset(), first half: restore the post-settle snapshot and place the button (:214-247)
+KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restrict__ d17, uint64_t genv) {
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) { e.q[i] = P.snap_q[i]; e.qd[i] = P.snap_qd[i]; }
+    e.ee[0] = P.snap_ee[0]; e.ee[1] = P.snap_ee[1]; e.ee[2] = P.snap_ee[2];
+    e.qb = P.snap_qb; e.qdb = P.snap_qdb;
+    e.bbx = P.btn_base[0]; e.bby = P.btn_base[1];
+    if (P.random_target) {
+        if (d17) { e.bbx = (float)d17[0]; e.bby = (float)d17[1]; }
+        else {
+            const uint4 r = philox4x32_10(P.seed, genv, e.episode, PHILOX_PURPOSE_RESET0);
+            e.bbx = (float)((double)P.btn_base[0] + (double)P.rand_x * (-1.0 + 2.0 * philox_u01(r.x, r.y)));  // :230
+            e.bby = (float)((double)P.btn_base[1] + (double)P.rand_y * (-1.0 + 2.0 * philox_u01(r.z, r.w)));  // :231
+        }
+    }
+}
+
+// reset(), second half: after the random steps, freeze the target and clear the episode counters (:273-274,215-217)
+KK_DEV void reset_end(const KukaParams& P, KukaEnv& e) {
+    e.tgt[0] = e.bbx; e.tgt[1] = e.bby;
+    e.tgt[2] = P.btn_base[2] + P.glider_z + e.qb + P.target_h;  // button link state + BUTTON_DISTANCE_HEIGHT
+    e.counter = 0; e.n_contacts = 0; e.n_outside = 0; e.terminated = 0;
+    e.ep_ret = 0.f; e.ep_len = 0;
+    e.episode += 1;
+}
+
+// thread -> env mapping with `epw` live lanes per warp
+KK_DEV int env_index(int n, int epw) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (lane >= epw) return -1;
+    const int i = warp * epw + lane;
+    return i < n ? i : -1;
+}
+
+enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2 };
+
+// ONE kernel for reset, lockstep step and fused T-step rollout.  Every thread runs a single micro-step loop
+//     forward kinematics + collision detection  ->  [finish the env step whose physics just ran: reward, done,
+//     auto-reset]  ->  pick the next micro action (policy action, or one of reset()'s random actions)  ->  physics
+// so that the expensive bodies (FK, dynamics, PGS) exist exactly once in the instruction stream, and an env that is
+// inside reset()'s 5 random steps costs its warp 5 extra micro-steps and nothing else.
+//   op = ROLLOUT: T env steps (step() + step2() + _reward() + _termination() + VecEnv auto-reset)
+//   op = RESET  : reset() of the masked envs with optional host-supplied draws
+//   op = SETTLE : the 500 zero-action steps of reset() (:242-247), identical for every episode -> snapshot
+__global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
+                                                       const void* __restrict__ actions, const float* __restrict__ noise,
+                                                       const uint8_t* __restrict__ mask, const double* __restrict__ draws,
+                                                       float* __restrict__ obs, float* __restrict__ rew,
+                                                       uint8_t* __restrict__ done, float* __restrict__ ep_ret,
+                                                       int32_t* __restrict__ ep_len, float* __restrict__ snap) {
+    const int i = env_index(n, d.epw);
+    if (i < 0) return;
+    if (op == KUKA_OP_RESET && mask && !mask[i]) return;
+    const KukaParams& P = d.P;
+    const uint64_t genv = P.env_offset + (uint64_t)i;
+    const size_t N = (size_t)n;
+    KukaEnv e; KukaKin k; KukaContacts ct;
+    env_load(d, i, e);
+
+    int reset_left = 0;          // > 0: inside reset(), this many random micro-steps to go
+    bool in_reset = false;       // reset() in progress (finalised when reset_left reaches 0)
+    bool pending = false;        // an env step's physics has run; reward / done / obs still to be produced
+    int rep = 0, t = 0;
+    int saved_cb = 0, saved_ct = 0;
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    const double* d17 = nullptr;
+    if (op == KUKA_OP_RESET) {
+        d17 = draws ? draws + (size_t)i * 17 : nullptr;
+        reset_begin(P, e, d17, genv);
+        in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
+    } else if (op == KUKA_OP_SETTLE) {
+#pragma unroll
+        for (int j = 0; j < KK_NB; ++j) { e.q[j] = P.snap_q[j]; e.qd[j] = 0.f; }  // resetJointState (kuka.py:68-69)
+        e.ee[0] = P.ee_init[0]; e.ee[1] = P.ee_init[1]; e.ee[2] = P.ee_init[2];
+        e.qb = 0.f; e.qdb = 0.f; e.bbx = P.btn_base[0]; e.bby = P.btn_base[1];
+        in_reset = true; reset_left = 500;
+    }
+    for (;;) {
+        kuka_fk<true>(P, e, k, ct);  // link states of the configuration just reached + collision detection for the next step
+        const int new_cb = e.cbutton, new_ct = e.ctable;
+        if (pending) {
+            // ---- _reward() (:428-463): manifold of the step that just ran, link states after it ----
+            pending = false;
+            const size_t off = (size_t)t * N + (size_t)i;
+            const float ddx = e.tgt[0] - e.grip[0], ddy = e.tgt[1] - e.grip[1], ddz = e.tgt[2] - e.grip[2];
+            const float distance = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+            float reward = saved_cb ? 1.f : 0.f;
+            e.n_contacts += saved_cb;
+            if (distance > P.max_distance || saved_ct) { reward = -1.f; e.n_outside += 1; } else e.n_outside = 0;
+            if (saved_ct || e.n_contacts >= N_CONTACTS_BEFORE_TERMINATION || e.n_outside >= N_STEPS_OUTSIDE_SAFETY_SPHERE) e.terminated = 1;
+            if (P.shape_reward) {
+                if (P.is_discrete) reward = -distance;
+                else if (e.terminated && reward > 0.f) reward = 50.f;
+                else if (e.terminated && reward < 0.f) reward = -250.f;
+                else reward = -distance;
+            }
+            const bool is_done = e.terminated || e.counter > P.max_steps;  // _termination() (:422-426)
+            e.ep_ret += reward; e.ep_len += 1;
+            if (rew) rew[off] = reward;
+            if (done) done[off] = is_done ? 1 : 0;
+            if (is_done) {
+                if (ep_ret) ep_ret[off] = e.ep_ret;
+                if (ep_len) ep_len[off] = e.ep_len;
+            }
+            if (is_done && P.auto_reset) {   // SubprocVecEnv worker: reset and return the post-reset observation
+                d17 = nullptr;
+                reset_begin(P, e, nullptr, genv);
+                in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
+                continue;                      // the snapshot configuration needs its own kinematics
+            }
+            if (obs) { float* o = obs + 3 * off; o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2]; }
+            ++t;
+        }
+        if (in_reset && reset_left == 0) {
+            in_reset = false;
+            if (op == KUKA_OP_SETTLE) {
+                for (int j = 0; j < KK_NB; ++j) { snap[j] = e.q[j]; snap[KK_NB + j] = e.qd[j]; }
+                snap[24] = e.ee[0]; snap[25] = e.ee[1]; snap[26] = e.ee[2]; snap[27] = e.qb; snap[28] = e.qdb;
+                return;
+            }
+            reset_end(P, e);
+            if (obs) {  // getSRLState after reset (:278-279)
+                float* o = obs + 3 * (op == KUKA_OP_RESET ? (size_t)i : (size_t)t * N + (size_t)i);
+                o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2];
+            }
+            if (op == KUKA_OP_ROLLOUT) ++t;
+        }
+        if (!in_reset && (op != KUKA_OP_ROLLOUT || t >= T)) break;
+        // ---- next micro action ----
+        bool armed;
+        if (in_reset) {
+            if (op == KUKA_OP_SETTLE) { dx = dy = dz = 0.f; }
+            else reset_action(P, d17, genv, e.episode, N_RANDOM_ACTIONS_AT_INIT - reset_left, dx, dy, dz);
+            --reset_left;
+            armed = false;  // the button motor is only commanded from step2() (:347)
+        } else {
+            if (rep == 0) {
+                // ---- step(): action decoding + noise (:293-340) ----
+                const size_t off = (size_t)t * N + (size_t)i;
+                float nz;
+                if (noise) nz = __ldg(noise + off);
+                else {
+                    const uint4 r = philox4x32_10(P.seed, genv, e.total_steps, PHILOX_PURPOSE_NOISE);
+                    const double u1 = philox_u01(r.x, r.y), u2 = philox_u01(r.z, r.w);
+                    nz = (float)((P.is_discrete ? NOISE_STD : NOISE_STD_CONTINUOUS) * sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2));
+                }
+                dx = dy = dz = 0.f;
+                uint4 ra = make_uint4(0, 0, 0, 0);
+                if (!actions) ra = philox4x32_10(P.seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
+                if (P.is_discrete) {
+                    const int a = actions ? __ldg(reinterpret_cast<const int32_t*>(actions) + off) : (int)__umulhi(ra.x, 6u);
+                    if (a >= 0) {  // a < 0 is the reference's step(None): zero action (:295-299)
+                        const float dv = DELTA_V + nz;
+                        const int am = a % 6;
+                        dx = am == 0 ? -dv : am == 1 ? dv : 0.f;
+                        dy = am == 2 ? -dv : am == 3 ? dv : 0.f;
+                        dz = am == 4 ? -dv : am == 5 ? (P.force_down ? -dv : dv) : 0.f;
+                    }
+                } else {
+                    float a0, a1, a2;
+                    if (actions) {
+                        const float* ap = reinterpret_cast<const float*>(actions) + 3 * off;
+                        a0 = __ldg(ap); a1 = __ldg(ap + 1); a2 = __ldg(ap + 2);
+                    } else {
+                        a0 = (float)((double)ra.x * (2.0 / 4294967296.0) - 1.0);
+                        a1 = (float)((double)ra.y * (2.0 / 4294967296.0) - 1.0);
+                        a2 = (float)((double)ra.z * (2.0 / 4294967296.0) - 1.0);
+                    }
+                    const float dv = DELTA_V_CONTINUOUS + nz;
+                    dx = a0 * dv; dy = a1 * dv;
+                    dz = P.force_down ? -fabsf(a2 * dv) : a2 * dv;
+                }
+                e.total_steps += 1;
+            }
+            armed = true;
+        }
+        // ---- applyAction + stepSimulation ----
+        apply_ee_delta(P, e, dx, dy, dz);
+        saved_cb = new_cb; saved_ct = new_ct;
+        kuka_physics_step(P, e, k, ct, armed);
+        if (!in_reset) {
+            // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
+            if (e.terminated || e.counter > P.max_steps) { pending = true; rep = 0; }
+            else { e.counter += 1; if (++rep == P.action_repeat) { pending = true; rep = 0; } }
+        }
+    }
+    e.cbutton = saved_cb; e.ctable = saved_ct;
+    env_store(d, i, e);
+}
+
+// ---- host side -------------------------------------------------------------------------------
+bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P) {
+    const double* d = (const double*)blob;
+    if (!blob || bytes < KM_HEADER_SIZE * sizeof(double) || d[KM_H_MAGIC] != KM_MAGIC || d[KM_H_VERSION] != KM_VERSION) {
+        srl_set_error("kuka: bad model blob (magic/version)"); return false;
+    }
+    if ((size_t)d[KM_H_TOTAL] * sizeof(double) != bytes || (int)d[KM_H_NBODY] != KK_NB || (int)d[KM_H_NSPHERE] > KM_MAX_SPHERES) {
+        srl_set_error("kuka: bad model blob (size / body count / sphere count)"); return false;
+    }
+    memset(&P, 0, sizeof(P));
+    const double* sc = d + (int)d[KM_H_SCENE_OFF];
+    const double dt = s->cfg.timestep > 0.f ? (double)s->cfg.timestep : sc[KM_SC_TIMESTEP];
+    static const int parent[KK_NB] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 7, 10};
+    for (int i = 0; i < KK_NB; ++i) {
+        const double* r = d + (int)d[KM_H_BODY_OFF] + i * KM_BODY_STRIDE;
+        const double* c = d + (int)d[KM_H_CTRL_OFF] + i * KM_CTRL_STRIDE;
+        if ((int)r[KM_B_PARENT] != parent[i] || (int)r[KM_B_JTYPE] != 0) {
+            srl_set_error("kuka: the kernels are specialised for the 8-chain + two 2-link fingers revolute topology"); return false;
+        }
+        for (int a = 0; a < 3; ++a) { P.org[i][a] = (float)r[KM_B_ORIGIN + a]; P.axis[i][a] = (float)r[KM_B_AXIS + a]; P.com[i][a] = (float)r[KM_B_COM + a]; }
+        for (int a = 0; a < 9; ++a) P.rot[i][a] = (float)r[KM_B_ROT + a];
+        for (int a = 0; a < 6; ++a) P.Ic[i][a] = (float)r[KM_B_INERTIA + a];
+        P.mass[i] = (float)r[KM_B_MASS]; P.damping[i] = (float)r[KM_B_DAMPING];
+        P.lower[i] = (float)r[KM_B_LOWER]; P.upper[i] = (float)r[KM_B_UPPER];
+        P.kp_dt[i] = (float)(c[KM_C_KP] / dt); P.kd[i] = (float)c[KM_C_KD];
+        P.maxvel[i] = (float)c[KM_C_MAXVEL]; P.maximp[i] = (float)(c[KM_C_MAXFORCE] * dt);
+        P.tmode[i] = (int)c[KM_C_TARGET];
+        P.snap_q[i] = (float)r[KM_B_QINIT];
+    }
+    P.nsph = (int)d[KM_H_NSPHERE];
+    for (int k = 0; k < P.nsph; ++k) {
+        const double* sp = d + (int)d[KM_H_SPHERE_OFF] + k * KM_SPHERE_STRIDE;
+        P.sph_body[k] = (int)sp[KM_S_BODY]; P.sph_r[k] = (float)sp[KM_S_RADIUS];
+        for (int a = 0; a < 3; ++a) P.sph_c[k][a] = (float)sp[KM_S_CENTER + a];
+    }
+    for (int a = 0; a < 3; ++a) { P.base[a] = (float)sc[KM_SC_BASE_POS + a]; P.btn_base[a] = (float)sc[KM_SC_BUTTON_BASE + a]; P.ee_init[a] = (float)sc[KM_SC_EE_INIT + a]; }
+    P.gz = (float)sc[KM_SC_GRAVITY_Z]; P.dt = (float)dt; P.inv_dt = (float)(1.0 / dt);
+    P.iters = s->cfg.solver_iterations > 0 ? s->cfg.solver_iterations : (int)sc[KM_SC_SOLVER_ITERS];
+    P.table_z = (float)sc[KM_SC_TABLE_TOP_Z]; P.txmin = (float)sc[KM_SC_TABLE_XMIN]; P.txmax = (float)sc[KM_SC_TABLE_XMAX];
+    P.tymin = (float)sc[KM_SC_TABLE_YMIN]; P.tymax = (float)sc[KM_SC_TABLE_YMAX];
+    P.glider_z = (float)sc[KM_SC_GLIDER_Z]; P.gl_lo = (float)sc[KM_SC_GLIDER_LOWER]; P.gl_hi = (float)sc[KM_SC_GLIDER_UPPER];
+    P.btn_minv = (float)(1.0 / sc[KM_SC_BUTTON_MASS]);
+    P.disc_r = (float)sc[KM_SC_DISC_RADIUS]; P.disc_z0 = (float)sc[KM_SC_DISC_Z0]; P.disc_z1 = (float)sc[KM_SC_DISC_Z1];
+    P.stack_r = (float)sc[KM_SC_STACK_RADIUS]; P.stack_top = (float)sc[KM_SC_STACK_TOP];
+    P.cdist = (float)sc[KM_SC_CONTACT_DIST]; P.mu = (float)sc[KM_SC_FRICTION]; P.erp = (float)sc[KM_SC_ERP];
+    P.kl = (float)sc[KM_SC_LIN_DAMPING]; P.ka = (float)sc[KM_SC_ANG_DAMPING];
+    const double* box = sc + (s->cfg.random_target ? KM_SC_BOX_LARGE : KM_SC_BOX_SMALL);  // small_constraints = not random_target (:239)
+    for (int a = 0; a < 6; ++a) P.box[a] = (float)box[a];
+    for (int a = 0; a < 4; ++a) P.ikq[a] = (float)sc[KM_SC_IK_QUAT + a];
+    P.ik_damp = sc[KM_SC_IK_DAMPING];
+    P.ee_body = (int)sc[KM_SC_EE_BODY]; P.grip_body = (int)sc[KM_SC_GRIPPER_BODY];
+    if (P.ee_body != 6 || P.grip_body != 8) { srl_set_error("kuka: kernels assume IK link 6 and gripper link 8 (kuka.py:31-32)"); return false; }
+    P.target_h = (float)sc[KM_SC_TARGET_HEIGHT]; P.rand_x = (float)sc[KM_SC_RAND_X]; P.rand_y = (float)sc[KM_SC_RAND_Y];
+    P.btn_idle_imp = (float)sc[KM_SC_BTN_IDLE_IMPULSE]; P.btn_kp_dt = (float)(sc[KM_SC_BTN_KP] / dt); P.btn_kd = (float)sc[KM_SC_BTN_KD];
+    P.btn_target = (float)sc[KM_SC_BTN_TARGET]; P.btn_maximp = (float)(sc[KM_SC_BTN_MAXFORCE] * dt);
+    P.lim_maximp = (float)sc[KM_SC_LIMIT_MAX_IMPULSE]; P.lim_eps = (float)sc[KM_SC_LIMIT_EPS];
+    P.max_contacts = (int)sc[KM_SC_MAX_CONTACTS];
+    if (P.max_contacts > KK_MAXC) P.max_contacts = KK_MAXC;
+    P.is_discrete = s->cfg.is_discrete; P.random_target = s->cfg.random_target; P.force_down = s->cfg.force_down;
+    P.shape_reward = s->cfg.shape_reward; P.action_repeat = s->cfg.action_repeat; P.max_steps = s->max_steps;
+    P.auto_reset = s->auto_reset; P.max_distance = s->cfg.max_distance;
+    P.seed = s->seed; P.env_offset = s->cfg.global_env_offset;
+    return true;
+}
+
+void grid_for(const srl_sim* s, const KukaDev* d, int& grid, int& block) {
+    const int warps = (s->n + d->epw - 1) / d->epw;
+    block = 128;
+    grid = (warps * 32 + block - 1) / block;
+}
+
+}  // namespace
+
+int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
+    if (s->kind != SRL_ENV_KUKA_BUTTON && s->kind != SRL_ENV_KUKA_RAND_BUTTON) {
+        srl_set_error("kuka: env kind %d is not implemented yet", s->kind); return 1;
+    }
+    KukaDev* d = new KukaDev();
+    memset(d, 0, sizeof(*d));
+    s->kuka = d;
+    if (!fill_params(blob, bytes, s, d->P)) return 1;
+    const size_t N = (size_t)s->n;
+    float4** f4[] = {&d->q[0], &d->q[1], &d->q[2], &d->qd[0], &d->qd[1], &d->qd[2], &d->misc0, &d->misc1, &d->tgt, &d->grip, &d->eepos};
+    for (float4** p : f4) { SRL_CUDA_OK(cudaMalloc(p, N * sizeof(float4))); SRL_CUDA_OK(cudaMemset(*p, 0, N * sizeof(float4))); }
+    SRL_CUDA_OK(cudaMalloc(&d->cnt, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(d->cnt, 0, N * sizeof(int4)));
+    SRL_CUDA_OK(cudaMalloc(&d->cnt2, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(d->cnt2, 0, N * sizeof(int4)));
+    // live lanes per warp: spread a small batch over every warp scheduler (4 per SM), ONE warp each -- the PGS
+    // sweep of a single warp already fills its scheduler's issue slots, a second resident warp only adds latency
+    // (measured on B200, 4096 envs: 4 lanes/warp 11.4 ms per 128 steps, 7 lanes/warp 9.0 ms, 32 lanes/warp 8.9 ms)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    int epw = s->cfg.envs_per_warp;
+    if (epw <= 0) { epw = (int)((N + (size_t)sms * 4 - 1) / ((size_t)sms * 4)); }
+    if (epw < 1) epw = 1;
+    if (epw > 32) epw = 32;
+    d->epw = epw;
+    // the 500 settle steps of reset(), once
+    float* snap = nullptr;
+    SRL_CUDA_OK(cudaMalloc(&snap, 32 * sizeof(float)));
+    { const int save_epw = d->epw; d->epw = 1;
+      kuka_kernel<<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
+      d->epw = save_epw; }
+    SRL_CUDA_OK(cudaGetLastError());
+    float h[32];
+    SRL_CUDA_OK(cudaMemcpy(h, snap, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(snap);
+    for (int i = 0; i < KK_NB; ++i) { d->P.snap_q[i] = h[i]; d->P.snap_qd[i] = h[KK_NB + i]; }
+    d->P.snap_ee[0] = h[24]; d->P.snap_ee[1] = h[25]; d->P.snap_ee[2] = h[26]; d->P.snap_qb = h[27]; d->P.snap_qdb = h[28];
+    s->launches += 1;
+    return 0;
+}
+
+void kuka_free(srl_sim* s) {
+    KukaDev* d = s->kuka;
+    if (!d) return;
+    for (int k = 0; k < 3; ++k) { cudaFree(d->q[k]); cudaFree(d->qd[k]); }
+    cudaFree(d->misc0); cudaFree(d->misc1); cudaFree(d->tgt); cudaFree(d->grip); cudaFree(d->eepos); cudaFree(d->cnt); cudaFree(d->cnt2);
+    delete d;
+    s->kuka = nullptr;
+}
+
+int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st) {
+    KukaDev* d = s->kuka;
+    int grid, block; grid_for(s, d, grid, block);
+    kuka_kernel<<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    SRL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
+                        float* ep_ret, int32_t* ep_len, cudaStream_t st) {
+    KukaDev* d = s->kuka;
+    int grid, block; grid_for(s, d, grid, block);
+    kuka_kernel<<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
+    SRL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
+    KukaDev* d = s->kuka;
+    const size_t N = (size_t)s->n;
+    SRL_CUDA_OK(cudaDeviceSynchronize());
+    auto need = [&](size_t width, size_t elem) { if (bytes != N * width * elem) { srl_set_error("get_state: size mismatch"); return false; } return true; };
+    std::vector<float4> a(N), b(N), c(N);
+    std::vector<int4> ia(N);
+    double* D = (double*)dst; int32_t* I = (int32_t*)dst;
+    auto pull = [&](std::vector<float4>& v, const float4* src) { return cudaMemcpy(v.data(), src, N * sizeof(float4), cudaMemcpyDeviceToHost); };
+    switch (field) {
+    case SRL_F_ROBOT_POS: case SRL_F_TARGET_POS: case SRL_F_EE_POS: {
+        if (!need(3, 8)) return 1;
+        SRL_CUDA_OK(pull(a, field == SRL_F_ROBOT_POS ? d->grip : field == SRL_F_TARGET_POS ? d->tgt : d->eepos));
+        for (size_t i = 0; i < N; ++i) { D[3 * i] = a[i].x; D[3 * i + 1] = a[i].y; D[3 * i + 2] = a[i].z; }
+        return 0;
+    }
+    case SRL_F_JOINT_POS: case SRL_F_JOINT_VEL: {
+        if (!need(KK_NB, 8)) return 1;
+        float4* const* src = field == SRL_F_JOINT_POS ? d->q : d->qd;
+        SRL_CUDA_OK(pull(a, src[0])); SRL_CUDA_OK(pull(b, src[1])); SRL_CUDA_OK(pull(c, src[2]));
+        for (size_t i = 0; i < N; ++i) {
+            const float4 v[3] = {a[i], b[i], c[i]};
+            for (int k = 0; k < 3; ++k) { D[12 * i + 4 * k] = v[k].x; D[12 * i + 4 * k + 1] = v[k].y; D[12 * i + 4 * k + 2] = v[k].z; D[12 * i + 4 * k + 3] = v[k].w; }
+        }
+        return 0;
+    }
+    case SRL_F_EE_CMD:
+        if (!need(3, 8)) return 1;
+        SRL_CUDA_OK(pull(a, d->misc0));
+        for (size_t i = 0; i < N; ++i) { D[3 * i] = a[i].x; D[3 * i + 1] = a[i].y; D[3 * i + 2] = a[i].z; }
+        return 0;
+    case SRL_F_BUTTON_GLIDER:
+        if (!need(2, 8)) return 1;
+        SRL_CUDA_OK(pull(a, d->misc0)); SRL_CUDA_OK(pull(b, d->misc1));
+        for (size_t i = 0; i < N; ++i) { D[2 * i] = a[i].w; D[2 * i + 1] = b[i].x; }
+        return 0;
+    case SRL_F_BUTTON_BASE:
+        if (!need(3, 8)) return 1;
+        SRL_CUDA_OK(pull(b, d->misc1));
+        for (size_t i = 0; i < N; ++i) { D[3 * i] = b[i].y; D[3 * i + 1] = b[i].z; D[3 * i + 2] = d->P.btn_base[2]; }
+        return 0;
+    case SRL_F_STEP_COUNTER:
+        if (!need(1, 4)) return 1;
+        SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) I[i] = ia[i].x;
+        return 0;
+    case SRL_F_COUNTERS: {
+        if (!need(4, 4)) return 1;
+        std::vector<int4> ib(N);
+        SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        SRL_CUDA_OK(cudaMemcpy(ib.data(), d->cnt2, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) { I[4 * i] = ia[i].y; I[4 * i + 1] = ia[i].z; I[4 * i + 2] = ia[i].w & 1; I[4 * i + 3] = ib[i].x; }
+        return 0;
+    }
+    case SRL_F_EPISODE_STATS: {
+        if (!need(2, 8)) return 1;
+        SRL_CUDA_OK(pull(b, d->misc1));
+        SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt2, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) { D[2 * i] = b[i].w; D[2 * i + 1] = (double)ia[i].z; }
+        return 0;
+    }
+    default:
+        srl_set_error("get_state: unknown field %d", field);
+        return 1;
+    }
+}
+
+int kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes) {
+    KukaDev* d = s->kuka;
+    const size_t N = (size_t)s->n;
+    SRL_CUDA_OK(cudaDeviceSynchronize());
+    auto need = [&](size_t width, size_t elem) { if (bytes != N * width * elem) { srl_set_error("set_state: size mismatch"); return false; } return true; };
+    const double* D = (const double*)src; const int32_t* I = (const int32_t*)src;
+    std::vector<float4> a(N), b(N), c(N);
+    auto pull = [&](std::vector<float4>& v, const float4* p) { return cudaMemcpy(v.data(), p, N * sizeof(float4), cudaMemcpyDeviceToHost); };
+    auto push = [&](const std::vector<float4>& v, float4* p) { return cudaMemcpy(p, v.data(), N * sizeof(float4), cudaMemcpyHostToDevice); };
+    switch (field) {
+    case SRL_F_JOINT_POS: case SRL_F_JOINT_VEL: {
+        if (!need(KK_NB, 8)) return 1;
+        float4* const* dst = field == SRL_F_JOINT_POS ? d->q : d->qd;
+        for (size_t i = 0; i < N; ++i) {
+            a[i] = make_float4((float)D[12 * i], (float)D[12 * i + 1], (float)D[12 * i + 2], (float)D[12 * i + 3]);
+            b[i] = make_float4((float)D[12 * i + 4], (float)D[12 * i + 5], (float)D[12 * i + 6], (float)D[12 * i + 7]);
+            c[i] = make_float4((float)D[12 * i + 8], (float)D[12 * i + 9], (float)D[12 * i + 10], (float)D[12 * i + 11]);
+        }
+        SRL_CUDA_OK(push(a, dst[0])); SRL_CUDA_OK(push(b, dst[1])); SRL_CUDA_OK(push(c, dst[2]));
+        return 0;
+    }
+    case SRL_F_EE_CMD:
+        if (!need(3, 8)) return 1;
+        SRL_CUDA_OK(pull(a, d->misc0));
+        for (size_t i = 0; i < N; ++i) { a[i].x = (float)D[3 * i]; a[i].y = (float)D[3 * i + 1]; a[i].z = (float)D[3 * i + 2]; }
+        SRL_CUDA_OK(push(a, d->misc0));
+        return 0;
+    case SRL_F_TARGET_POS:
+        if (!need(3, 8)) return 1;
+        for (size_t i = 0; i < N; ++i) a[i] = make_float4((float)D[3 * i], (float)D[3 * i + 1], (float)D[3 * i + 2], 0.f);
+        SRL_CUDA_OK(push(a, d->tgt));
+        return 0;
+    case SRL_F_BUTTON_GLIDER:
+        if (!need(2, 8)) return 1;
+        SRL_CUDA_OK(pull(a, d->misc0)); SRL_CUDA_OK(pull(b, d->misc1));
+        for (size_t i = 0; i < N; ++i) { a[i].w = (float)D[2 * i]; b[i].x = (float)D[2 * i + 1]; }
+        SRL_CUDA_OK(push(a, d->misc0)); SRL_CUDA_OK(push(b, d->misc1));
+        return 0;
+    case SRL_F_BUTTON_BASE:
+        if (!need(3, 8)) return 1;
+        SRL_CUDA_OK(pull(b, d->misc1));
+        for (size_t i = 0; i < N; ++i) { b[i].y = (float)D[3 * i]; b[i].z = (float)D[3 * i + 1]; }
+        SRL_CUDA_OK(push(b, d->misc1));
+        return 0;
+    case SRL_F_STEP_COUNTER: case SRL_F_COUNTERS: {
+        if (!need(field == SRL_F_STEP_COUNTER ? 1 : 4, 4)) return 1;
+        std::vector<int4> ia(N);
+        SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) {
+            if (field == SRL_F_STEP_COUNTER) ia[i].x = I[i];
+            else { ia[i].y = I[4 * i]; ia[i].z = I[4 * i + 1]; ia[i].w = (ia[i].w & ~1) | (I[4 * i + 2] & 1); }
+        }
+        SRL_CUDA_OK(cudaMemcpy(d->cnt, ia.data(), N * sizeof(int4), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    default:
+        srl_set_error("set_state: field %d not settable", field);
+        return 1;
+    }
+}

@@ -1,0 +1,268 @@
+"""
+CPU tests for the Kuka path (no GPU): URDF loader, the oracle's building blocks against an independent
+Lagrangian numpy reference (tests/kuka_numpy_ref.py), env-level semantics against the reference's documented
+behaviour (kuka_button_gym_env.py:293-463), and the committed oracle golden trajectories.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import kuka_numpy_ref as ref
+from conftest import GOLDEN, ORACLE_LIB
+from srl_sim import _abi
+from srl_sim.model import KM, KukaScene, load_kuka_scene
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return load_kuka_scene()
+
+
+@pytest.fixture(scope="module")
+def hooks(oracle_lib):
+    lib = ctypes.CDLL(ORACLE_LIB)
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---- loader ----------------------------------------------------------------------------------------
+def test_loader_topology_and_recalled_asset_values(scene):
+    assert [b.ref_joint for b in scene.bodies] == [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13]  # movable PyBullet joints
+    assert [b.parent for b in scene.bodies] == KukaScene.EXPECTED_PARENTS
+    assert [b.mass for b in scene.bodies[:7]] == [4, 4, 3, 2.7, 1.7, 1.8, 0.3]
+    assert scene.bodies[8].mass == pytest.approx(0.4) and scene.bodies[10].mass == pytest.approx(0.4)  # finger + merged finger base
+    # zero-configuration link heights of the SDF
+    P, _ = scene.forward_kinematics(np.zeros(12))
+    base = scene.scene[KM["KM_SC_BASE_POS"]:KM["KM_SC_BASE_POS"] + 3]
+    assert np.allclose([p[2] - base[2] for p in P[:8]], [0.1575, 0.36, 0.5645, 0.78, 0.9645, 1.18, 1.261, 1.305], atol=1e-9)
+    sc = scene.scene
+    assert sc[KM["KM_SC_TABLE_TOP_Z"]] == pytest.approx(-0.195)           # table at z=-0.82, top slab 0.6 + 0.025
+    assert sc[KM["KM_SC_BUTTON_BASE"] + 2] == pytest.approx(-0.195)       # button base rests on the table top
+    assert (sc[KM["KM_SC_GLIDER_LOWER"]], sc[KM["KM_SC_GLIDER_UPPER"]]) == (0.0, 0.01)  # urdf/simple_button.urdf:15
+    assert sc[KM["KM_SC_DISC_RADIUS"]] == 0.09 and sc[KM["KM_SC_STACK_RADIUS"]] == 0.1  # mesh extents
+    # IK orientation target: pybullet.getQuaternionFromEuler([0, -pi, 0])
+    assert np.allclose(sc[KM["KM_SC_IK_QUAT"]:KM["KM_SC_IK_QUAT"] + 4], [0, -1, 0, 0], atol=1e-15)
+    assert scene.blob[KM["KM_H_TOTAL"]] == scene.blob.size
+
+
+def test_blob_layout_matches_header():
+    hdr = open(os.path.join(os.path.dirname(_abi.CUDA_LIBRARY_PATH), "kuka_model.h")).read()
+    for name in ("KM_BODY_STRIDE", "KM_SCENE_SIZE", "KM_SC_LIMIT_EPS", "KM_B_REFJOINT"):
+        assert ("#define %s " % name) in hdr and name in KM
+    assert KM["KM_B_REFJOINT"] < KM["KM_BODY_STRIDE"] and KM["KM_SC_LIMIT_EPS"] < KM["KM_SCENE_SIZE"]
+
+
+# ---- oracle building blocks vs independent numpy mechanics -------------------------------------------
+def test_oracle_fk_minv_fd_against_lagrangian_reference(scene, hooks):
+    blob = scene.blob
+    nb = ctypes.c_size_t(blob.nbytes)
+    rs = np.random.RandomState(0)
+    for _ in range(3):
+        q = scene.q_init + rs.uniform(-0.5, 0.5, 12)
+        qd = rs.uniform(-1, 1, 12)
+        p = np.zeros((12, 3)); R = np.zeros((12, 9)); com = np.zeros((12, 3))
+        assert hooks.oracle_kuka_fk(_p(blob), nb, _p(q), _p(p), _p(R), _p(com)) == 0
+        Pn, Rn = scene.forward_kinematics(q)
+        assert max(np.abs(p[i] - Pn[i]).max() for i in range(12)) < 1e-14
+        assert max(np.abs(R[i].reshape(3, 3) - Rn[i]).max() for i in range(12)) < 1e-14
+        Minv = np.zeros((12, 12))
+        assert hooks.oracle_kuka_minv(_p(blob), nb, _p(q), _p(Minv)) == 0
+        M = ref.mass_matrix(scene, q)
+        assert np.abs(Minv - Minv.T).max() < 1e-10
+        assert np.abs(M @ Minv - np.eye(12)).max() < 1e-9          # ABA impulse responses invert the Jacobian-built M
+        assert np.all(np.linalg.eigvalsh(M) > 0)
+        qdd = np.zeros(12)
+        assert hooks.oracle_kuka_fd(_p(blob), nb, _p(q), _p(qd), 0, _p(qdd)) == 0
+        qn = ref.forward_dynamics(scene, q, qd)                     # Lagrangian: M qdd = -c(q, qd) - dV/dq
+        assert np.abs(qdd - qn).max() < 5e-6 * max(1.0, np.abs(qn).max())
+
+
+def test_oracle_gravity_only_free_fall_of_the_chain(scene, hooks):
+    """At rest, qdd = -M^-1 G; damping terms vanish at zero velocity."""
+    blob = scene.blob
+    q = scene.q_init.copy(); qd = np.zeros(12); a = np.zeros(12); b = np.zeros(12)
+    hooks.oracle_kuka_fd(_p(blob), ctypes.c_size_t(blob.nbytes), _p(q), _p(qd), 1, _p(a))
+    hooks.oracle_kuka_fd(_p(blob), ctypes.c_size_t(blob.nbytes), _p(q), _p(qd), 0, _p(b))
+    assert np.array_equal(a, b)
+    assert np.allclose(a, -np.linalg.solve(ref.mass_matrix(scene, q), ref.gravity_torque(scene, q)), atol=1e-6)
+
+
+def test_oracle_ik_is_one_dls_iteration(scene, hooks):
+    blob = scene.blob
+    q = scene.q_init.copy()
+    P, R = scene.forward_kinematics(q)
+    target = P[6] + np.array([0.01, -0.02, 0.015])
+    q_ik = np.zeros(12)
+    assert hooks.oracle_kuka_ik(_p(blob), ctypes.c_size_t(blob.nbytes), _p(q), _p(target), _p(q_ik)) == 0
+    # numpy DLS with the same error definition
+    axes = [R[i] @ scene.bodies[i].axis for i in range(7)]
+    J = np.zeros((6, 7))
+    for j in range(7):
+        J[:3, j] = np.cross(axes[j], P[6] - P[j]); J[3:, j] = axes[j]
+    Rt = np.diag([-1.0, 1.0, -1.0])                                  # euler (0, -pi, 0)
+    Rerr = Rt @ R[6].T
+    ang = np.arccos(np.clip((np.trace(Rerr) - 1) / 2, -1, 1))
+    axis = np.array([Rerr[2, 1] - Rerr[1, 2], Rerr[0, 2] - Rerr[2, 0], Rerr[1, 0] - Rerr[0, 1]])
+    axis = axis / np.linalg.norm(axis)
+    e = np.concatenate([target - P[6], ang * axis])
+    dth = np.linalg.solve(J.T @ J + 1e-5 * np.eye(7), J.T @ e)
+    assert np.allclose(q_ik[:7] - q[:7], dth, atol=1e-9)
+    assert np.array_equal(q_ik[7:], q[7:])
+    # the step reduces the pose error
+    P2, _ = scene.forward_kinematics(q_ik)
+    assert np.linalg.norm(target - P2[6]) < 0.2 * np.linalg.norm(target - P[6])
+
+
+# ---- env-level behaviour ---------------------------------------------------------------------------------
+def _sim(backend, n=2, kind="KukaButtonGymEnv-v0", **cfg):
+    return backend.make_sim(kind, n, model_blob=load_kuka_scene().blob, **cfg)
+
+
+def _step(sim, a, noise=None):
+    n = sim.num_envs
+    obs = np.zeros((n, 3), np.float32); rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8)
+    sim.step(np.asarray(a), None if noise is None else np.asarray(noise, np.float32), obs, rew, done)
+    return obs, rew, done
+
+
+def test_reset_settles_on_the_commanded_pose_and_freezes_the_target(oracle_backend):
+    sim = _sim(oracle_backend, seed=1)
+    obs = np.zeros((2, 3), np.float32)
+    draws = np.zeros((2, 17)); draws[:, 0] = 0.5  # button at the default place, five zero actions
+    sim.reset(reset_draws=draws, obs_out=obs)
+    ee, cmd = sim.get_state(_abi.F_EE_POS), sim.get_state(_abi.F_EE_CMD)
+    assert np.allclose(cmd, [0.537, 0.0, 0.5])                       # kuka.py:73
+    assert np.abs(ee - cmd).max() < 3e-3                              # 505 steps of IK + motors reach the command
+    tgt = sim.get_state(_abi.F_TARGET_POS)
+    assert np.allclose(tgt, [0.5, 0.0, -0.195 + 0.005 + 0.28])        # button link origin + BUTTON_DISTANCE_HEIGHT
+    assert np.allclose(obs, sim.get_state(_abi.F_ROBOT_POS) - tgt, atol=1e-6)
+    g = sim.get_state(_abi.F_BUTTON_GLIDER)
+    assert np.abs(g).max() < 1e-9                                     # idle joint motor holds the button during reset
+    assert np.abs(sim.get_state(_abi.F_JOINT_VEL)).max() < 5e-3       # arm at rest
+
+
+def test_action_decoding_noise_and_clip(oracle_backend):
+    sim = _sim(oracle_backend, n=6, seed=1)
+    sim.reset(reset_draws=np.tile(np.r_[0.5, 0.0, np.zeros(15)], (6, 1)))
+    c0 = sim.get_state(_abi.F_EE_CMD)
+    _step(sim, np.arange(6, dtype=np.int32), noise=np.full(6, 0.002))
+    d = sim.get_state(_abi.F_EE_CMD) - c0
+    dv = 0.03 + np.float32(0.002)
+    # dx = [-dv, dv, 0, 0, 0, 0], dy = [0, 0, -dv, dv, 0, 0], dz = [0, 0, 0, 0, -dv, -dv] (force_down), clipped to the box
+    assert np.allclose(d[0], [max(-dv, 0.50 - 0.537), 0, 0]) and np.allclose(d[1], [dv, 0, 0])
+    assert np.allclose(d[2], [0, -dv, 0]) and np.allclose(d[3], [0, dv, 0])
+    assert np.allclose(d[4], [0, 0, -dv]) and np.allclose(d[5], [0, 0, -dv])
+    # step(None): negative action -> zero displacement
+    c1 = sim.get_state(_abi.F_EE_CMD)
+    _step(sim, np.full(6, -1, np.int32), noise=np.full(6, 0.5))
+    assert np.array_equal(sim.get_state(_abi.F_EE_CMD), c1)
+    # the button motor is armed by step2(): it drives the glider onto its upper limit and the limit holds it
+    for _ in range(5):
+        _step(sim, np.full(6, -1, np.int32))
+    g = sim.get_state(_abi.F_BUTTON_GLIDER)
+    assert np.allclose(g[:, 0], 0.01, atol=1e-6) and np.abs(g[:, 1]).max() < 1e-3
+
+
+def test_time_limit_and_autoreset(oracle_backend):
+    sim = _sim(oracle_backend, n=3, seed=2, max_steps=20)
+    sim.reset()
+    T = 50
+    done = np.zeros((T, 3), np.uint8); ep_len = np.zeros((T, 3), np.int32); obs = np.zeros((T, 3, 3), np.float32)
+    sim.rollout(T, np.full((T, 3), -1, np.int32), None, obs, None, done, None, ep_len)
+    # done <=> _env_step_counter > max_steps: the 21st and 42nd steps
+    assert np.array_equal(np.where(done[:, 0])[0], [20, 41]) and (ep_len[20] == 21).all()
+    assert (sim.get_state(_abi.F_STEP_COUNTER)[:, 0] == T - 42).all()
+    assert (sim.get_state(_abi.F_COUNTERS)[:, 3] == 3).all()          # three episodes started
+    # no_auto_reset: the env stays terminated and keeps returning the terminal observation stream
+    sim2 = _sim(oracle_backend, n=1, seed=2, max_steps=5, no_auto_reset=True)
+    sim2.reset()
+    d = [int(_step(sim2, np.array([-1], np.int32))[2][0]) for _ in range(9)]
+    assert d == [0, 0, 0, 0, 0, 1, 1, 1, 1]
+
+
+def test_table_contact_terminates_with_negative_reward(oracle_backend):
+    sim = _sim(oracle_backend, n=1, seed=3)
+    sim.reset(reset_draws=np.r_[0.5, 0.0, np.zeros(15)][None])
+    # drive the arm down next to the button (x = 0.65 is outside the 0.1 m stack): the fingertips reach the table
+    rews, dones = [], []
+    a = np.array([1], np.int32)
+    for t in range(1000):
+        _, r, d = _step(sim, a if t < 10 else np.array([4], np.int32), noise=np.zeros(1))
+        rews.append(float(r[0])); dones.append(int(d[0]))
+        if d[0]:
+            break
+    assert dones[-1] == 1 and rews[-1] == -1.0 and set(rews[:-1]) <= {0.0}
+    assert 100 < len(rews) < 1000                                      # ended by the table manifold, not the step limit
+
+
+def test_button_contact_gives_reward_and_terminates_after_five(oracle_backend):
+    sim = _sim(oracle_backend, n=1, seed=3, no_auto_reset=True)
+    sim.reset(reset_draws=np.r_[0.5, 0.0, np.zeros(15)][None])
+    rews = []
+    for t in range(1000):
+        a = 0 if t < 2 else 4                                         # nudge over the button, then descend
+        _, r, d = _step(sim, np.array([a], np.int32), noise=np.zeros(1))
+        rews.append(float(r[0]))
+        if d[0]:
+            break
+    assert rews[-5:] == [1.0] * 5 and set(rews[:-5]) == {0.0}          # N_CONTACTS_BEFORE_TERMINATION = 5
+    c = sim.get_state(_abi.F_COUNTERS)[0]
+    assert c[0] == 5 and c[2] == 1
+
+
+def test_oracle_sharding_and_determinism(oracle_backend):
+    T = 120
+    def run(n, off):
+        sim = _sim(oracle_backend, n=n, seed=7, random_target=True, global_env_offset=off, kind="KukaRandButtonGymEnv-v0")
+        sim.reset()
+        obs = np.zeros((T, n, 3), np.float32); rew = np.zeros((T, n), np.float32)
+        sim.rollout(T, None, None, obs, rew, None)                     # in-stream actions and noise
+        return obs, rew
+    whole, a, b = run(5, 0), run(3, 0), run(2, 3)
+    assert np.array_equal(whole[0], np.concatenate([a[0], b[0]], axis=1))
+    assert np.array_equal(whole[1], np.concatenate([a[1], b[1]], axis=1))
+    assert np.array_equal(run(5, 0)[0], whole[0])
+
+
+def test_oracle_reproduces_committed_golden(oracle_backend):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_kuka_golden", os.path.join(GOLDEN, "gen_kuka_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    g = np.load(os.path.join(GOLDEN, "kuka_oracle_golden.npz"))
+    blob = load_kuka_scene().blob
+    for tag, (env_id, n, T, cfg) in gen.CASES.items():
+        acts, noise = gen.inputs(tag, n, T, cfg)
+        res = gen.run(oracle_backend, env_id, n, T, cfg, acts, noise, blob)
+        for k, v in res.items():
+            # same compiler, same flags: float64 state agrees to the last few bits
+            assert np.allclose(v, g["%s/%s" % (tag, k)], rtol=0, atol=1e-9), (tag, k)
+
+
+def test_single_env_classes_on_oracle(use_oracle_backend):
+    from environments.registry import registered_env
+    env = registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth")
+    assert env.action_space.n == 6 and env.observation_space.shape == (3,) and env.getGroundTruthDim() == 3
+    env.seed(5)
+    o = env.reset()
+    assert o.shape == (3,) and np.allclose(o, np.array(env.getArmPos()) - env.getTargetPos())
+    o2, r, d, info = env.step(4)
+    assert isinstance(r, int) and r == 0 and d is False and info == {}
+    o3, _, _, _ = env.step(None)
+    assert o3.shape == (3,)
+    j = registered_env["KukaButtonGymEnv-v0"][0](srl_model="joints_position")
+    j.seed(5); s = j.reset()
+    assert s.shape == (17,) and np.allclose(s[3:], j._kuka.joint_positions)
+    c = registered_env["KukaRandButtonGymEnv-v0"][0](srl_model="ground_truth", is_discrete=False, random_target=True, shape_reward=True)
+    c.seed(1); c.reset()
+    assert c.action_space.shape == (3,) and abs(c.getTargetPos()[0] - 0.5) <= 0.15 and abs(c.getTargetPos()[1]) <= 0.3
+    _, r, _, _ = c.step(c.action_space.sample())
+    assert isinstance(r, float) and r < 0
+    with pytest.raises(NotImplementedError):
+        registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth", action_joints=True)
+    with pytest.raises(NotImplementedError):
+        registered_env["KukaButtonGymEnv-v0"][0]().reset()             # default raw_pixels: no rasteriser

@@ -1,0 +1,220 @@
+"""
+GPU parity tests, Kuka button-push family: the fp32 sm_100a kernel, called through the C-ABI, against the
+float64 CPU oracle on the same (seed, action, noise) sequences.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8(d)): gripper / end-effector position <= 1e-3 m,
+joint positions <= 1e-3 rad, joint velocities <= 1e-2 rad/s over 1000 steps; reward and done flags bit-exact.
+PARITY UNPINNED at the PyBullet boundary (see oracle/oracle_kuka.cpp header).
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from srl_sim import _abi
+from srl_sim.model import load_kuka_scene
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, Q_TOL, QD_TOL = 1e-3, 1e-3, 1e-2
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("gen_kuka_golden", os.path.join(GOLDEN, "gen_kuka_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    return gen
+
+
+def _run(be, kind, n, T, acts, noise, chunk=None, stepwise=False, **cfg):
+    sim = be.make_sim(kind, n, model_blob=load_kuka_scene().blob, **cfg)
+    obs0 = be.zeros((n, 3), np.float32)
+    sim.reset(obs_out=obs0, stream=be.stream())
+    obs = be.zeros((T, n, 3), np.float32); rew = be.zeros((T, n), np.float32); done = be.zeros((T, n), np.uint8)
+    ep_ret = be.zeros((T, n), np.float32); ep_len = be.zeros((T, n), np.int32)
+    a = None if acts is None else be.from_host(acts)
+    nz = None if noise is None else be.from_host(noise)
+    snaps = []
+    chunk = 1 if stepwise else (chunk or T)
+    for s in range(0, T, chunk):
+        e = min(T, s + chunk)
+        if stepwise:
+            sim.step(a[s], None if nz is None else nz[s], obs[s], rew[s], done[s], ep_ret[s], ep_len[s], stream=be.stream())
+        else:
+            sim.rollout(e - s, None if a is None else a[s:e], None if nz is None else nz[s:e], obs[s:e], rew[s:e],
+                        done[s:e], ep_ret[s:e], ep_len[s:e], stream=be.stream())
+        if chunk != T and not stepwise:
+            snaps.append((sim.get_state(_abi.F_JOINT_POS), sim.get_state(_abi.F_JOINT_VEL), sim.get_state(_abi.F_EE_POS)))
+    out = dict(obs0=be.to_host(obs0).copy(), obs=be.to_host(obs).copy(), rew=be.to_host(rew).copy(),
+               done=be.to_host(done).copy(), ep_ret=be.to_host(ep_ret).copy(), ep_len=be.to_host(ep_len).copy(),
+               q=sim.get_state(_abi.F_JOINT_POS), qd=sim.get_state(_abi.F_JOINT_VEL), ee=sim.get_state(_abi.F_EE_POS),
+               grip=sim.get_state(_abi.F_ROBOT_POS), target=sim.get_state(_abi.F_TARGET_POS),
+               counters=sim.get_state(_abi.F_COUNTERS), counter=sim.get_state(_abi.F_STEP_COUNTER),
+               glider=sim.get_state(_abi.F_BUTTON_GLIDER), snaps=snaps, launches=sim.launch_count)
+    sim.close()
+    return out
+
+
+def _assert_parity(c, o, flags_exact=True):
+    assert np.abs(c["obs0"] - o["obs0"]).max() < POS_TOL
+    if flags_exact:
+        assert np.array_equal(c["done"], o["done"]), "done flags differ"
+        assert np.array_equal(c["rew"] == 1, o["rew"] == 1) and np.array_equal(c["rew"] == -1, o["rew"] == -1)
+    d = o["done"].astype(bool)
+    assert np.array_equal(c["ep_len"][d], o["ep_len"][d])
+    assert np.abs(c["obs"] - o["obs"]).max() < POS_TOL                 # gripper position relative to the target
+    assert np.abs(c["grip"] - o["grip"]).max() < POS_TOL and np.abs(c["ee"] - o["ee"]).max() < POS_TOL
+    assert np.abs(c["q"] - o["q"]).max() < Q_TOL and np.abs(c["qd"] - o["qd"]).max() < QD_TOL
+    assert np.array_equal(c["counters"], o["counters"]) and np.array_equal(c["counter"], o["counter"])
+    for (qc, qdc, eec), (qo, qdo, eeo) in zip(c["snaps"], o["snaps"]):
+        assert np.abs(qc - qo).max() < Q_TOL and np.abs(qdc - qdo).max() < QD_TOL and np.abs(eec - eeo).max() < POS_TOL
+
+
+def test_config2_discrete_1000_steps_vs_oracle(cuda_backend, oracle_backend):
+    """SURVEY 8(d) config 2 on envs 0..63: 1000 random discrete actions + N(0, 0.01) step noise."""
+    n, T = 64, 1000
+    acts = np.random.default_rng(0).integers(0, 6, (T, n), dtype=np.int32)
+    noise = np.random.default_rng(1).normal(0, 0.01, (T, n)).astype(np.float32)
+    cfg = dict(seed=0, is_discrete=True, random_target=False, force_down=True, action_repeat=1, max_distance=0.8)
+    c = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, chunk=100, **cfg)
+    o = _run(oracle_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, chunk=100, **cfg)
+    _assert_parity(c, o)
+    assert o["done"].sum() >= n                                          # every env finished at least one episode
+
+
+def test_config5_continuous_random_target_2000_steps_vs_oracle(cuda_backend, oracle_backend):
+    """SURVEY 8(d) config 5 flavour: KukaRandButton, continuous actions, randomised button, 2000 steps."""
+    n, T = 32, 2000
+    acts = np.random.default_rng(0).uniform(-1, 1, (T, n, 3)).astype(np.float32)
+    noise = np.random.default_rng(1).normal(0, 1e-4, (T, n)).astype(np.float32)
+    cfg = dict(seed=5, is_discrete=False, random_target=True)
+    c = _run(cuda_backend, "KukaRandButtonGymEnv-v0", n, T, acts, noise, chunk=250, **cfg)
+    o = _run(oracle_backend, "KukaRandButtonGymEnv-v0", n, T, acts, noise, chunk=250, **cfg)
+    _assert_parity(c, o)
+    assert o["done"].sum() >= n                                          # >= 1 forced reset per env (1001-step limit)
+    assert np.abs(o["target"][:, 0] - 0.5).max() <= 0.15 + 1e-6 and np.abs(o["target"][:, 1]).max() <= 0.3 + 1e-6
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(is_discrete=True, shape_reward=True, action_repeat=2),
+    dict(is_discrete=False, shape_reward=True, random_target=True),
+    dict(is_discrete=True, force_down=False, max_steps=60),
+])
+def test_variants_vs_oracle(cfg, cuda_backend, oracle_backend):
+    n, T = 16, 300
+    rs = np.random.RandomState(3)
+    if cfg.get("is_discrete", True):
+        acts = rs.randint(-1, 6, size=(T, n)).astype(np.int32)           # includes step(None) (-1)
+        noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
+    else:
+        acts = rs.uniform(-1, 1, size=(T, n, 3)).astype(np.float32)
+        noise = rs.normal(0, 1e-4, size=(T, n)).astype(np.float32)
+    c = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=9, **cfg)
+    o = _run(oracle_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=9, **cfg)
+    _assert_parity(c, o, flags_exact=not cfg.get("shape_reward", False))
+    assert np.array_equal(c["done"], o["done"])
+    if cfg.get("shape_reward", False):
+        assert np.abs(c["rew"] - o["rew"]).max() < POS_TOL                # reward = -distance
+
+
+def test_cuda_matches_committed_golden(cuda_backend):
+    gen = _gen()
+    g = np.load(os.path.join(GOLDEN, "kuka_oracle_golden.npz"))
+    blob = load_kuka_scene().blob
+    for tag, (env_id, n, T, cfg) in gen.CASES.items():
+        acts, noise = gen.inputs(tag, n, T, cfg)
+        res = gen.run(cuda_backend, env_id, n, T, cfg, acts, noise, blob)
+        assert np.array_equal(res["done"], g[tag + "/done"]), tag
+        if not cfg.get("shape_reward", False):
+            assert np.array_equal(res["rew"], g[tag + "/rew"]), tag
+        for k, tol in (("obs0", POS_TOL), ("obs", POS_TOL), ("grip", POS_TOL), ("ee", POS_TOL), ("q", Q_TOL), ("qd", QD_TOL), ("target", 1e-6)):
+            assert np.abs(res[k] - g["%s/%s" % (tag, k)]).max() < tol, (tag, k)
+
+
+def test_step_equals_rollout_and_lane_packing_invariance(cuda_backend):
+    """Lockstep step() x T == fused rollout(T), and the result does not depend on envs_per_warp (bit-exact)."""
+    n, T = 40, 90
+    rs = np.random.RandomState(4)
+    acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
+    base = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40)
+    assert base["done"].sum() >= 2 * n
+    for kw in (dict(stepwise=True), dict(envs_per_warp=1), dict(envs_per_warp=7), dict(envs_per_warp=32), dict(chunk=13)):
+        other = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40, **kw)
+        for k in ("obs0", "obs", "rew", "done", "ep_ret", "ep_len", "q", "qd", "grip", "counters"):
+            assert np.array_equal(base[k], other[k]), (kw, k)
+    assert base["launches"] == 3                                        # settle (create) + reset + ONE fused rollout
+
+
+def test_in_kernel_streams_and_sharding_invariance(cuda_backend, oracle_backend):
+    """actions = noise = NULL: Philox actions/noise/reset draws keyed by the global env index."""
+    T = 300
+    kind, cfg = "KukaRandButtonGymEnv-v0", dict(seed=21, random_target=True, max_steps=100)
+    whole = _run(cuda_backend, kind, 24, T, None, None, **cfg)
+    lo = _run(cuda_backend, kind, 10, T, None, None, global_env_offset=0, **cfg)
+    hi = _run(cuda_backend, kind, 14, T, None, None, global_env_offset=10, **cfg)
+    for k, ax in (("obs", 1), ("rew", 1), ("done", 1), ("q", 0), ("target", 0)):
+        assert np.array_equal(whole[k], np.concatenate([lo[k], hi[k]], axis=ax)), k
+    # the oracle draws the same integers from the same streams; button placement agrees to float32 rounding
+    o = _run(oracle_backend, kind, 24, T, None, None, **cfg)
+    assert np.array_equal(whole["done"], o["done"]) and np.abs(whole["obs"] - o["obs"]).max() < POS_TOL
+    assert np.abs(whole["target"] - o["target"]).max() < 1e-6
+
+
+def test_full_size_properties_4096_envs(cuda_backend):
+    """BASELINE config 2 size: 4096 envs, fused rollouts; size-independent invariants of the env."""
+    n, T = 4096, 384
+    rs = np.random.default_rng(0)
+    acts = rs.integers(0, 6, (T, n), dtype=np.int32); noise = rs.normal(0, 0.01, (T, n)).astype(np.float32)
+    r = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, chunk=128, seed=0, max_steps=300)
+    assert np.isfinite(r["obs"]).all() and np.isfinite(r["q"]).all() and np.isfinite(r["qd"]).all()
+    assert set(np.unique(r["rew"])) <= {-1.0, 0.0, 1.0}
+    d = r["done"].astype(bool)
+    assert d.any(axis=0).all()                                            # max_steps=300 forces >= 1 episode end per env
+    assert r["ep_len"][d].max() <= 301 and r["ep_len"][d].min() >= 1      # counter > max_steps <=> 301 steps
+    # Monitor semantics: episode return == sum of the rewards of that episode (first episode of each env)
+    first = d.argmax(axis=0)
+    csum = np.cumsum(r["rew"], axis=0)
+    assert np.allclose(r["ep_ret"][first, np.arange(n)], csum[first, np.arange(n)])
+    assert (r["ep_len"][first, np.arange(n)] == first + 1).all()
+    # a +1 reward needs the button manifold: the gripper COM is then within reach of the button target
+    near = np.linalg.norm(r["obs"][(r["rew"] == 1) & ~d], axis=-1)
+    assert near.size > 0 and near.max() < 0.4
+    # joints respect their limits (+ solver slop), the commanded pose its box, the glider its travel
+    sc = load_kuka_scene()
+    lo = np.array([b.lower for b in sc.bodies]); hi = np.array([b.upper for b in sc.bodies])
+    assert (r["q"] >= lo - 0.02).all() and (r["q"] <= hi + 0.02).all()
+    assert (r["glider"][:, 0] > -1e-4).all() and (r["glider"][:, 0] < 0.0101).all()
+    assert np.abs(r["qd"][:, :7]).max() < 2.0
+
+
+def test_rollout_host_matches_device_rollout(cuda_backend):
+    n, T = 256, 64
+    rs = np.random.RandomState(8)
+    acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
+    dev = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=6)
+    sim = cuda_backend.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=6)
+    sim.reset(stream=cuda_backend.stream())
+    import torch
+    torch.cuda.synchronize()
+    obs = np.zeros((T, n, 3), np.float32); rew = np.zeros((T, n), np.float32); done = np.zeros((T, n), np.uint8)
+    sim.rollout_host(T, acts, noise, obs, rew, done)
+    assert np.array_equal(obs, dev["obs"]) and np.array_equal(rew, dev["rew"]) and np.array_equal(done, dev["done"])
+    assert sim.last_kernel_ms() > 0
+
+
+def test_single_env_classes_on_cuda(cuda_lib):
+    from srl_sim import backend
+    backend.use_library(None, None)
+    from environments.registry import registered_env
+    env = registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth")
+    env.seed(5)
+    o = env.reset()
+    assert o.shape == (3,) and np.allclose(o, np.array(env.getArmPos()) - env.getTargetPos())
+    tot = 0
+    for t in range(40):
+        o, r, d, info = env.step(env.action_space.sample())
+        tot += r
+        assert isinstance(r, int) and info == {}
+    assert np.isfinite(o).all()
+    env.close()
