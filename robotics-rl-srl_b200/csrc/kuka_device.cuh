@@ -21,6 +21,14 @@
 #include "philox.cuh"
 
 #define KK_DEV __device__ __forceinline__
+// Code-shape switches (measured on B200, see DESIGN.md "Kernel code shape"): per-body passes as rolled loops over
+// thread-local arrays (small code, LDL latency) or fully unrolled register code (large code, instruction-fetch bound).
+#ifndef KK_ROLL_IK
+#define KK_ROLL_IK 0
+#endif
+#ifndef KK_ROLL_DYN
+#define KK_ROLL_DYN 0
+#endif
 
 struct f3 { float x, y, z; };
 KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -57,6 +65,7 @@ struct KukaKin {             // kinematics of the current configuration
     f3 a[KK_NB];             // joint axes, world
     f3 p[KK_NB];             // joint frame origins, world
     f3 c[KK_NB];             // centres of mass, world
+    f3 pv[KK_NB];            // p x a: linear part of the joint motion vector about the world origin
     float Iw[KK_NB][6];      // rotational inertia about the COM, world axes
     float R6[9];             // rotation of the IK link (body 6)
 };
@@ -88,18 +97,29 @@ KK_DEV void sphere_cylinder(f3 s, float r, float cx, float cy, float z0, float z
 }
 
 // Forward kinematics + link states + collision detection against table / button disc / button stack.
+//
+// CODE-SIZE NOTE (measured, profiles/): this kernel runs ONE warp per scheduler, and everything outside the PGS sweep
+// executes once per step.  Fully unrolled, that once-per-step code was ~9000 SASS instructions (145 KB) that each warp
+// streamed from L2 every step -- 58% of all stall samples were `no_inst` (instruction fetch).  The per-body passes are
+// therefore ROLLED loops over the 12 bodies with their arrays in thread-local memory: a few hundred instructions that
+// stay resident in the instruction caches.
 template <bool WITH_CONTACTS>
 KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& ct) {
     float R[9], R7[9];
     float Rall[WITH_CONTACTS ? KK_NB : 1][9];  // per-body rotations for the sphere loop (local memory)
+    float ql[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) ql[i] = e.q[i];
     f3 p = mk3(P.base[0], P.base[1], P.base[2]), p7 = p;
     R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) R7[t] = R[t];
     int cbutton = 0, ctable = 0;
     if (WITH_CONTACTS) ct.n = 0;
     const float bz = P.btn_base[2];
     const float disc0 = bz + P.glider_z + e.qb + P.disc_z0, disc1 = bz + P.glider_z + e.qb + P.disc_z1;
     const float zmax_shapes = fmaxf(disc1, fmaxf(bz + P.stack_top, P.table_z));
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < KK_NB; ++i) {
         if (i == 10) {  // second finger restarts from the gripper base
 #pragma unroll
@@ -107,11 +127,10 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
             p = p7;
         }
         // child frame: p_i = p_parent + R_parent * origin ; R_i = R_parent * rot * Rodrigues(axis, q)
-        p = mk3(p.x + R[0] * P.org[i][0] + R[1] * P.org[i][1] + R[2] * P.org[i][2],
-                p.y + R[3] * P.org[i][0] + R[4] * P.org[i][1] + R[5] * P.org[i][2],
-                p.z + R[6] * P.org[i][0] + R[7] * P.org[i][1] + R[8] * P.org[i][2]);
+        const float ox = P.org[i][0], oy = P.org[i][1], oz = P.org[i][2];
+        p = mk3(p.x + R[0] * ox + R[1] * oy + R[2] * oz, p.y + R[3] * ox + R[4] * oy + R[5] * oz, p.z + R[6] * ox + R[7] * oy + R[8] * oz);
         float s, c;
-        sincosf(e.q[i], &s, &c);
+        sincosf(ql[i], &s, &c);
         const float t = 1.f - c, ax = P.axis[i][0], ay = P.axis[i][1], az = P.axis[i][2];
         const float Q[9] = {c + t * ax * ax, t * ax * ay - s * az, t * ax * az + s * ay,
                             t * ax * ay + s * az, c + t * ay * ay, t * ay * az - s * ax,
@@ -129,19 +148,20 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
                 Rn[3 * r + cc] = R[3 * r] * B[cc] + R[3 * r + 1] * B[3 + cc] + R[3 * r + 2] * B[6 + cc];
 #pragma unroll
         for (int t2 = 0; t2 < 9; ++t2) R[t2] = Rn[t2];
+        const f3 ai = mk3(R[0] * ax + R[1] * ay + R[2] * az, R[3] * ax + R[4] * ay + R[5] * az, R[6] * ax + R[7] * ay + R[8] * az);
+        const float mx = P.com[i][0], my = P.com[i][1], mz = P.com[i][2];
         k.p[i] = p;
-        k.a[i] = mk3(R[0] * ax + R[1] * ay + R[2] * az, R[3] * ax + R[4] * ay + R[5] * az, R[6] * ax + R[7] * ay + R[8] * az);
-        k.c[i] = mk3(p.x + R[0] * P.com[i][0] + R[1] * P.com[i][1] + R[2] * P.com[i][2],
-                     p.y + R[3] * P.com[i][0] + R[4] * P.com[i][1] + R[5] * P.com[i][2],
-                     p.z + R[6] * P.com[i][0] + R[7] * P.com[i][1] + R[8] * P.com[i][2]);
+        k.a[i] = ai;
+        k.pv[i] = cross3(p, ai);
+        k.c[i] = mk3(p.x + R[0] * mx + R[1] * my + R[2] * mz, p.y + R[3] * mx + R[4] * my + R[5] * mz, p.z + R[6] * mx + R[7] * my + R[8] * mz);
         {   // Iw = R Ic R^T
-            const float* I = P.Ic[i];
+            const float I0 = P.Ic[i][0], I1 = P.Ic[i][1], I2 = P.Ic[i][2], I3 = P.Ic[i][3], I4 = P.Ic[i][4], I5 = P.Ic[i][5];
             float T[9];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                T[3 * r + 0] = R[3 * r] * I[0] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[2];
-                T[3 * r + 1] = R[3 * r] * I[1] + R[3 * r + 1] * I[3] + R[3 * r + 2] * I[4];
-                T[3 * r + 2] = R[3 * r] * I[2] + R[3 * r + 1] * I[4] + R[3 * r + 2] * I[5];
+                T[3 * r + 0] = R[3 * r] * I0 + R[3 * r + 1] * I1 + R[3 * r + 2] * I2;
+                T[3 * r + 1] = R[3 * r] * I1 + R[3 * r + 1] * I3 + R[3 * r + 2] * I4;
+                T[3 * r + 2] = R[3 * r] * I2 + R[3 * r + 1] * I4 + R[3 * r + 2] * I5;
             }
             k.Iw[i][0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
             k.Iw[i][1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
@@ -221,6 +241,88 @@ KK_DEV void quat_from_matrix(const float* R, float* q) {
     }
 }
 
+#if KK_ROLL_IK
+// One damped-least-squares IK iteration at the current joint state (pybullet 1.8.6 / BussIK DLS):
+// dtheta = (J^T J + lambda I)^-1 J^T e over the 7 arm joints.  The 7x7 normal equations are formed and
+// solved in float64: they square the Jacobian's condition number, which float32 cannot afford.
+// Rolled loops over thread-local arrays (see the code-size note above kuka_fk).
+KK_DEV void kuka_ik(const KukaParams& P, const KukaEnv& e, const KukaKin& k, float* q_ik) {
+    constexpr int n = 7;
+    float J[n][6];
+    const f3 pe = k.p[6];
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const f3 aj = k.a[j];
+        const f3 l = cross3(aj, pe - k.p[j]);
+        J[j][0] = l.x; J[j][1] = l.y; J[j][2] = l.z; J[j][3] = aj.x; J[j][4] = aj.y; J[j][5] = aj.z;
+    }
+    float err[6];
+    err[0] = e.ee[0] - pe.x; err[1] = e.ee[1] - pe.y; err[2] = e.ee[2] - pe.z;
+    float qc[4];
+    quat_from_matrix(k.R6, qc);
+    const float cx = -qc[0], cy = -qc[1], cz = -qc[2], cw = qc[3];
+    const float dx = P.ikq[3] * cx + P.ikq[0] * cw + P.ikq[1] * cz - P.ikq[2] * cy;
+    const float dy = P.ikq[3] * cy - P.ikq[0] * cz + P.ikq[1] * cw + P.ikq[2] * cx;
+    const float dz = P.ikq[3] * cz + P.ikq[0] * cy - P.ikq[1] * cx + P.ikq[2] * cw;
+    const float dw = P.ikq[3] * cw - P.ikq[0] * cx - P.ikq[1] * cy - P.ikq[2] * cz;
+    const float vn = sqrtf(dx * dx + dy * dy + dz * dz);
+    // angle = 2 atan2(|v|, w) (== btQuaternion::getAngle, but well conditioned for small angles in fp32)
+    float angle = 2.0f * atan2f(vn, dw);
+    if (angle > 3.14159265358979f) angle -= 6.28318530717959f;
+    if (vn > 1e-12f) { const float sc = angle / vn; err[3] = sc * dx; err[4] = sc * dy; err[5] = sc * dz; }
+    else { err[3] = err[4] = err[5] = 0.f; }
+    double A[n][n], b[n];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+#pragma unroll 1
+        for (int j = 0; j <= i; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc = fma((double)J[i][r], (double)J[j][r], acc);
+            A[i][j] = acc;
+        }
+        A[i][i] += P.ik_damp;
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc = fma((double)J[i][r], (double)err[r], acc);
+        b[i] = acc;
+    }
+    // Cholesky A = L L^T (A is SPD thanks to the damping), forward/back substitution
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        double d = A[j][j];
+        for (int kk = 0; kk < j; ++kk) d -= A[j][kk] * A[j][kk];
+        const double inv = rsqrt(d);
+        A[j][j] = inv;  // store 1 / L_jj
+#pragma unroll 1
+        for (int i = j + 1; i < n; ++i) {
+            double acc = A[i][j];
+            for (int kk = 0; kk < j; ++kk) acc -= A[i][kk] * A[j][kk];
+            A[i][j] = acc * inv;
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        double acc = b[i];
+        for (int kk = 0; kk < i; ++kk) acc -= A[i][kk] * b[kk];
+        b[i] = acc * A[i][i];
+    }
+#pragma unroll 1
+    for (int i = n - 1; i >= 0; --i) {
+        double acc = b[i];
+        for (int kk = i + 1; kk < n; ++kk) acc -= A[kk][i] * b[kk];
+        b[i] = acc * A[i][i];
+    }
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(b[i]));
+    const double max_angle = 0.78539816339744830962;  // BussIK MaxAngleDLS = 45 degrees
+    const double scale = mx > max_angle ? max_angle / mx : 1.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) q_ik[i] = e.q[i] + (float)(scale * b[i]);
+}
+
+#else
 // One damped-least-squares IK iteration at the current joint state (pybullet 1.8.6 / BussIK DLS):
 // dtheta = (J^T J + lambda I)^-1 J^T e over the 7 arm joints.  The 7x7 normal equations are formed and
 // solved in float64: they square the Jacobian's condition number, which float32 cannot afford.
@@ -302,6 +404,85 @@ KK_DEV void kuka_ik(const KukaParams& P, const KukaEnv& e, const KukaKin& k, flo
     for (int i = 0; i < n; ++i) q_ik[i] = e.q[i] + (float)(scale * b[i]);
 }
 
+#endif
+#if KK_ROLL_DYN
+// Mass matrix (lower triangle, M[i][j], j <= i) by the composite-rigid-body algorithm and bias torques
+// (gravity, velocity products, Bullet link damping) by recursive Newton-Euler, both in world coordinates
+// about the world origin: sub-tree quantities accumulate by plain addition.  Rolled per-body loops.
+KK_DEV void kuka_dynamics(const KukaParams& P, const KukaEnv& e, const KukaKin& k, float (&M)[KK_NB][KK_NB], float* bias) {
+    float qdl[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) qdl[i] = e.qd[i];
+    f3 nn[KK_NB], ff[KK_NB];          // body wrenches about the origin, then sub-tree sums
+    float cm[KK_NB]; f3 ch[KK_NB]; float cI[KK_NB][6];  // composite mass, first moment, inertia about the origin
+    // ---- RNEA forward pass + body wrenches (running parent state; the second finger restarts from body 7) ----
+    f3 w = mk3(0.f, 0.f, 0.f), vO = w, aw = w, av = mk3(0.f, 0.f, -P.gz);  // gravity as a fictitious base acceleration
+    f3 w7 = w, vO7 = w, aw7 = w, av7 = av;
+#pragma unroll 1
+    for (int i = 0; i < KK_NB; ++i) {
+        if (i == 10) { w = w7; vO = vO7; aw = aw7; av = av7; }
+        const float qd = qdl[i];
+        const f3 ai = k.a[i], pvi = k.pv[i];
+        const f3 awn = aw + qd * cross3(w, ai);
+        const f3 avn = av + qd * (cross3(w, pvi) + cross3(vO, ai));
+        w = w + qd * ai;
+        vO = vO + qd * pvi;
+        aw = awn; av = avn;
+        if (i == 7) { w7 = w; vO7 = vO; aw7 = aw; av7 = av; }
+        // spatial inertia about the origin: m, h = m c, I_O = Iw + m (|c|^2 1 - c c^T)
+        const float m = P.mass[i];
+        const f3 c = k.c[i];
+        const f3 h = m * c;
+        float Iw[6], IO[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) Iw[t] = k.Iw[i][t];
+        IO[0] = Iw[0] + m * (c.y * c.y + c.z * c.z);
+        IO[1] = Iw[1] - m * c.x * c.y;
+        IO[2] = Iw[2] - m * c.x * c.z;
+        IO[3] = Iw[3] + m * (c.x * c.x + c.z * c.z);
+        IO[4] = Iw[4] - m * c.y * c.z;
+        IO[5] = Iw[5] + m * (c.x * c.x + c.y * c.y);
+        cm[i] = m; ch[i] = h;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) cI[i][t] = IO[t];
+        const f3 Lv = symv(IO, w) + cross3(h, vO);
+        const f3 Pv = m * vO + cross3(w, h);
+        const f3 La = symv(IO, aw) + cross3(h, av);
+        const f3 Pa = m * av + cross3(aw, h);
+        f3 n = La + cross3(w, Lv) + cross3(vO, Pv);
+        f3 f = Pa + cross3(w, Pv);
+        // btMultiBody link damping (linear/angular 0.04, K1 = K2): resisting wrench added to the bias
+        const f3 vc = vO + cross3(w, c);
+        const f3 F = (P.kl * m * (1.0f + norm3(vc))) * vc;
+        const f3 T = (P.ka * (1.0f + norm3(w))) * symv(Iw, w);
+        nn[i] = n + T + cross3(c, F);
+        ff[i] = f + F;
+    }
+    // ---- backward pass: bias_i = s_i . (wrench of the sub-tree); CRBA: M_ij = s_i . (I^c_j s_j), i ancestor-or-self of j ----
+#pragma unroll 1
+    for (int j = KK_NB - 1; j >= 0; --j) {
+        const f3 aj = k.a[j], pvj = k.pv[j];
+        const f3 nj = nn[j], fj = ff[j];
+        bias[j] = dot3(aj, nj) + dot3(pvj, fj);
+        const float mj = cm[j]; const f3 hj = ch[j];
+        float Ij[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) Ij[t] = cI[j][t];
+        const f3 Pm = mj * pvj + cross3(aj, hj);              // linear momentum of the composite under unit joint rate
+        const f3 Lm = symv(Ij, aj) + cross3(hj, pvj);         // angular momentum about the origin
+        for (int i = 0; i <= j; ++i) M[j][i] = 0.f;
+        for (int i = j; i >= 0; i = KK_PAR(i)) M[j][i] = dot3(k.a[i], Lm) + dot3(k.pv[i], Pm);
+        const int pa = KK_PAR(j);
+        if (pa >= 0) {
+            nn[pa] = nn[pa] + nj; ff[pa] = ff[pa] + fj;
+            cm[pa] += mj; ch[pa] = ch[pa] + hj;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) cI[pa][t] += Ij[t];
+        }
+    }
+}
+
+#else
 // Mass matrix (lower triangle, m[i][j], j <= i) by the composite-rigid-body algorithm and bias torques
 // (gravity, velocity products, Bullet link damping) by recursive Newton-Euler, both in world coordinates
 // about the world origin: sub-tree quantities accumulate by plain addition.
@@ -392,6 +573,7 @@ KK_DEV void kuka_dynamics(const KukaParams& P, const KukaEnv& e, const KukaKin& 
     }
 }
 
+#endif
 // In-place: M (lower) -> A = M^-1 (lower triangle valid), via Cholesky and triangular inverse.
 KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
     constexpr int n = KK_NB;
@@ -447,7 +629,20 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     kuka_ik(P, e, k, q_ik);
     // ---- dynamics ----
     float A[KK_NB][KK_NB], bias[KK_NB];
+#if KK_ROLL_DYN
+    {
+        float Mloc[KK_NB][KK_NB], bloc[KK_NB];  // thread-local (dynamically indexed by the rolled loops)
+        kuka_dynamics(P, e, k, Mloc, bloc);
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {       // -> registers (static indices only from here on)
+            bias[i] = bloc[i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) A[i][j] = Mloc[i][j];
+        }
+    }
+#else
     kuka_dynamics(P, e, k, A, bias);
+#endif
     kuka_spd_inverse(A);
     float v[KK_ND];
     {
@@ -532,51 +727,101 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         }
     }
     // ---- projected Gauss-Seidel: row order = motors (button first), limits (button first), contact normals, friction ----
-    for (int it = 0; it < P.iters; ++it) {
-        {   // button motor
-            const float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
-            v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
-        }
+    // Button rows are made branch-free: an inactive limit row gets the bound [0, 0] (an exact no-op).
+    const float bl_lo_hi = bl_lo ? P.lim_maximp : 0.f, bl_hi_hi = bl_hi ? P.lim_maximp : 0.f;
+    float mi[KK_NB];  // impulse bounds in vector registers: no uniform-register reloads inside the sweep
 #pragma unroll
-        for (int i = 0; i < KK_NB; ++i) {  // arm motors: unit Jacobian, W = A[:, i]
-            const float s = fminf(fmaxf(fmaf(tgt[i] - v[i], invd[i], lam[i]), -P.maximp[i]), P.maximp[i]);
-            const float d = s - lam[i];
-            lam[i] = s;
+    for (int i = 0; i < KK_NB; ++i) asm volatile("mov.f32 %0, %1;" : "=f"(mi[i]) : "f"(P.maximp[i]));  // opaque copy: keeps ptxas from re-reading the constant bank
+    if ((lim_lo_mask | lim_hi_mask) == 0u && nc == 0) {
+        // FAST PATH (no arm joint on a limit, no contact manifold): straight-line sweep, registers only.
+        // The loop-carried dependency runs through consecutive motor rows; it is shortened from
+        //   FFMA(v_i) -> FADD -> FFMA -> FMNMX -> FMNMX -> FADD        (26 cycles)   to
+        //   FFMA -> FMNMX -> FMNMX -> FADD                               (18 cycles)
+        // by folding the previous row's contribution to v_i into the impulse update algebraically:
+        //   lam_i + (tgt_i - v_i) / D_i  =  [lam_i + tgt_i/D_i - v'_i/D_i]  -  (A_{i,i-1}/D_i) * delta_{i-1}
+        // where v'_i lacks only the previous row's update (applied off the critical path afterwards).
+        float tk[KK_NB], kk[KK_NB];
 #pragma unroll
-            for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
-        }
-        if (bl_lo) { const float s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), P.lim_maximp);
-                     v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s; }
-        if (bl_hi) { const float s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), P.lim_maximp);
-                     v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s; }
-        if (lim_lo_mask | lim_hi_mask) {
+        for (int i = 0; i < KK_NB; ++i) { tk[i] = tgt[i] * invd[i]; kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f; }
+#pragma unroll 1
+        for (int it = 0; it < P.iters; ++it) {
+            {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
+                float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
+                s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
+                s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
+                v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
+            }
+            float dprev = 0.f;
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {
-                if (lim_lo_mask & (1u << i)) {  // J = +e_i
-                    const float t = -P.erp * (e.q[i] - P.lower[i]) * P.inv_dt;
-                    const float s = fminf(fmaxf(fmaf(t - v[i], invd[i], lim_lam_lo[i]), 0.f), P.lim_maximp);
-                    const float d = s - lim_lam_lo[i]; lim_lam_lo[i] = s;
+                const float e = fmaf(-invd[i], v[i], lam[i] + tk[i]);          // off the critical path
+                const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        // critical path
+                if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             // deferred update from row i-1
+                const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
+                const float d = s - lam[i];
+                lam[i] = s;
 #pragma unroll
-                    for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
-                }
-                if (lim_hi_mask & (1u << i)) {  // J = -e_i
-                    const float t = -P.erp * (P.upper[i] - e.q[i]) * P.inv_dt;
-                    const float s = fminf(fmaxf(fmaf(t + v[i], invd[i], lim_lam_hi[i]), 0.f), P.lim_maximp);
-                    const float d = s - lim_lam_hi[i]; lim_lam_hi[i] = s;
-#pragma unroll
-                    for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(-KK_A(j, i), d, v[j]);
-                }
+                for (int j = 0; j < KK_NB; ++j)
+                    if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
+                dprev = d;
             }
         }
-        if (nc > 0) {
+    } else {
+        // GENERAL PATH (a joint on its limit and / or a contact manifold): same row order, plain form.
+#pragma unroll 1
+        for (int it = 0; it < P.iters; ++it) {
+            {   // button motor
+                const float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
+            }
+#pragma unroll
+            for (int i = 0; i < KK_NB; ++i) {  // arm motors: unit Jacobian, W = A[:, i]
+                const float s = fminf(fmaxf(fmaf(tgt[i] - v[i], invd[i], lam[i]), -mi[i]), mi[i]);
+                const float d = s - lam[i];
+                lam[i] = s;
+#pragma unroll
+                for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
+            }
+            {   // button limits
+                float s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
+                s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
+                v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
+            }
+            if (lim_lo_mask | lim_hi_mask) {
+#pragma unroll
+                for (int i = 0; i < KK_NB; ++i) {
+                    if (lim_lo_mask & (1u << i)) {  // J = +e_i
+                        const float t = -P.erp * (e.q[i] - P.lower[i]) * P.inv_dt;
+                        const float s = fminf(fmaxf(fmaf(t - v[i], invd[i], lim_lam_lo[i]), 0.f), P.lim_maximp);
+                        const float d = s - lim_lam_lo[i]; lim_lam_lo[i] = s;
+#pragma unroll
+                        for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
+                    }
+                    if (lim_hi_mask & (1u << i)) {  // J = -e_i
+                        const float t = -P.erp * (P.upper[i] - e.q[i]) * P.inv_dt;
+                        const float s = fminf(fmaxf(fmaf(t + v[i], invd[i], lim_lam_hi[i]), 0.f), P.lim_maximp);
+                        const float d = s - lim_lam_hi[i]; lim_lam_hi[i] = s;
+#pragma unroll
+                        for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(-KK_A(j, i), d, v[j]);
+                    }
+                }
+            }
             for (int r = 0; r < 3 * nc; ++r) {
+                float lo = 0.f, hi = 1e10f;
+                if (r >= nc) {
+                    hi = P.mu * c_lam[(r - nc) >> 1]; lo = -hi;
+                    if (hi == 0.f && c_lam[r] == 0.f) continue;  // friction under a zero normal impulse: bounds [0, 0], an exact no-op
+                }
                 float jv = 0.f;
 #pragma unroll
                 for (int j = 0; j < KK_ND; ++j) jv = fmaf(cJ[r][j], v[j], jv);
-                float lo = 0.f, hi = 1e10f;
-                if (r >= nc) { hi = P.mu * c_lam[(r - nc) >> 1]; lo = -hi; }
                 const float s = fminf(fmaxf(fmaf(c_tgt[r] - jv, c_invd[r], c_lam[r]), lo), hi);
-                const float d = s - c_lam[r]; c_lam[r] = s;
+                const float d = s - c_lam[r];
+                if (d == 0.f) continue;       // inactive (separating) contact: nothing to apply
+                c_lam[r] = s;
 #pragma unroll
                 for (int j = 0; j < KK_ND; ++j) v[j] = fmaf(cW[r][j], d, v[j]);
             }

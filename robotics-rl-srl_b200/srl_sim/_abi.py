@@ -242,7 +242,8 @@ class Sim(object):
 
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CUDA_LIBRARY_PATH = os.path.join(_PKG_ROOT, "csrc", "libsrl_sim_b200.so")
+# SRL_SIM_CUDA_LIB lets a developer A/B another build of the SAME sm_100a library (e.g. a code-shape variant)
+CUDA_LIBRARY_PATH = os.environ.get("SRL_SIM_CUDA_LIB") or os.path.join(_PKG_ROOT, "csrc", "libsrl_sim_b200.so")
 _cuda_library = None
 
 
