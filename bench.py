@@ -323,7 +323,7 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/); filled in per round, None until measured.
-TRAFFIC_BYTES = {"kuka": None, "mobile": None}
+TRAFFIC_BYTES = {"kuka": 65799168, "mobile": 86867968}  # profiles/r01_*_ncu_full.txt
 
 
 def main():

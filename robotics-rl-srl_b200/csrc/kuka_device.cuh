@@ -732,8 +732,12 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     float mi[KK_NB];  // impulse bounds in vector registers: no uniform-register reloads inside the sweep
 #pragma unroll
     for (int i = 0; i < KK_NB; ++i) asm volatile("mov.f32 %0, %1;" : "=f"(mi[i]) : "f"(P.maximp[i]));  // opaque copy: keeps ptxas from re-reading the constant bank
-    if ((lim_lo_mask | lim_hi_mask) == 0u && nc == 0) {
-        // FAST PATH (no arm joint on a limit, no contact manifold): straight-line sweep, registers only.
+    int it0 = 0;                 // first sweep the general loop still has to do
+    bool resume_mid_sweep = false;  // the fast path already ran the motor + button rows of sweep it0
+    if ((lim_lo_mask | lim_hi_mask) == 0u) {
+        // FAST PATH (no arm joint on a limit): straight-line sweep, registers only.  Contact rows of the manifold are
+        // WATCHED: while every normal row is separating (lam = 0 and J v >= target) it and its friction rows are exact
+        // no-ops; the first time one would activate, the solve continues in the general loop from that very row.
         // The loop-carried dependency runs through consecutive motor rows; it is shortened from
         //   FFMA(v_i) -> FADD -> FFMA -> FMNMX -> FMNMX -> FADD        (26 cycles)   to
         //   FFMA -> FMNMX -> FMNMX -> FADD                               (18 cycles)
@@ -767,11 +771,25 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                     if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
                 dprev = d;
             }
-        }
-    } else {
-        // GENERAL PATH (a joint on its limit and / or a contact manifold): same row order, plain form.
+            if (nc > 0) {
+                bool act = false;
 #pragma unroll 1
-        for (int it = 0; it < P.iters; ++it) {
+                for (int c = 0; c < nc; ++c) {
+                    float jv = 0.f;
+#pragma unroll
+                    for (int j = 0; j < KK_ND; ++j) jv = fmaf(cJ[c][j], v[j], jv);
+                    act = act | (c_tgt[c] - jv > 0.f);
+                }
+                if (act) { it0 = it; resume_mid_sweep = true; break; }
+            }
+            it0 = it + 1;
+        }
+    }
+    if (it0 < P.iters) {
+        // GENERAL PATH (a joint on its limit and / or an active contact): same row order, plain form.
+#pragma unroll 1
+        for (int it = it0; it < P.iters; ++it) {
+            if (!resume_mid_sweep) {
             {   // button motor
                 const float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
                 v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
@@ -790,6 +808,8 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
                 v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
             }
+            }
+            resume_mid_sweep = false;
             if (lim_lo_mask | lim_hi_mask) {
 #pragma unroll
                 for (int i = 0; i < KK_NB; ++i) {

@@ -1,0 +1,138 @@
+"""
+``BatchedSRLVecEnv`` -- a stable-baselines-style ``VecEnv`` over ONE lockstep batch of simulated envs.
+
+It takes the place of the ``SubprocVecEnv`` / ``DummyVecEnv`` the reference builds in
+``rl_baselines/utils.py:194-229`` (``createEnvs``): instead of one OS process per env exchanging pickled
+(obs, reward, done, info) tuples over pipes, all ``num_envs`` envs live in structure-of-arrays HBM and one
+kernel launch steps them.  Semantics kept from stable-baselines 2.5:
+
+* ``reset() -> obs[N, D]``; ``step_async(actions)`` / ``step_wait()`` / ``step(actions)``
+  ``-> (obs[N, D], rewards[N], dones[N], infos[N])``;
+* an env that finishes is reset immediately and the returned observation is the post-reset one;
+* ``infos[i]['episode'] = {'r': return, 'l': length, 't': wall time}`` on done (``bench.Monitor``, environments/utils.py:53-54).
+
+numpy in / numpy out by default; ``step_tensors`` / ``rollout_tensors`` keep everything on the GPU (zero copies) for a
+GPU-resident policy.
+"""
+import time
+
+import numpy as np
+
+from . import _abi, spaces
+from .backend import default_backend
+
+_KUKA_IDS = ("KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0")
+_OBS_DIM = {"MobileRobot1DGymEnv-v0": 1}
+_N_ACTIONS = {"MobileRobot1DGymEnv-v0": 2, "MobileRobotGymEnv-v0": 4, "MobileRobot2TargetGymEnv-v0": 4,
+              "MobileRobotLineTargetGymEnv-v0": 4, "KukaButtonGymEnv-v0": 6, "KukaRandButtonGymEnv-v0": 6}
+
+
+class BatchedSRLVecEnv(object):
+    """
+    :param env_id: (str) one of the ids of ``environments.registry.registered_env``
+    :param num_envs: (int) envs in this process / on this GPU
+    :param seed: (int) base seed; env ``i`` uses the stream of global index ``global_env_offset + i``
+    :param device: (int) CUDA ordinal (default 0)
+    :param global_env_offset: (int) index of local env 0 in the global batch (rank * num_envs under torchrun)
+    :param env_kwargs: the reference's env keyword arguments (is_discrete, random_target, shape_reward, force_down,
+        action_repeat, max_distance, srl_model, ...); unknown ones are ignored like the reference's ``**_``
+    """
+
+    def __init__(self, env_id, num_envs, seed=0, device=None, global_env_offset=0, **env_kwargs):
+        if env_id not in _abi.ENV_KINDS:
+            raise KeyError("unknown env id %r" % env_id)
+        srl_model = env_kwargs.pop("srl_model", "ground_truth")
+        if srl_model != "ground_truth":
+            raise NotImplementedError("BatchedSRLVecEnv provides the ground_truth observation (got srl_model=%r)" % srl_model)
+        self.env_id = env_id
+        self.num_envs = int(num_envs)
+        self.backend = default_backend(device)
+        cfg = dict(is_discrete=env_kwargs.get("is_discrete", True), random_target=env_kwargs.get("random_target", False),
+                   shape_reward=env_kwargs.get("shape_reward", False), force_down=env_kwargs.get("force_down", True),
+                   action_repeat=env_kwargs.get("action_repeat", 1), global_env_offset=global_env_offset)
+        blob = None
+        if env_id in _KUKA_IDS:
+            from .model import load_kuka_scene
+            blob = load_kuka_scene().blob
+            cfg["max_distance"] = env_kwargs.get("max_distance", 0.8)
+        for k in ("max_steps", "envs_per_warp", "solver_iterations"):
+            if k in env_kwargs:
+                cfg[k] = env_kwargs[k]
+        self.sim = self.backend.make_sim(env_id, self.num_envs, seed=seed, model_blob=blob, **cfg)
+        self.is_discrete = bool(cfg["is_discrete"])
+        D = self.sim.obs_dim
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(D,), dtype=np.float32)
+        if self.is_discrete:
+            self.action_space = spaces.Discrete(_N_ACTIONS[env_id])
+        else:
+            self.action_space = spaces.Box(low=-1, high=1, shape=(self.sim.action_dim,), dtype=np.float32)
+        be = self.backend
+        n = self.num_envs
+        self._obs = be.zeros((n, D), np.float32)
+        self._rew = be.zeros((n,), np.float32)
+        self._done = be.zeros((n,), np.uint8)
+        self._ep_ret = be.zeros((n,), np.float32)
+        self._ep_len = be.zeros((n,), np.int32)
+        self._actions = None
+        self._t0 = time.time()
+        self.closed = False
+
+    # ---- VecEnv API (numpy) --------------------------------------------------------------------------
+    def reset(self):
+        self.sim.reset(obs_out=self._obs, stream=self.backend.stream())
+        return self.backend.to_host(self._obs).copy()
+
+    def step_async(self, actions):
+        if self.is_discrete:
+            a = np.asarray([-1 if x is None else x for x in actions] if isinstance(actions, (list, tuple)) else actions, dtype=np.int32)
+            a = a.reshape(self.num_envs)
+        else:
+            a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.sim.action_dim)
+        self._actions = self.backend.from_host(a)
+
+    def step_wait(self):
+        be = self.backend
+        self.sim.step(self._actions, None, self._obs, self._rew, self._done, self._ep_ret, self._ep_len, stream=be.stream())
+        obs = be.to_host(self._obs).copy()
+        rew = be.to_host(self._rew).copy()
+        done = be.to_host(self._done).astype(bool)
+        infos = [{} for _ in range(self.num_envs)]
+        if done.any():
+            ep_ret, ep_len = be.to_host(self._ep_ret), be.to_host(self._ep_len)
+            t = round(time.time() - self._t0, 6)
+            for i in np.nonzero(done)[0]:
+                infos[i]["episode"] = {"r": round(float(ep_ret[i]), 6), "l": int(ep_len[i]), "t": t}
+        return obs, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        if not self.closed:
+            self.sim.close()
+            self.closed = True
+
+    def seed(self, seed=None):
+        raise NotImplementedError("the batch is seeded at construction (counter-based streams keyed by env index)")
+
+    def get_images(self):
+        raise NotImplementedError("image observations are out of scope of the batched simulator")
+
+    def render(self, mode="human"):
+        raise NotImplementedError("image observations are out of scope of the batched simulator")
+
+    # ---- zero-copy GPU API ---------------------------------------------------------------------------
+    def step_tensors(self, actions, noise=None):
+        """``actions``: torch CUDA tensor int32[N] / float32[N, A]; returns CUDA tensors (views of internal buffers)."""
+        self.sim.step(actions, noise, self._obs, self._rew, self._done, self._ep_ret, self._ep_len, stream=self.backend.stream())
+        return self._obs, self._rew, self._done, self._ep_ret, self._ep_len
+
+    def rollout_tensors(self, T, actions=None, noise=None, out=None):
+        """T fused steps in one launch.  ``actions``: CUDA int32[T, N] / float32[T, N, A] or None (random agent)."""
+        be, n, D = self.backend, self.num_envs, self.sim.obs_dim
+        if out is None:
+            out = dict(obs=be.empty((T, n, D), np.float32), rew=be.empty((T, n), np.float32), done=be.empty((T, n), np.uint8),
+                       ep_ret=be.zeros((T, n), np.float32), ep_len=be.zeros((T, n), np.int32))
+        self.sim.rollout(T, actions, noise, out["obs"], out["rew"], out["done"], out["ep_ret"], out["ep_len"], stream=be.stream())
+        return out

@@ -1,0 +1,92 @@
+"""
+The C-ABI boundary (include/srl_sim.h) without a GPU: both libraries load and export every declared symbol, the
+config struct layouts agree, and the CUDA library refuses (loudly) to run without a device -- there is no CPU path
+in the product library.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import CUDA_LIB, ORACLE_LIB, ROOT
+from srl_sim import _abi
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "srl_sim.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(srl_sim_\w+)\s*\(", hdr)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_abi.EXPORTED_SYMBOLS)
+    hdr = open(os.path.join(ROOT, "include", "srl_sim.h")).read()
+    fields = re.findall(r"^\s+(?:uint32_t|int32_t|float|uint64_t)\s+(\w+);", hdr[hdr.index("typedef struct srl_cfg"):hdr.index("} srl_cfg;")], flags=re.M)
+    assert fields == [f[0] for f in _abi.SrlCfg._fields_]
+    assert ctypes.sizeof(_abi.SrlCfg) == 64
+    for name, kind in _abi.ENV_KINDS.items():
+        assert re.search(r"=\s*%d,?\s*/\*\s*%s" % (kind, re.escape(name)), hdr), name
+
+
+@pytest.mark.parametrize("path", [ORACLE_LIB, CUDA_LIB])
+def test_library_loads_and_exports_every_symbol(path, oracle_lib):
+    if not os.path.isfile(path):
+        pytest.fail("%s has not been built (python __graft_entry__.py build)" % path)
+    lib = _abi.SimLibrary(path)            # raises if a symbol is missing or the ABI version differs
+    assert lib.lib.srl_sim_abi_version() == _abi.ABI_VERSION
+    assert lib.lib.srl_sim_num_envs(None) == 0 and lib.lib.srl_sim_obs_dim(None) == 0
+
+
+def test_cuda_library_has_no_cpu_path():
+    import torch
+    lib = _abi.SimLibrary(CUDA_LIB)
+    with pytest.raises(_abi.SimError, match="no CPU path"):
+        _abi.Sim(lib, "MobileRobotGymEnv-v0", 4, -1)
+    if not torch.cuda.is_available():
+        with pytest.raises(_abi.SimError):
+            _abi.Sim(lib, "MobileRobotGymEnv-v0", 4, 0)       # no device: must fail, never fall back
+        from srl_sim.backend import Backend
+        with pytest.raises(_abi.SimError, match="no CPU fallback"):
+            Backend(lib, 0)
+
+
+def test_bad_arguments_are_reported_not_thrown(oracle_lib):
+    with pytest.raises(_abi.SimError, match="num_envs"):
+        _abi.Sim(oracle_lib, "MobileRobotGymEnv-v0", 0, -1)
+    with pytest.raises(_abi.SimError, match="model blob"):
+        _abi.Sim(oracle_lib, "KukaButtonGymEnv-v0", 2, -1, model_blob=np.zeros(8))
+    with pytest.raises(_abi.SimError, match="action_joints"):
+        _abi.Sim(oracle_lib, "KukaButtonGymEnv-v0", 2, -1, action_joints=True)
+    sim = _abi.Sim(oracle_lib, "MobileRobotGymEnv-v0", 3, -1)
+    with pytest.raises(_abi.SimError, match="not available"):
+        sim.get_state(_abi.F_JOINT_POS)
+
+
+def test_vec_env_semantics_on_oracle(use_oracle_backend):
+    """stable-baselines VecEnv contract: shapes, auto-reset, Monitor-style info['episode'], createEnvs wrapping."""
+    import argparse
+    from rl_baselines.utils import createEnvs
+    from srl_sim.vec_env import BatchedSRLVecEnv
+    env = BatchedSRLVecEnv("MobileRobotGymEnv-v0", 4, seed=0, is_discrete=True)   # config 1: 4 envs, random agent
+    obs = env.reset()
+    assert obs.shape == (4, 2) and obs.dtype == np.float32 and env.action_space.n == 4
+    steps, episodes = 0, []
+    for t in range(1600 // 4):                                                     # tests/test_pipeline.py:14 NUM_TIMESTEP
+        actions = [env.action_space.sample() for _ in range(4)]
+        obs, rew, done, infos = env.step(actions)
+        steps += 4
+        assert obs.shape == (4, 2) and rew.shape == (4,) and done.dtype == bool and len(infos) == 4
+        for i in np.nonzero(done)[0]:
+            episodes.append(infos[i]["episode"])
+    assert steps == 1600 and len(episodes) == 4 and all(e["l"] == 251 for e in episodes)
+    env.close()
+    args = argparse.Namespace(env="KukaButtonGymEnv-v0", num_cpu=3, seed=0, num_stack=2, srl_model="ground_truth")
+    venv = createEnvs(args, env_kwargs=dict(is_discrete=False, max_steps=10))
+    o = venv.reset()
+    assert o.shape == (3, 6) and np.abs(o).max() <= 10.0
+    for _ in range(12):
+        o, r, d, infos = venv.step(np.zeros((3, 3), np.float32))
+    assert venv.get_original_obs().shape == (3, 6)
+    venv.close()
