@@ -478,10 +478,15 @@ static void plane_space(V3 n, V3& p, V3& q) { /* btPlaneSpace1 */
     }
 }
 
+
 struct StepScratch { std::vector<Row> rows; };
 
-/* One p.stepSimulation() preceded by Kuka.applyAction's IK + motor set-points (kuka.py:142-187). */
-static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterations, StepScratch& sc) {
+/* Motor set-points as PyBullet's setJointMotorControl2 records them (one per movable joint + the button glider). */
+struct MotorCmd { double target, kp, kd, maxforce, maxvel; };
+struct ButtonCmd { int position_control; double target, kp, kd, maxforce; };
+
+/* One p.stepSimulation() with explicit motor set-points. */
+static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, const ButtonCmd& btn, int iterations, StepScratch& sc) {
     const double dt = m.sc[KM_SC_TIMESTEP];
     Kin k;
     forward_kinematics(m, e.q, k);
@@ -491,21 +496,6 @@ static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterati
     Contact contacts[8];
     const int max_contacts = (int)m.sc[KM_SC_MAX_CONTACTS];
     const int nc = detect_contacts(m, k, e, contacts, max_contacts, e.contact_button, e.contact_table);
-
-    /* applyAction: IK at the current joint state, then the 12 POSITION_CONTROL set-points */
-    double q_ik[NB];
-    inverse_kinematics(m, k, e.q, e.ee, q_ik);
-    const double finger_angle = 0.0; /* kuka_button_gym_env.py:313,334 */
-    double target[NB];
-    for (int i = 0; i < NB; ++i) {
-        switch (m.b[i].target_mode) {
-        case 0: target[i] = q_ik[i]; break;
-        case 1: target[i] = e.ee_angle; break;
-        case 2: target[i] = -finger_angle; break;
-        case 3: target[i] = finger_angle; break;
-        default: target[i] = 0.0;
-        }
-    }
 
     /* unconstrained velocity update: v = qd + dt * FD(q, qd) */
     Aba A;
@@ -554,9 +544,9 @@ static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterati
            impulse bound = force * dt.  Button first (it is loaded before the Kuka), then joints 0..11. */
     {
         Row r = joint_row(NB, 1.0);
-        if (button_armed) { /* :347  POSITION_CONTROL targetPosition=0.1, default gains, default max force */
-            r.target = m.sc[KM_SC_BTN_KP] * (m.sc[KM_SC_BTN_TARGET] - e.qb) / dt + v0[NB] + m.sc[KM_SC_BTN_KD] * (0.0 - v0[NB]);
-            r.hi = m.sc[KM_SC_BTN_MAXFORCE] * dt;
+        if (btn.position_control) { /* :347  POSITION_CONTROL targetPosition=0.1, default gains, default max force */
+            r.target = btn.kp * (btn.target - e.qb) / dt + v0[NB] + btn.kd * (0.0 - v0[NB]);
+            r.hi = btn.maxforce * dt;
         } else {            /* default joint motor created at load time: velocity target 0, small impulse bound */
             r.target = 0.0;
             r.hi = m.sc[KM_SC_BTN_IDLE_IMPULSE];
@@ -565,9 +555,9 @@ static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterati
         finish_row(r); rows.push_back(r);
     }
     for (int i = 0; i < NB; ++i) {
-        const KBody& b = m.b[i];
+        const MotorCmd& b = cmd[i];
         Row r = joint_row(i, 1.0);
-        double t = b.kp * (target[i] - e.q[i]) / dt + v0[i] + b.kd * (0.0 - v0[i]);
+        double t = b.kp * (b.target - e.q[i]) / dt + v0[i] + b.kd * (0.0 - v0[i]);
         if (b.maxvel > 0.0) { if (t > b.maxvel) t = b.maxvel; if (t < -b.maxvel) t = -b.maxvel; }
         r.target = t; r.hi = b.maxforce * dt; r.lo = -r.hi;
         finish_row(r); rows.push_back(r);
@@ -630,6 +620,32 @@ static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterati
     const int g = (int)m.sc[KM_SC_GRIPPER_BODY], eb = (int)m.sc[KM_SC_EE_BODY];
     e.gripper_pos[0] = k.com[g].x; e.gripper_pos[1] = k.com[g].y; e.gripper_pos[2] = k.com[g].z;
     e.ee_pos[0] = k.p[eb].x; e.ee_pos[1] = k.p[eb].y; e.ee_pos[2] = k.p[eb].z;
+}
+
+/* One p.stepSimulation() preceded by Kuka.applyAction's IK + motor set-points (kuka.py:142-187). */
+static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterations, StepScratch& sc) {
+    Kin k;
+    forward_kinematics(m, e.q, k);
+    /* applyAction: IK at the current joint state, then the 12 POSITION_CONTROL set-points */
+    double q_ik[NB];
+    inverse_kinematics(m, k, e.q, e.ee, q_ik);
+    const double finger_angle = 0.0; /* kuka_button_gym_env.py:313,334 */
+    MotorCmd cmd[NB];
+    for (int i = 0; i < NB; ++i) {
+        const KBody& b = m.b[i];
+        switch (b.target_mode) {
+        case 0: cmd[i].target = q_ik[i]; break;
+        case 1: cmd[i].target = e.ee_angle; break;
+        case 2: cmd[i].target = -finger_angle; break;
+        case 3: cmd[i].target = finger_angle; break;
+        default: cmd[i].target = 0.0;
+        }
+        cmd[i].kp = b.kp; cmd[i].kd = b.kd; cmd[i].maxforce = b.maxforce; cmd[i].maxvel = b.maxvel;
+    }
+    ButtonCmd btn;
+    btn.position_control = button_armed;
+    btn.target = m.sc[KM_SC_BTN_TARGET]; btn.kp = m.sc[KM_SC_BTN_KP]; btn.kd = m.sc[KM_SC_BTN_KD]; btn.maxforce = m.sc[KM_SC_BTN_MAXFORCE];
+    physics_step_cmd(m, e, cmd, btn, iterations, sc);
 }
 
 } /* namespace */
@@ -901,6 +917,61 @@ int oracle_kuka_ik(const void* blob, size_t bytes, const double* q, const double
     for (int i = 0; i < NB; ++i) q_ik[i] = q[i];
     inverse_kinematics(m, k, q, target_pos, q_ik);
     return 0;
+}
+
+} /* extern "C" */
+
+
+/* ---- low-level "bullet-like" world for tests/golden/fake_pybullet.py --------------------------------------
+ * Lets the UNMODIFIED reference env classes (environments/kuka_gym/ *.py) run on the oracle's physics, so that
+ * their own Python logic (action decoding, RNG order, reward, termination, reset sequencing) produces the golden
+ * vectors our env-level restatement is checked against. */
+extern "C" {
+
+struct OkbWorld { KModel m; KEnv e; StepScratch sc; int iterations; };
+
+void* okb_create(const void* blob, size_t bytes) {
+    OkbWorld* w = new OkbWorld();
+    if (!parse_model(blob, bytes, w->m)) { delete w; return NULL; }
+    memset(&w->e, 0, sizeof(KEnv));
+    w->iterations = (int)w->m.sc[KM_SC_SOLVER_ITERS];
+    for (int a = 0; a < 3; ++a) w->e.button_base[a] = w->m.sc[KM_SC_BUTTON_BASE + a];
+    return w;
+}
+void okb_destroy(void* h) { delete (OkbWorld*)h; }
+void okb_reset_world(void* h) {           /* p.resetSimulation(): everything back to the load-time state */
+    OkbWorld* w = (OkbWorld*)h;
+    memset(&w->e, 0, sizeof(KEnv));
+    for (int a = 0; a < 3; ++a) w->e.button_base[a] = w->m.sc[KM_SC_BUTTON_BASE + a];
+    refresh_link_states(w->m, w->e);
+}
+void okb_set_iterations(void* h, int n) { ((OkbWorld*)h)->iterations = n; }
+void okb_set_button_base(void* h, double x, double y) { OkbWorld* w = (OkbWorld*)h; w->e.button_base[0] = x; w->e.button_base[1] = y; }
+void okb_reset_joint(void* h, int body, double q) {  /* p.resetJointState */
+    OkbWorld* w = (OkbWorld*)h; w->e.q[body] = q; w->e.qd[body] = 0.0; refresh_link_states(w->m, w->e);
+}
+void okb_ik(void* h, const double* target_pos, double* q_out) {  /* p.calculateInverseKinematics at the current state */
+    OkbWorld* w = (OkbWorld*)h;
+    Kin k; forward_kinematics(w->m, w->e.q, k);
+    for (int i = 0; i < NB; ++i) q_out[i] = w->e.q[i];
+    inverse_kinematics(w->m, k, w->e.q, target_pos, q_out);
+}
+/* p.stepSimulation() with the motor table accumulated from setJointMotorControl2 calls: 12 x (target, kp, kd, force, maxvel) */
+void okb_step(void* h, const double* motors, int btn_position_control, double btn_target, double btn_kp, double btn_kd, double btn_force) {
+    OkbWorld* w = (OkbWorld*)h;
+    MotorCmd cmd[NB];
+    for (int i = 0; i < NB; ++i) { cmd[i].target = motors[5 * i]; cmd[i].kp = motors[5 * i + 1]; cmd[i].kd = motors[5 * i + 2]; cmd[i].maxforce = motors[5 * i + 3]; cmd[i].maxvel = motors[5 * i + 4]; }
+    ButtonCmd btn; btn.position_control = btn_position_control; btn.target = btn_target; btn.kp = btn_kp; btn.kd = btn_kd; btn.maxforce = btn_force;
+    physics_step_cmd(w->m, w->e, cmd, btn, w->iterations, w->sc);
+}
+/* out[0..11] q, [12..23] qd, [24] glider q, [25..27] link-8 COM, [28..30] button link origin, [31] button manifold, [32] table manifold */
+void okb_get(void* h, double* out) {
+    OkbWorld* w = (OkbWorld*)h; const KEnv& e = w->e;
+    for (int i = 0; i < NB; ++i) { out[i] = e.q[i]; out[NB + i] = e.qd[i]; }
+    out[24] = e.qb;
+    for (int a = 0; a < 3; ++a) out[25 + a] = e.gripper_pos[a];
+    out[28] = e.button_base[0]; out[29] = e.button_base[1]; out[30] = e.button_base[2] + w->m.sc[KM_SC_GLIDER_Z] + e.qb;
+    out[31] = e.contact_button; out[32] = e.contact_table;
 }
 
 } /* extern "C" */

@@ -1,0 +1,95 @@
+"""
+Generate tests/golden/kuka_ref_logic_golden.npz by running the REFERENCE Kuka env classes
+(/root/reference/environments/kuka_gym/kuka_button_gym_env.py, kuka_rand_button_gym_env.py, kuka.py -- unmodified)
+on top of tests/golden/fake_pybullet.py (the oracle's physics behind a pybullet-shaped API).  Build container only:
+
+    python tests/golden/gen_kuka_ref_logic_golden.py
+
+What this pins: every line of the reference's env-level Python (action tables, noise draws, EE clip box, the
+setJointMotorControl2 gains/forces, the 500 + 5 step reset sequence, button target, reward/termination counters,
+step(None), action_repeat, KukaRandButton's extra RNG draws).  What it cannot pin: PyBullet's own arithmetic.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import _ref_stubs  # noqa: E402
+import fake_pybullet  # noqa: E402
+
+_ref_stubs.install(os.path.join(ROOT, "robotics-rl-srl_b200"))
+sys.modules["pybullet"] = fake_pybullet.as_module()      # replace the inert stub by the oracle-backed one
+import torch  # noqa: E402,F401  (the reference imports it)
+
+from environments.kuka_gym.kuka_button_gym_env import KukaButtonGymEnv  # noqa: E402
+from environments.kuka_gym.kuka_rand_button_gym_env import KukaRandButtonGymEnv  # noqa: E402
+
+assert "/root/reference" in sys.modules[KukaButtonGymEnv.__module__].__file__, "must import the reference classes"
+
+CASES = [
+    # tag, class name, kwargs, seed, max env steps recorded
+    ("disc", "KukaButtonGymEnv", dict(is_discrete=True), 0, 700),
+    ("disc_rand_shaped", "KukaButtonGymEnv", dict(is_discrete=True, random_target=True, shape_reward=True), 1, 500),
+    ("cont", "KukaButtonGymEnv", dict(is_discrete=False), 2, 400),
+    ("cont_shaped_up", "KukaButtonGymEnv", dict(is_discrete=False, shape_reward=True, force_down=False), 3, 400),
+    ("disc_rep3_none", "KukaButtonGymEnv", dict(is_discrete=True, action_repeat=3), 4, 300),
+    ("rand_button_cont", "KukaRandButtonGymEnv", dict(is_discrete=False, random_target=True), 5, 400),
+    ("rand_button_disc", "KukaRandButtonGymEnv", dict(is_discrete=True, random_target=True), 6, 500),
+]
+CLASSES = {"KukaButtonGymEnv": KukaButtonGymEnv, "KukaRandButtonGymEnv": KukaRandButtonGymEnv}
+
+
+def make_actions(tag, kwargs, n, seed):
+    rs = np.random.RandomState(500 + seed)
+    if kwargs.get("is_discrete", True):
+        a = rs.randint(0, 6, size=n).astype(np.float64)
+        # a biased descent makes the episodes end through contacts as well as through the step limit
+        a[rs.rand(n) < 0.35] = 4
+        if "none" in tag:
+            a[rs.rand(n) < 0.1] = -1           # -1 encodes step(None)
+        return np.stack([a, np.zeros(n), np.zeros(n)], axis=1)
+    a = rs.uniform(-1, 1, size=(n, 3))
+    a[:, 2] = -np.abs(a[:, 2]) if "up" not in tag else a[:, 2]
+    return a.astype(np.float32).astype(np.float64)
+
+
+def run_case(tag, clsname, kwargs, seed, nsteps):
+    env = CLASSES[clsname](srl_model="ground_truth", **kwargs)
+    env.seed(seed)
+    np.random.seed(1234)                         # the reference's KukaRandButton also draws from the GLOBAL numpy RNG
+    actions = make_actions(tag, kwargs, nsteps, seed)
+    rec = dict(action=actions, obs=[], reward=[], done=[], arm=[], target=[], reset_obs=[], reset_target=[], reset_at=[])
+    t = 0
+    while t < nsteps:
+        o = env.reset()
+        rec["reset_obs"].append(np.asarray(o, np.float64)); rec["reset_target"].append(np.asarray(env.getTargetPos(), np.float64))
+        rec["reset_at"].append(t)
+        done = False
+        while not done and t < nsteps:
+            if kwargs.get("is_discrete", True):
+                a = None if actions[t, 0] < 0 else int(actions[t, 0])
+            else:
+                a = actions[t].astype(np.float32)
+            o, r, done, _ = env.step(a)
+            rec["obs"].append(np.asarray(o, np.float64)); rec["reward"].append(float(r)); rec["done"].append(bool(done))
+            rec["arm"].append(np.asarray(env.getArmPos(), np.float64)); rec["target"].append(np.asarray(env.getTargetPos(), np.float64))
+            t += 1
+    return {k: np.asarray(v) for k, v in rec.items()}
+
+
+def main():
+    out = {}
+    for tag, clsname, kwargs, seed, nsteps in CASES:
+        rec = run_case(tag, clsname, kwargs, seed, nsteps)
+        for k, v in rec.items():
+            out["%s/%s" % (tag, k)] = v
+        print(tag, "steps", len(rec["reward"]), "episodes", len(rec["reset_at"]), "dones", int(rec["done"].sum()), "reward sum %.3f" % rec["reward"].sum())
+    np.savez_compressed(os.path.join(HERE, "kuka_ref_logic_golden.npz"), **out)
+    print("wrote kuka_ref_logic_golden.npz")
+
+
+if __name__ == "__main__":
+    main()

@@ -266,3 +266,59 @@ def test_single_env_classes_on_oracle(use_oracle_backend):
         registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth", action_joints=True)
     with pytest.raises(NotImplementedError):
         registered_env["KukaButtonGymEnv-v0"][0]().reset()             # default raw_pixels: no rasteriser
+
+
+# ---- env-level logic pinned against the REFERENCE classes ---------------------------------------------------
+REF_LOGIC_CASES = {
+    # tag: (class, kwargs, seed) -- must match tests/golden/gen_kuka_ref_logic_golden.py
+    "disc": ("KukaButtonGymEnv-v0", dict(is_discrete=True), 0),
+    "disc_rand_shaped": ("KukaButtonGymEnv-v0", dict(is_discrete=True, random_target=True, shape_reward=True), 1),
+    "cont": ("KukaButtonGymEnv-v0", dict(is_discrete=False), 2),
+    "cont_shaped_up": ("KukaButtonGymEnv-v0", dict(is_discrete=False, shape_reward=True, force_down=False), 3),
+    "disc_rep3_none": ("KukaButtonGymEnv-v0", dict(is_discrete=True, action_repeat=3), 4),
+    "rand_button_cont": ("KukaRandButtonGymEnv-v0", dict(is_discrete=False, random_target=True), 5),
+    "rand_button_disc": ("KukaRandButtonGymEnv-v0", dict(is_discrete=True, random_target=True), 6),
+}
+
+
+def replay_ref_logic_case(tag, pos_tol):
+    """Replay one case recorded from the reference's own Kuka classes (running on the oracle's physics through
+    tests/golden/fake_pybullet.py) through OUR env classes on whatever backend is installed."""
+    from environments.registry import registered_env
+    g = np.load(os.path.join(GOLDEN, "kuka_ref_logic_golden.npz"))
+    env_id, kwargs, seed = REF_LOGIC_CASES[tag]
+    env = registered_env[env_id][0](srl_model="ground_truth", **kwargs)
+    env.seed(seed)
+    actions, obs, reward, done = g[tag + "/action"], g[tag + "/obs"], g[tag + "/reward"], g[tag + "/done"]
+    arm, target = g[tag + "/arm"], g[tag + "/target"]
+    reset_at = list(g[tag + "/reset_at"])
+    n, t, ep = len(reward), 0, 0
+    while t < n:
+        assert reset_at[ep] == t, (tag, "episode boundaries differ", t)
+        o = env.reset()
+        assert np.abs(np.asarray(o) - g[tag + "/reset_obs"][ep]).max() < pos_tol, (tag, "reset obs", ep)
+        assert np.abs(env.getTargetPos() - g[tag + "/reset_target"][ep]).max() < 1e-6, (tag, "reset target", ep)
+        d = False
+        while not d and t < n:
+            if kwargs.get("is_discrete", True):
+                a = None if actions[t, 0] < 0 else int(actions[t, 0])
+            else:
+                a = actions[t].astype(np.float32)
+            o, r, d, _ = env.step(a)
+            assert np.abs(np.asarray(o) - obs[t]).max() < pos_tol, (tag, "obs", t)
+            assert np.abs(np.asarray(env.getArmPos()) - arm[t]).max() < pos_tol and np.abs(env.getTargetPos() - target[t]).max() < 1e-6
+            if kwargs.get("shape_reward", False):
+                assert abs(r - reward[t]) < max(pos_tol, 1e-5), (tag, "reward", t, r, reward[t])
+            else:
+                assert isinstance(r, int) and r == reward[t], (tag, "reward", t, r, reward[t])
+            assert d == bool(done[t]), (tag, "done", t)
+            t += 1
+        ep += 1
+    env.close()
+    return int(done.sum())
+
+
+@pytest.mark.parametrize("tag", sorted(REF_LOGIC_CASES))
+def test_env_logic_matches_reference_classes_on_oracle(tag, use_oracle_backend):
+    # same physics (the oracle) on both sides: only the float32 rounding of the per-step noise through the ABI differs
+    replay_ref_logic_case(tag, 1e-6)

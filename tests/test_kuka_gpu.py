@@ -218,3 +218,13 @@ def test_single_env_classes_on_cuda(cuda_lib):
         assert isinstance(r, int) and info == {}
     assert np.isfinite(o).all()
     env.close()
+
+
+@pytest.mark.parametrize("tag", ["disc", "cont", "disc_rep3_none", "rand_button_disc", "disc_rand_shaped"])
+def test_reference_class_logic_golden_through_cuda(tag, cuda_lib):
+    """Trajectories recorded from the REFERENCE Kuka classes (on the oracle's physics, tests/golden/fake_pybullet.py)
+    replayed through our env classes -> C-ABI -> the fp32 kernel: flags exact, positions within 1e-3 m."""
+    from srl_sim import backend
+    from test_kuka_cpu import replay_ref_logic_case
+    backend.use_library(None, None)
+    replay_ref_logic_case(tag, POS_TOL)
