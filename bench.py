@@ -43,6 +43,20 @@ MOBILE_STATE_BYTES = 2 * 80
 MOBILE_STEP_BYTES = 4 + 8 + 4 + 1     # action in, obs f32[2] + reward + done out (in-kernel actions: no action read)
 
 
+def effective_cores():
+    """Host threads that can actually run: min(visible CPUs, cgroup CPU quota).  The GPU boxes show 128 CPUs but the
+    container's cgroup grants 16 CPUs of time (cpu.max = 1600000 100000); the oracle scales linearly to 16 threads and is
+    flat beyond (scripts/cpu_scaling.py), so that is the core count reported with the CPU numbers."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(round(float(quota) / float(period)))))
+    except Exception:
+        pass
+    return n
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -173,7 +187,7 @@ def run_reference(args):
     if rank != 0:
         return
     spec = workload_spec(args.workload)
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     n, T = spec["n"], spec["T"] if args.workload == "kuka" else 256
     pool = OraclePool(args.workload, n, T, cores)
     for _ in range(args.warmup):
@@ -181,7 +195,8 @@ def run_reference(args):
     times = [pool.step() for _ in range(args.steps)]
     total = sum(times)
     value = n * T * args.steps / total
-    sample = "%d envs x %d steps per step, %d host threads, CPU oracle (PyBullet itself is not installable offline)" % (n, T, pool.threads)
+    sample = ("%d envs x %d steps per step, %d host threads (container CPU quota; %d CPUs visible), CPU oracle "
+              "(PyBullet itself is not installable offline)" % (n, T, pool.threads, os.cpu_count() or 1))
     line = {"impl": "reference", "metric": "env-steps/sec %s ground_truth" % spec["env_id"], "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -315,7 +330,7 @@ def run_b200(args):
             "episodes_finished": int(ep_stats[1].item()),
             "episode_return_mean": float(ep_stats[0].item() / max(1.0, ep_stats[1].item()))}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, os.cpu_count() or 1)
+        line["cpu_baseline"] = cpu_baseline(args.workload, effective_cores())
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

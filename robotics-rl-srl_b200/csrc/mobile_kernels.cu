@@ -203,6 +203,37 @@ __device__ __forceinline__ void mobile_step_env(MobileEnvRegs& e, int a_disc, fl
 
 // Fused T-step rollout; T = 1 is the plain lockstep step.  Auto-reset on done reproduces the
 // SubprocVecEnv worker loop (rl_baselines/utils.py:216-220): the stored obs is the post-reset one.
+//
+// The state update is a short serial chain (add -> compare -> select), but the action / noise streams do not depend
+// on it: they are PREFETCHED two chunks of MOBILE_PF steps ahead into registers (double buffering), so MOBILE_PF
+// independent 128-byte loads per warp are in flight while the previous chunk is being stepped.  Without it the kernel
+// sat at `long_sb` 56 % (one dependent global load per step, ncu round 1).
+constexpr int MOBILE_PF = 16;
+
+template <bool DISCRETE>
+struct ActionChunk {
+    int a[MOBILE_PF];
+    float x[DISCRETE ? 1 : MOBILE_PF], y[DISCRETE ? 1 : MOBILE_PF];
+    float nz[MOBILE_PF];
+};
+
+template <bool DISCRETE>
+__device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE>& c, const void* __restrict__ actions, const float* __restrict__ noise,
+                                           int t0, int T, size_t N, size_t i) {
+#pragma unroll
+    for (int k = 0; k < MOBILE_PF; ++k) {
+        const int t = t0 + k;
+        if (t < T) {
+            const size_t off = (size_t)t * N + i;
+            if (actions) {
+                if (DISCRETE) c.a[k] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
+                else { const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + off); c.x[DISCRETE ? 0 : k] = v.x; c.y[DISCRETE ? 0 : k] = v.y; }
+            }
+            if (noise) c.nz[k] = __ldg(noise + off);
+        }
+    }
+}
+
 template <int KIND, bool DISCRETE>
 __global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, int T, const void* __restrict__ actions,
                                                             const float* __restrict__ noise, float* __restrict__ obs,
@@ -220,44 +251,48 @@ __global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, 
     mobile_load(m, i, e, TWO);
     bool targets_dirty = false;
     const size_t N = (size_t)n;
-#pragma unroll 4
-    for (int t = 0; t < T; ++t) {
-        const size_t off = (size_t)t * N + (size_t)i;
-        int a_disc = 0;
-        float a0 = 0.f, a1 = 0.f;
-        if (actions) {
-            if (DISCRETE) {
-                a_disc = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
+    ActionChunk<DISCRETE> cur, nxt;
+    load_chunk<DISCRETE>(cur, actions, noise, 0, T, N, (size_t)i);
+    for (int t0 = 0; t0 < T; t0 += MOBILE_PF) {
+        load_chunk<DISCRETE>(nxt, actions, noise, t0 + MOBILE_PF, T, N, (size_t)i);   // in flight while `cur` is stepped
+#pragma unroll
+        for (int k = 0; k < MOBILE_PF; ++k) {
+            const int t = t0 + k;
+            if (t >= T) break;
+            const size_t off = (size_t)t * N + (size_t)i;
+            int a_disc = 0;
+            float a0 = 0.f, a1 = 0.f;
+            if (actions) {
+                if (DISCRETE) a_disc = cur.a[k];
+                else { a0 = cur.x[DISCRETE ? 0 : k]; a1 = cur.y[DISCRETE ? 0 : k]; }
             } else {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(actions) + off);
-                a0 = a.x; a1 = a.y;
+                const uint4 r = philox4x32_10(seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
+                if (DISCRETE) {
+                    a_disc = (int)__umulhi(r.x, NA);
+                } else {
+                    a0 = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0);
+                    a1 = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0);
+                }
             }
-        } else {
-            const uint4 r = philox4x32_10(seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
-            if (DISCRETE) {
-                a_disc = (int)__umulhi(r.x, NA);
-            } else {
-                a0 = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0);
-                a1 = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0);
+            // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
+            const double dv = noise ? __dadd_rn(DELTA_POS, (double)cur.nz[k]) : DELTA_POS;
+            e.total_steps += 1;
+            float r_out;
+            bool d_out;
+            mobile_step_env<KIND, DISCRETE>(e, a_disc, a0, a1, dv, shape_reward, max_steps, r_out, d_out);
+            if (rew) rew[off] = r_out;
+            if (done) done[off] = d_out ? 1 : 0;
+            if (d_out) {
+                if (ep_ret) ep_ret[off] = (float)e.ep_ret;
+                if (ep_len) ep_len[off] = (int32_t)e.ep_len;
+                if (auto_reset) {
+                    mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
+                    targets_dirty = true;
+                }
             }
+            if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);
         }
-        // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
-        const double dv = noise ? __dadd_rn(DELTA_POS, (double)__ldg(noise + off)) : DELTA_POS;
-        e.total_steps += 1;
-        float r_out;
-        bool d_out;
-        mobile_step_env<KIND, DISCRETE>(e, a_disc, a0, a1, dv, shape_reward, max_steps, r_out, d_out);
-        if (rew) rew[off] = r_out;
-        if (done) done[off] = d_out ? 1 : 0;
-        if (d_out) {
-            if (ep_ret) ep_ret[off] = (float)e.ep_ret;
-            if (ep_len) ep_len[off] = (int32_t)e.ep_len;
-            if (auto_reset) {
-                mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
-                targets_dirty = true;
-            }
-        }
-        if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);
+        cur = nxt;
     }
     mobile_store(m, i, e, targets_dirty, TWO);
 }
@@ -265,7 +300,8 @@ __global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, 
 template <int KIND>
 int launch_rollout_kind(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
-    const int block = 64;
+    // one warp per CTA below ~19k envs: spreads the (latency-bound) warps over all 148 SMs
+    const int block = s->n <= 148 * 128 ? 32 : 64;
     const int grid = (s->n + block - 1) / block;
     if (s->cfg.is_discrete)
         mobile_rollout_kernel<KIND, true><<<grid, block, 0, st>>>(s->mob, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
