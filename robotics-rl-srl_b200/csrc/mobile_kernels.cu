@@ -25,7 +25,6 @@ constexpr double MAX_X = 4.0, MAX_Y = 4.0, MIN_X = 0.0, MIN_Y = 0.0;
 constexpr double DELTA_POS = 0.1;
 constexpr double ROBOT_WIDTH = 0.2, ROBOT_LENGTH = 0.325 * 2;
 constexpr double COLLISION_MARGIN = 0.1;
-constexpr double REWARD_DIST_THRESHOLD = 0.4;
 constexpr double LINE_REWARD_DIST_THRESHOLD = 0.1, LINE_ROBOT_OFFSET = 0.2;  // line_target_env.py:3-4
 
 struct MobileEnvRegs {
@@ -143,76 +142,30 @@ __global__ void __launch_bounds__(128) mobile_reset_kernel(MobileDev m, int n, c
     if (obs) mobile_store_obs<KIND>(e, obs, (size_t)i);
 }
 
-// One env step (mobile_robot_env.py:235-280 + :336-363), state in registers.
-template <int KIND, bool DISCRETE>
-__device__ __forceinline__ void mobile_step_env(MobileEnvRegs& e, int a_disc, float a0, float a1, double dv,
-                                                bool shape_reward, int max_steps, float& reward_out, bool& done_out) {
-    e.has_bumped = 0;  // :237
-    double ax = 0.0, ay = 0.0;
-    if (DISCRETE) {
-        if (KIND == SRL_ENV_MOBILE_1D) {
-            ax = (a_disc & 1) ? dv : -dv;  // 1D_env.py:115
-        } else {
-            const int a = a_disc & 3;      // :242-243
-            ax = (a == 0) ? -dv : (a == 1) ? dv : 0.0;
-            ay = (a == 2) ? -dv : (a == 3) ? dv : 0.0;
-        }
-    } else {
-        // float32 action array * python float -> float32 product, then += into float64 (:250,255)
-        const float fdv = (float)dv;
-        ax = (double)__fmul_rn(fmaxf(fminf(a0, 1.0f), -1.0f), fdv);
-        ay = (double)__fmul_rn(fmaxf(fminf(a1, 1.0f), -1.0f), fdv);
-    }
-    const double prev_x = e.px, prev_y = e.py;  // :254
-    e.px = __dadd_rn(e.px, ax);
-    if (KIND != SRL_ENV_MOBILE_1D) e.py = __dadd_rn(e.py, ay);
-    // Handle collisions (:257-263): x margin uses ROBOT_LENGTH, y margin uses ROBOT_WIDTH
-    constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;
-    bool bumped = (e.px < mx) || (e.px > MAX_X - mx);
-    if (KIND != SRL_ENV_MOBILE_1D) bumped = bumped || (e.py < my) || (e.py > MAX_Y - my);
-    if (bumped) { e.px = prev_x; e.py = prev_y; }
-    e.has_bumped = bumped ? 1 : 0;
-    e.counter += 1;  // :268
-
-    // _reward (:345-363)
-    const double tx = e.current_target ? e.t1x : e.t0x;
-    const double ty = e.current_target ? e.t1y : e.t0y;
-    double distance, thr = REWARD_DIST_THRESHOLD;
-    if (KIND == SRL_ENV_MOBILE_LINE_TARGET) {
-        distance = fabs(__dsub_rn(__dsub_rn(tx, LINE_ROBOT_OFFSET), e.px));  // line_target_env.py:113
-        thr = LINE_REWARD_DIST_THRESHOLD;
-    } else if (KIND == SRL_ENV_MOBILE_1D) {
-        const double dx = __dsub_rn(tx, e.px);
-        distance = __dsqrt_rn(__dmul_rn(dx, dx));
-    } else {
-        const double dx = __dsub_rn(tx, e.px), dy = __dsub_rn(ty, e.py);
-        distance = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));  // np.linalg.norm = sqrt(x.dot(x))
-    }
-    double reward = 0.0;
-    if (distance <= thr) {
-        reward = 1.0;
-        if (KIND == SRL_ENV_MOBILE_2TARGET && e.current_target < 1) e.current_target += 1;  // 2target_env.py:172-173
-    }
-    if (bumped) reward = -1.0;
-    if (shape_reward) reward = -distance;
-    e.ep_ret = __dadd_rn(e.ep_ret, reward);
-    e.ep_len += 1.0;
-    reward_out = (float)reward;
-    done_out = e.counter > max_steps;  // _termination (:336-343); `terminated` is never set
-}
+// sqrt_rn(s) <= 0.4  <=>  s <= S_THR_04 for every non-negative double s (sqrt is monotone and correctly rounded; the
+// constant is the largest double whose rounded square root does not exceed 0.4, found by exact rational arithmetic).
+// It lets the unshaped reward test `np.linalg.norm(.) <= REWARD_DIST_THRESHOLD` (:353) skip the square root BIT-EXACTLY.
+constexpr double S_THR_04 = 0x1.47ae147ae147cp-3;
 
 // Fused T-step rollout; T = 1 is the plain lockstep step.  Auto-reset on done reproduces the
 // SubprocVecEnv worker loop (rl_baselines/utils.py:216-220): the stored obs is the post-reset one.
 //
-// The state update is a short serial chain (add -> compare -> select), but the action / noise streams do not depend
-// on it: they are PREFETCHED two chunks of MOBILE_PF steps ahead into registers (double buffering), so MOBILE_PF
-// independent 128-byte loads per warp are in flight while the previous chunk is being stepped.  Without it the kernel
-// sat at `long_sb` 56 % (one dependent global load per step, ncu round 1).
-constexpr int MOBILE_PF = 16;
+// Throughput structure (ncu round 1: one dependent global load + a ~900-cycle dependent fp64 chain per step, `long_sb` 56 %):
+//  * the action / noise streams do not depend on the state: they are PREFETCHED a chunk of MOBILE_PF steps ahead into
+//    registers (double buffering), MOBILE_PF independent 128-byte loads per warp in flight;
+//  * each chunk is stepped in TWO PASSES.  Pass 1 is the only truly serial part -- position += action, bump test, revert,
+//    step counter, episode end / reset -- and records (target - position) per step.  Pass 2 turns those into distance,
+//    reward, observation and the HBM stores; its MOBILE_PF steps are independent, so the long-latency fp64 work
+//    (sqrt, conversions) overlaps instead of serialising.
+//  * the chunk is kept SHORT (4 steps): with one or two warps per SM nothing hides instruction fetch, and a 16-step
+//    unrolled body (54 KB of SASS) ran from L2 -- `no_inst` 29 %, 0.50 ms; 8 steps 0.44 ms; 4 steps 0.33 ms (measured; an extra
+//    `prefetch.global.L2` 32 steps ahead made it slower, 0.42 ms, and was dropped).
+// Arithmetic per step is unchanged (same operations, same order), so results stay bit-exact.
+constexpr int MOBILE_PF = 4;        // steps per chunk: the unrolled chunk body must stay small (see below)
 
 template <bool DISCRETE>
 struct ActionChunk {
-    int a[MOBILE_PF];
+    int a[DISCRETE ? MOBILE_PF : 1];
     float x[DISCRETE ? 1 : MOBILE_PF], y[DISCRETE ? 1 : MOBILE_PF];
     float nz[MOBILE_PF];
 };
@@ -226,7 +179,7 @@ __device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE>& c, const void*
         if (t < T) {
             const size_t off = (size_t)t * N + i;
             if (actions) {
-                if (DISCRETE) c.a[k] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
+                if (DISCRETE) c.a[DISCRETE ? k : 0] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
                 else { const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + off); c.x[DISCRETE ? 0 : k] = v.x; c.y[DISCRETE ? 0 : k] = v.y; }
             }
             if (noise) c.nz[k] = __ldg(noise + off);
@@ -246,6 +199,7 @@ __global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, 
     constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
     constexpr int D = (KIND == SRL_ENV_MOBILE_1D) ? 1 : 2;
     constexpr uint32_t NA = (KIND == SRL_ENV_MOBILE_1D) ? 2u : 4u;
+    constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;  // :257-258
     const uint64_t genv = env_offset + (uint64_t)i;
     MobileEnvRegs e;
     mobile_load(m, i, e, TWO);
@@ -255,42 +209,113 @@ __global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, 
     load_chunk<DISCRETE>(cur, actions, noise, 0, T, N, (size_t)i);
     for (int t0 = 0; t0 < T; t0 += MOBILE_PF) {
         load_chunk<DISCRETE>(nxt, actions, noise, t0 + MOBILE_PF, T, N, (size_t)i);   // in flight while `cur` is stepped
+        // ---------------- pass 1: the serial state chain (mobile_robot_env.py:237-268) ----------------
+        double ddx[MOBILE_PF], ddy[MOBILE_PF];   // what _reward() and getSRLState() are made of: target - position
+        uint32_t bump_mask = 0u, done_mask = 0u, obs_done_mask = 0u, reach_mask = 0u;
+        const double ep_ret0 = e.ep_ret, ep_len0 = e.ep_len;   // the episode sums belong to pass 2
 #pragma unroll
         for (int k = 0; k < MOBILE_PF; ++k) {
             const int t = t0 + k;
-            if (t >= T) break;
-            const size_t off = (size_t)t * N + (size_t)i;
-            int a_disc = 0;
-            float a0 = 0.f, a1 = 0.f;
-            if (actions) {
-                if (DISCRETE) a_disc = cur.a[k];
-                else { a0 = cur.x[DISCRETE ? 0 : k]; a1 = cur.y[DISCRETE ? 0 : k]; }
-            } else {
-                const uint4 r = philox4x32_10(seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
-                if (DISCRETE) {
-                    a_disc = (int)__umulhi(r.x, NA);
+            if (t < T) {
+                int a_disc = 0;
+                float a0 = 0.f, a1 = 0.f;
+                if (actions) {
+                    if (DISCRETE) a_disc = cur.a[DISCRETE ? k : 0];
+                    else { a0 = cur.x[DISCRETE ? 0 : k]; a1 = cur.y[DISCRETE ? 0 : k]; }
                 } else {
-                    a0 = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0);
-                    a1 = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0);
+                    const uint4 r = philox4x32_10(seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
+                    if (DISCRETE) a_disc = (int)__umulhi(r.x, NA);
+                    else { a0 = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0); a1 = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0); }
+                }
+                // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
+                const double dv = noise ? __dadd_rn(DELTA_POS, (double)cur.nz[k]) : DELTA_POS;
+                e.total_steps += 1;
+                double ax = 0.0, ay = 0.0;
+                if (DISCRETE) {
+                    if (KIND == SRL_ENV_MOBILE_1D) ax = (a_disc & 1) ? dv : -dv;  // 1D_env.py:115
+                    else { const int a = a_disc & 3; ax = (a == 0) ? -dv : (a == 1) ? dv : 0.0; ay = (a == 2) ? -dv : (a == 3) ? dv : 0.0; }  // :242-243
+                } else {
+                    // float32 action array * python float -> float32 product, then += into float64 (:250,255)
+                    const float fdv = (float)dv;
+                    ax = (double)__fmul_rn(fmaxf(fminf(a0, 1.0f), -1.0f), fdv);
+                    ay = (double)__fmul_rn(fmaxf(fminf(a1, 1.0f), -1.0f), fdv);
+                }
+                const double prev_x = e.px, prev_y = e.py;  // :254
+                e.px = __dadd_rn(e.px, ax);
+                if (KIND != SRL_ENV_MOBILE_1D) e.py = __dadd_rn(e.py, ay);
+                bool bumped = (e.px < mx) || (e.px > MAX_X - mx);   // :257-263
+                if (KIND != SRL_ENV_MOBILE_1D) bumped = bumped || (e.py < my) || (e.py > MAX_Y - my);
+                if (bumped) { e.px = prev_x; e.py = prev_y; bump_mask |= 1u << k; }
+                e.has_bumped = bumped ? 1 : 0;
+                e.counter += 1;  // :268
+                const double tx = e.current_target ? e.t1x : e.t0x, ty = e.current_target ? e.t1y : e.t0y;
+                if (KIND == SRL_ENV_MOBILE_LINE_TARGET) {
+                    const double lx = __dsub_rn(tx, LINE_ROBOT_OFFSET);      // line_target_env.py:35-40,113
+                    ddx[k] = __dsub_rn(lx, e.px); ddy[k] = __dsub_rn(lx, e.py);
+                } else {
+                    ddx[k] = __dsub_rn(tx, e.px); ddy[k] = (KIND == SRL_ENV_MOBILE_1D) ? 0.0 : __dsub_rn(ty, e.py);
+                }
+                if (TWO) {  // the target switch feeds later steps: decide it here (2target_env.py:170-173)
+                    const double sq = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k]));
+                    if (sq <= S_THR_04) {
+                        reach_mask |= 1u << k;
+                        if (e.current_target < 1) {
+                            e.current_target += 1;   // the observation of THIS step is already relative to the new target
+                            obs_done_mask |= 1u << k;
+                            if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);
+                        }
+                    }
+                }
+                if (e.counter > max_steps) {  // _termination (:336-343); `terminated` is never set
+                    done_mask |= 1u << k;
+                    if (auto_reset) {
+                        mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
+                        targets_dirty = true;
+                        obs_done_mask |= 1u << k;
+                        if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);   // post-reset observation
+                    }
                 }
             }
-            // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
-            const double dv = noise ? __dadd_rn(DELTA_POS, (double)cur.nz[k]) : DELTA_POS;
-            e.total_steps += 1;
-            float r_out;
-            bool d_out;
-            mobile_step_env<KIND, DISCRETE>(e, a_disc, a0, a1, dv, shape_reward, max_steps, r_out, d_out);
-            if (rew) rew[off] = r_out;
-            if (done) done[off] = d_out ? 1 : 0;
-            if (d_out) {
-                if (ep_ret) ep_ret[off] = (float)e.ep_ret;
-                if (ep_len) ep_len[off] = (int32_t)e.ep_len;
-                if (auto_reset) {
-                    mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
-                    targets_dirty = true;
+        }
+        // ---------------- pass 2: rewards and outputs, independent across the chunk (:345-363) ----------------
+        e.ep_ret = ep_ret0; e.ep_len = ep_len0;
+#pragma unroll
+        for (int k = 0; k < MOBILE_PF; ++k) {
+            const int t = t0 + k;
+            if (t < T) {
+                const size_t off = (size_t)t * N + (size_t)i;
+                const bool bumped = (bump_mask >> k) & 1u, is_done = (done_mask >> k) & 1u;
+                double reward;
+                if (shape_reward) {
+                    double distance;
+                    if (KIND == SRL_ENV_MOBILE_LINE_TARGET) distance = fabs(ddx[k]);
+                    else if (KIND == SRL_ENV_MOBILE_1D) distance = __dsqrt_rn(__dmul_rn(ddx[k], ddx[k]));
+                    else distance = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])));  // np.linalg.norm = sqrt(x.dot(x))
+                    reward = -distance;
+                } else {
+                    bool reached;
+                    if (KIND == SRL_ENV_MOBILE_LINE_TARGET) reached = fabs(ddx[k]) <= LINE_REWARD_DIST_THRESHOLD;
+                    else if (TWO) reached = (reach_mask >> k) & 1u;
+                    else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(ddx[k], ddx[k]) <= S_THR_04;
+                    else reached = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])) <= S_THR_04;
+                    reward = reached ? 1.0 : 0.0;
+                    if (bumped) reward = -1.0;
+                }
+                e.ep_ret = __dadd_rn(e.ep_ret, reward);
+                e.ep_len += 1.0;
+                if (rew) rew[off] = (float)reward;
+                if (done) done[off] = is_done ? 1 : 0;
+                if (is_done) {
+                    if (ep_ret) ep_ret[off] = (float)e.ep_ret;
+                    if (ep_len) ep_len[off] = (int32_t)e.ep_len;
+                    if (auto_reset) { e.ep_ret = 0.0; e.ep_len = 0.0; }
+                }
+                if (obs && !((obs_done_mask >> k) & 1u)) {
+                    // getSRLState = getGroundTruth() - getTargetPos() = -(target - position): negation is exact
+                    if (KIND == SRL_ENV_MOBILE_1D) obs[(size_t)t * N + (size_t)i] = -(float)ddx[k];
+                    else reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(-(float)ddx[k], -(float)ddy[k]);
                 }
             }
-            if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);
         }
         cur = nxt;
     }
