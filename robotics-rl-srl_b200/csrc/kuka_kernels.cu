@@ -317,10 +317,14 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
         P.snap_q[i] = (float)r[KM_B_QINIT];
     }
     P.nsph = (int)d[KM_H_NSPHERE];
+    P.sph_min_body = KK_NB; P.sph_reach = 0.f;
     for (int k = 0; k < P.nsph; ++k) {
         const double* sp = d + (int)d[KM_H_SPHERE_OFF] + k * KM_SPHERE_STRIDE;
         P.sph_body[k] = (int)sp[KM_S_BODY]; P.sph_r[k] = (float)sp[KM_S_RADIUS];
         for (int a = 0; a < 3; ++a) P.sph_c[k][a] = (float)sp[KM_S_CENTER + a];
+        if (P.sph_body[k] < P.sph_min_body) P.sph_min_body = P.sph_body[k];
+        const float reach = sqrtf(P.sph_c[k][0] * P.sph_c[k][0] + P.sph_c[k][1] * P.sph_c[k][1] + P.sph_c[k][2] * P.sph_c[k][2]) + P.sph_r[k];
+        if (reach > P.sph_reach) P.sph_reach = reach * 1.0001f;
     }
     for (int a = 0; a < 3; ++a) { P.base[a] = (float)sc[KM_SC_BASE_POS + a]; P.btn_base[a] = (float)sc[KM_SC_BUTTON_BASE + a]; P.ee_init[a] = (float)sc[KM_SC_EE_INIT + a]; }
     P.gz = (float)sc[KM_SC_GRAVITY_Z]; P.dt = (float)dt; P.inv_dt = (float)(1.0 / dt);

@@ -32,6 +32,8 @@ struct KukaParams {
     int   sph_body[KM_MAX_SPHERES];
     float sph_c[KM_MAX_SPHERES][3];
     float sph_r[KM_MAX_SPHERES];
+    int   sph_min_body;    // lowest body index that carries a sphere
+    float sph_reach;       // max over spheres of |centre| + radius: no sphere surface is further from its body origin
     // ---- scene ----
     float base[3];
     float gz, dt, inv_dt;
