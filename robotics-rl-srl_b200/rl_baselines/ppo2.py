@@ -1,0 +1,171 @@
+"""
+PPO2 consumer of the batched simulator (BASELINE config 3).
+
+The reference trains with stable-baselines' TF-1.8 ``PPO2`` through ``rl_baselines/rl_algorithm/ppo2.py:58-73`` and
+``rl_baselines/base_classes.py:214-253``; neither TensorFlow nor stable-baselines exists in this image, so the algorithm is
+restated in PyTorch with the reference's hyper-parameters (n_steps=128, nminibatches=4, noptepochs=4, lr=2.5e-4 * f,
+ent_coef=0.01, vf_coef=0.5, cliprange=0.2, gamma=0.99, lam=0.95, max_grad_norm=0.5) and stable-baselines' ``MlpPolicy``
+(two separate 64-64 tanh networks for policy and value).  Everything -- envs, observation normalisation
+(``VecNormalize(norm_obs=True, norm_reward=False)``, rl_baselines/utils.py:224-227), policy, GAE, optimisation -- stays on the
+GPU: the env step is ``srl_sim_step`` on torch tensors, no host round trip per step.
+This is a CONSUMER of the hot path (library GEMMs via torch are fine here); the product is the simulator underneath.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from srl_sim.vec_env import BatchedSRLVecEnv
+
+PPO2_DEFAULTS = dict(n_steps=128, ent_coef=0.01, learning_rate=2.5e-4, vf_coef=0.5, max_grad_norm=0.5, gamma=0.99, lam=0.95,
+                     nminibatches=4, noptepochs=4, cliprange=0.2)   # rl_algorithm/ppo2.py:58-72
+
+
+class MlpPolicy(nn.Module):
+    """stable-baselines 2.5 ``MlpPolicy``: separate pi / vf towers, 2 x 64 tanh, orthogonal init."""
+
+    def __init__(self, obs_dim, n_actions=None, action_dim=None):
+        super().__init__()
+        self.discrete = n_actions is not None
+        out = n_actions if self.discrete else action_dim
+
+        def tower(last, gain):
+            layers = [nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, last)]
+            for m in layers:
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, np.sqrt(2)); nn.init.zeros_(m.bias)
+            nn.init.orthogonal_(layers[-1].weight, gain)
+            return nn.Sequential(*layers)
+        self.pi, self.vf = tower(out, 0.01), tower(1, 1.0)
+        if not self.discrete:
+            self.logstd = nn.Parameter(torch.zeros(out))
+
+    def dist(self, obs):
+        logits = self.pi(obs)
+        if self.discrete:
+            return torch.distributions.Categorical(logits=logits)
+        return torch.distributions.Normal(logits, self.logstd.exp())
+
+    def act(self, obs):
+        d = self.dist(obs)
+        a = d.sample()
+        logp = d.log_prob(a) if self.discrete else d.log_prob(a).sum(-1)
+        return a, logp, self.vf(obs).squeeze(-1)
+
+    def evaluate(self, obs, actions):
+        d = self.dist(obs)
+        logp = d.log_prob(actions) if self.discrete else d.log_prob(actions).sum(-1)
+        ent = d.entropy() if self.discrete else d.entropy().sum(-1)
+        return logp, ent, self.vf(obs).squeeze(-1)
+
+
+class RunningNorm(object):
+    """VecNormalize's observation filter on the device: running mean / var, clip to +-10."""
+
+    def __init__(self, dim, device, clip=10.0, eps=1e-8):
+        self.mean = torch.zeros(dim, device=device, dtype=torch.float64)
+        self.var = torch.ones(dim, device=device, dtype=torch.float64)
+        self.count, self.clip, self.eps = 1e-4, clip, eps
+
+    def update(self, x):
+        x = x.double()
+        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        delta, tot = bm - self.mean, self.count + bc
+        self.mean = self.mean + delta * bc / tot
+        self.var = (self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot) / tot
+        self.count = tot
+
+    def __call__(self, x, update=True):
+        if update:
+            self.update(x)
+        return torch.clamp((x - self.mean.float()) / torch.sqrt(self.var.float() + self.eps), -self.clip, self.clip)
+
+
+def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1):
+    """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps)."""
+    hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
+    torch.manual_seed(seed)
+    env_kwargs = dict(env_kwargs or {})
+    env = BatchedSRLVecEnv(env_id, num_envs, seed=seed, device=device, **env_kwargs)
+    dev = env.backend.torch_device
+    D = env.observation_space.shape[0]
+    if env.is_discrete:
+        policy = MlpPolicy(D, n_actions=env.action_space.n).to(dev)
+    else:
+        policy = MlpPolicy(D, action_dim=env.action_space.shape[0]).to(dev)
+    opt = torch.optim.Adam(policy.parameters(), lr=hp["learning_rate"], eps=1e-5)
+    norm = RunningNorm(D, dev)
+    N, T = num_envs, hp["n_steps"]
+    n_updates = max(1, int(num_timesteps) // (N * T))
+    if log_dir:
+        os.makedirs(log_dir, exist_ok=True)
+        with open(os.path.join(log_dir, "args.json"), "w") as f:       # train.py:282-283
+            json.dump(dict(env=env_id, algo="ppo2", num_cpu=N, num_timesteps=num_timesteps, seed=seed, srl_model="ground_truth", **hp), f)
+        with open(os.path.join(log_dir, "env_globals.json"), "w") as f:  # train.py:285-315
+            json.dump({k: v for k, v in env_kwargs.items() if isinstance(v, (int, float, str, bool))}, f)
+    env.sim.reset(obs_out=env._obs, stream=env.backend.stream())
+    obs = norm(env._obs.clone())
+    buf = dict(obs=torch.empty((T, N, D), device=dev), act=torch.empty((T, N) if env.is_discrete else (T, N, env.sim.action_dim), device=dev,
+                                                                       dtype=torch.int64 if env.is_discrete else torch.float32),
+               logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev), rew=torch.empty((T, N), device=dev),
+               done=torch.empty((T, N), device=dev))
+    history, ep_returns = [], []
+    t_start = time.time()
+    for update in range(1, n_updates + 1):
+        frac = 1.0 - (update - 1.0) / n_updates
+        for g in opt.param_groups:
+            g["lr"] = hp["learning_rate"] * frac                          # learning_rate = lambda f: f * 2.5e-4
+        with torch.no_grad():
+            for t in range(T):
+                a, logp, v = policy.act(obs)
+                buf["obs"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = obs, a, logp, v
+                act_dev = a.to(torch.int32) if env.is_discrete else torch.clamp(a, -1, 1).contiguous()
+                o, r, d, ep_ret, _ = env.step_tensors(act_dev)            # one kernel launch, tensors stay on the GPU
+                buf["rew"][t], buf["done"][t] = r, d.float()
+                if bool(d.any()):
+                    ep_returns.extend(ep_ret[d.bool()].tolist())
+                obs = norm(o.clone())
+            last_val = policy.vf(obs).squeeze(-1)
+            # GAE(lambda)
+            adv = torch.zeros((T, N), device=dev)
+            lastgae = torch.zeros(N, device=dev)
+            for t in reversed(range(T)):
+                nonterminal = 1.0 - buf["done"][t]
+                nextval = last_val if t == T - 1 else buf["val"][t + 1]
+                delta = buf["rew"][t] + hp["gamma"] * nextval * nonterminal - buf["val"][t]
+                lastgae = delta + hp["gamma"] * hp["lam"] * nonterminal * lastgae
+                adv[t] = lastgae
+            ret = adv + buf["val"]
+        flat = {k: v.reshape((T * N,) + v.shape[2:]) for k, v in buf.items()}
+        flat_adv, flat_ret = adv.reshape(-1), ret.reshape(-1)
+        mb = T * N // hp["nminibatches"]
+        for _ in range(hp["noptepochs"]):
+            perm = torch.randperm(T * N, device=dev)
+            for s in range(0, T * N, mb):
+                idx = perm[s:s + mb]
+                logp, ent, v = policy.evaluate(flat["obs"][idx], flat["act"][idx])
+                a_mb = flat_adv[idx]
+                a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+                ratio = torch.exp(logp - flat["logp"][idx])
+                pg = torch.max(-a_mb * ratio, -a_mb * torch.clamp(ratio, 1 - hp["cliprange"], 1 + hp["cliprange"])).mean()
+                vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -hp["cliprange"], hp["cliprange"])
+                vf_loss = 0.5 * torch.max((v - flat_ret[idx]) ** 2, (vclip - flat_ret[idx]) ** 2).mean()
+                loss = pg - hp["ent_coef"] * ent.mean() + hp["vf_coef"] * vf_loss
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(policy.parameters(), hp["max_grad_norm"])
+                opt.step()
+        steps = update * N * T
+        fps = steps / (time.time() - t_start)
+        window = ep_returns[-max(40, N):]                                  # episode_window (train.py:180)
+        mean_ret = float(np.mean(window)) if window else float("nan")
+        history.append((steps, mean_ret, fps))
+        if verbose:
+            print("update %d/%d  steps %d  mean episode return %.3f  episodes %d  fps %.0f" % (update, n_updates, steps, mean_ret, len(ep_returns), fps))
+    if log_dir:
+        torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean, obs_var=norm.var), os.path.join(log_dir, "ppo2_model.pt"))
+    env.close()
+    return history
