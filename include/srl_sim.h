@@ -123,8 +123,9 @@ int srl_sim_create(srl_sim** out, int env_kind, int num_envs, int device, const 
  *   MobileRobot R=6: x_start, y_start, x_target, y_target, x_target2, y_target2 -- the final
  *                    values, not the raw uniforms (mobile_robot_env.py:168-181,
  *                    mobile_robot_2target_env.py:52-69); unused slots are ignored
- *   Kuka        R=17: button x_pos, y_pos, then 5 x (dx,dy,dz) random init actions
- *                     (kuka_button_gym_env.py:227-234,250-268)
+ *   Kuka        R=18: button x_pos, y_pos, then 5 x (dx,dy,dz) random init actions
+ *                     (kuka_button_gym_env.py:227-234,250-268), then the signed button speed of
+ *                     KukaMovingButtonGymEnv (kuka_moving_button_gym_env.py:33; 0 for the other kinds)
  * `obs_out` (nullable): f32[N, D] observation after reset (rows of unmasked envs untouched). */
 int srl_sim_reset(srl_sim* sim, const uint8_t* mask, const double* reset_draws, float* obs_out,
                   void* stream);

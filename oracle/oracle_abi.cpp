@@ -81,7 +81,7 @@ float srl_sim_last_kernel_ms(srl_sim*) { return -1.0f; }
 int srl_sim_reset(srl_sim* s, const uint8_t* mask, const double* reset_draws, float* obs_out, void*) {
     if (!s) { oracle_set_error("reset: null handle"); return 1; }
     const int D = srl_sim_obs_dim(s);
-    const int R = is_mobile(s->kind) ? 6 : 17;
+    const int R = is_mobile(s->kind) ? 6 : 18;
     for (int i = 0; i < s->n; ++i) {
         if (mask && !mask[i]) continue;
         const double* d = reset_draws ? reset_draws + (size_t)i * R : NULL;

@@ -183,7 +183,8 @@ struct KEnv {
     double qb, qdb;          /* button glider */
     double ee[3], ee_angle;  /* commanded end-effector pose, kuka.py:73-74 */
     double button_base[3];   /* button base link origin */
-    double button_pos[3];    /* target, frozen at reset (:273-274) */
+    double button_pos[3];    /* target, frozen at reset (:273-274); y slides in the moving-button variant */
+    double btn_speed;        /* kuka_moving_button_gym_env.py:33 */
     int counter, n_contacts, n_outside, terminated;
     int contact_button, contact_table; /* manifold flags of the last stepSimulation */
     double gripper_pos[3], ee_pos[3];  /* link states after the last stepSimulation */
@@ -698,8 +699,9 @@ KukaWorld* oracle_kuka_create(srl_sim* s, const void* blob, size_t bytes) {
     w->iterations = s->cfg.solver_iterations > 0 ? s->cfg.solver_iterations : (int)w->m.sc[KM_SC_SOLVER_ITERS];
     w->max_steps = s->cfg.max_steps > 0 ? s->cfg.max_steps : 1000; /* MAX_STEPS, :17 and kuka_rand_button_gym_env.py:3 */
     if (s->cfg.timestep > 0) w->m.sc[KM_SC_TIMESTEP] = (double)s->cfg.timestep;
-    if (s->kind != SRL_ENV_KUKA_BUTTON && s->kind != SRL_ENV_KUKA_RAND_BUTTON) {
-        oracle_set_error("kuka: env kind %d is not implemented yet", s->kind); delete w; return NULL;
+    if (s->kind == SRL_ENV_KUKA_MOVING_BUTTON && s->cfg.max_steps <= 0) w->max_steps = 1500; /* kuka_moving_button_gym_env.py:3,28 */
+    if (s->kind == SRL_ENV_KUKA_2BUTTON) {
+        oracle_set_error("Kuka2ButtonGymEnv-v0 (two buttons, null-space IK) is not implemented"); delete w; return NULL;
     }
     w->envs.resize(s->n);
     memset(w->envs.data(), 0, sizeof(KEnv) * (size_t)s->n);
@@ -713,10 +715,11 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
     KukaWorld& w = *s->kuka;
     KEnv& e = w.envs[i];
     const uint32_t episode = e.episode, total = e.total_steps;
-    double d[17];
+    double d[18];
     if (draws) {
         memcpy(d, draws, sizeof(d));
     } else {
+        d[17] = 0.0;
         const uint64_t genv = s->cfg.global_env_offset + (uint64_t)i;
         uint32_t r[4];
         philox4x32_10(s->seed, genv, episode, PHILOX_PURPOSE_RESET0 + 0, r);
@@ -739,9 +742,14 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
                 d[2 + 3 * k] = d[3 + 3 * k] = d[4 + 3 * k] = sign * 0.0035;
             }
         }
+        if (s->kind == SRL_ENV_KUKA_MOVING_BUTTON) { /* BUTTON_SPEED * np_random.choice([-1, 1]) */
+            philox4x32_10(s->seed, genv, episode, PHILOX_PURPOSE_RESET0 + 6, r);
+            d[17] = (r[0] & 1u) ? 0.001 : -0.001;
+        }
     }
     e = w.snapshot;
     e.episode = episode + 1; e.total_steps = total;
+    e.btn_speed = (s->kind == SRL_ENV_KUKA_MOVING_BUTTON) ? d[17] : 0.0;
     if (s->cfg.random_target) { e.button_base[0] = d[0]; e.button_base[1] = d[1]; }
     for (int k = 0; k < 5; ++k) { /* N_RANDOM_ACTIONS_AT_INIT, :250-269 */
         apply_ee_delta(w, s, e, d + 2 + 3 * k);
@@ -795,6 +803,14 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
         d[2] = s->cfg.force_down ? -fabs((double)a[2] * dv) : (double)a[2] * dv;
     }
     e.total_steps += 1;
+    if (s->kind == SRL_ENV_KUKA_MOVING_BUTTON) {
+        /* kuka_moving_button_gym_env.py:109-119: bounce at the table edge, slide the target, teleport the button base to
+           (button_pos - BUTTON_DISTANCE_HEIGHT) -- i.e. x, y follow the target and z becomes the button LINK height of reset */
+        if (e.button_pos[1] > 0.3 || e.button_pos[1] < -0.3) e.btn_speed = -e.btn_speed;
+        e.button_pos[1] += e.btn_speed;
+        e.button_base[0] = e.button_pos[0]; e.button_base[1] = e.button_pos[1];
+        e.button_base[2] = e.button_pos[2] - w.m.sc[KM_SC_TARGET_HEIGHT];
+    }
     /* ---- step2() (:342-368) ---- */
     for (int rep = 0; rep < s->cfg.action_repeat; ++rep) {
         apply_ee_delta(w, s, e, d);
@@ -947,6 +963,7 @@ void okb_reset_world(void* h) {           /* p.resetSimulation(): everything bac
 }
 void okb_set_iterations(void* h, int n) { ((OkbWorld*)h)->iterations = n; }
 void okb_set_button_base(void* h, double x, double y) { OkbWorld* w = (OkbWorld*)h; w->e.button_base[0] = x; w->e.button_base[1] = y; }
+void okb_set_button_base3(void* h, double x, double y, double z) { OkbWorld* w = (OkbWorld*)h; w->e.button_base[0] = x; w->e.button_base[1] = y; w->e.button_base[2] = z; }
 void okb_reset_joint(void* h, int body, double q) {  /* p.resetJointState */
     OkbWorld* w = (OkbWorld*)h; w->e.q[body] = q; w->e.qd[body] = 0.0; refresh_link_states(w->m, w->e);
 }

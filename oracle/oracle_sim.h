@@ -54,7 +54,7 @@ void oracle_mobile_step_env(srl_sim* s, int i, const void* actions, const float*
 /* kuka */
 KukaWorld* oracle_kuka_create(srl_sim* s, const void* blob, size_t bytes);
 void oracle_kuka_destroy(KukaWorld* w);
-void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws /*nullable, 17 values*/);
+void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws /*nullable, 18 values*/);
 void oracle_kuka_obs(const srl_sim* s, int i, float* obs);
 void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* noise,
                           float* obs, float* rew, uint8_t* done, float* ep_ret, int32_t* ep_len);

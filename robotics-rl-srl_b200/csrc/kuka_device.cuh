@@ -52,7 +52,10 @@ struct KukaEnv {
     float q[KK_NB], qd[KK_NB];
     float qb, qdb;           // button glider
     float ee[3];             // commanded end-effector position (kuka.py:73,134-139)
-    float bbx, bby;          // button base x, y (z is a model constant)
+    float bbx, bby, bbz;     // button base origin (z moves only in the moving-button variant)
+    float bspeed;            // signed button speed (moving-button variant)
+    double by64;             // moving button: target y carried in float64 exactly like the reference's numpy accumulation,
+                             // so the bounce at |y| > 0.3 happens on the same step (a 1-ulp matter after 300 additions of 0.001)
     float tgt[3];            // button_pos: target frozen at reset (:273-274)
     float grip[3], eepos[3]; // link states after the last step
     int counter, n_contacts, n_outside, terminated;
@@ -117,7 +120,7 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
     int cbutton = 0, ctable = 0;
     float zmin_body = 1e30f;
     if (WITH_CONTACTS) ct.n = 0;
-    const float bz = P.btn_base[2];
+    const float bz = e.bbz;
     const float disc0 = bz + P.glider_z + e.qb + P.disc_z0, disc1 = bz + P.glider_z + e.qb + P.disc_z1;
     const float zmax_shapes = fmaxf(disc1, fmaxf(bz + P.stack_top, P.table_z));
 #pragma unroll 1

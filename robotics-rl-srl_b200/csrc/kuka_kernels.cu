@@ -22,11 +22,11 @@ struct KukaDev {
     float4* qd[3];   // [N] joint velocities
     float4* misc0;   // ee.x ee.y ee.z qb
     float4* misc1;   // qdb btn_base.x btn_base.y ep_ret
-    float4* tgt;     // button_pos.xyz, -
-    float4* grip;    // gripper_pos.xyz, -
-    float4* eepos;   // link-6 origin xyz, -
+    float4* tgt;     // button_pos.xyz, button base z
+    float4* grip;    // gripper_pos.xyz, signed button speed
+    float4* eepos;   // link-6 origin xyz, moving button: low word of the float64 target y
     int4*   cnt;     // counter, n_contacts, n_outside, terminated | cbutton << 1 | ctable << 2
-    int4*   cnt2;    // episode, total_steps, ep_len, -
+    int4*   cnt2;    // episode, total_steps, ep_len, moving button: high word of the float64 target y
     KukaParams P;
     int epw;         // live lanes per warp
 };
@@ -48,12 +48,13 @@ KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
     const int4 c = d.cnt[i], c2 = d.cnt2[i];
     e.ee[0] = m0.x; e.ee[1] = m0.y; e.ee[2] = m0.z; e.qb = m0.w;
     e.qdb = m1.x; e.bbx = m1.y; e.bby = m1.z; e.ep_ret = m1.w;
-    e.tgt[0] = tg.x; e.tgt[1] = tg.y; e.tgt[2] = tg.z;
-    e.grip[0] = gr.x; e.grip[1] = gr.y; e.grip[2] = gr.z;
+    e.tgt[0] = tg.x; e.tgt[1] = tg.y; e.tgt[2] = tg.z; e.bbz = tg.w;
+    e.grip[0] = gr.x; e.grip[1] = gr.y; e.grip[2] = gr.z; e.bspeed = gr.w;
     e.eepos[0] = ep.x; e.eepos[1] = ep.y; e.eepos[2] = ep.z;
     e.counter = c.x; e.n_contacts = c.y; e.n_outside = c.z;
     e.terminated = c.w & 1; e.cbutton = (c.w >> 1) & 1; e.ctable = (c.w >> 2) & 1;
     e.episode = (uint32_t)c2.x; e.total_steps = (uint32_t)c2.y; e.ep_len = c2.z;
+    e.by64 = __hiloint2double(c2.w, __float_as_int(ep.w));
 }
 
 KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
@@ -64,11 +65,11 @@ KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
     }
     d.misc0[i] = make_float4(e.ee[0], e.ee[1], e.ee[2], e.qb);
     d.misc1[i] = make_float4(e.qdb, e.bbx, e.bby, e.ep_ret);
-    d.tgt[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], 0.f);
-    d.grip[i] = make_float4(e.grip[0], e.grip[1], e.grip[2], 0.f);
-    d.eepos[i] = make_float4(e.eepos[0], e.eepos[1], e.eepos[2], 0.f);
+    d.tgt[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.bbz);
+    d.grip[i] = make_float4(e.grip[0], e.grip[1], e.grip[2], e.bspeed);
+    d.eepos[i] = make_float4(e.eepos[0], e.eepos[1], e.eepos[2], __int_as_float(__double2loint(e.by64)));
     d.cnt[i] = make_int4(e.counter, e.n_contacts, e.n_outside, e.terminated | (e.cbutton << 1) | (e.ctable << 2));
-    d.cnt2[i] = make_int4((int)e.episode, (int)e.total_steps, e.ep_len, 0);
+    d.cnt2[i] = make_int4((int)e.episode, (int)e.total_steps, e.ep_len, __double2hiint(e.by64));
 }
 
 // Kuka.applyAction's accumulate + clip of the commanded end-effector position (kuka.py:134-139)
@@ -103,13 +104,20 @@ KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restric
     for (int i = 0; i < KK_NB; ++i) { e.q[i] = P.snap_q[i]; e.qd[i] = P.snap_qd[i]; }
     e.ee[0] = P.snap_ee[0]; e.ee[1] = P.snap_ee[1]; e.ee[2] = P.snap_ee[2];
     e.qb = P.snap_qb; e.qdb = P.snap_qdb;
-    e.bbx = P.btn_base[0]; e.bby = P.btn_base[1];
+    e.bbx = P.btn_base[0]; e.bby = P.btn_base[1]; e.bbz = P.btn_base[2];
+    e.bspeed = 0.f;
+    if (P.moving_button) {   // BUTTON_SPEED * np_random.choice([-1, 1]) (kuka_moving_button_gym_env.py:33)
+        if (d17) e.bspeed = (float)d17[17];
+        else e.bspeed = (philox4x32_10(P.seed, genv, e.episode, PHILOX_PURPOSE_RESET0 + 6).x & 1u) ? 0.001f : -0.001f;
+    }
+    e.by64 = (double)P.btn_base[1];
     if (P.random_target) {
-        if (d17) { e.bbx = (float)d17[0]; e.bby = (float)d17[1]; }
+        if (d17) { e.bbx = (float)d17[0]; e.bby = (float)d17[1]; e.by64 = d17[1]; }
         else {
             const uint4 r = philox4x32_10(P.seed, genv, e.episode, PHILOX_PURPOSE_RESET0);
             e.bbx = (float)((double)P.btn_base[0] + (double)P.rand_x * (-1.0 + 2.0 * philox_u01(r.x, r.y)));  // :230
-            e.bby = (float)((double)P.btn_base[1] + (double)P.rand_y * (-1.0 + 2.0 * philox_u01(r.z, r.w)));  // :231
+            e.by64 = (double)P.btn_base[1] + (double)P.rand_y * (-1.0 + 2.0 * philox_u01(r.z, r.w));              // :231
+            e.bby = (float)e.by64;
         }
     }
 }
@@ -117,7 +125,7 @@ KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restric
 // reset(), second half: after the random steps, freeze the target and clear the episode counters (:273-274,215-217)
 KK_DEV void reset_end(const KukaParams& P, KukaEnv& e) {
     e.tgt[0] = e.bbx; e.tgt[1] = e.bby;
-    e.tgt[2] = P.btn_base[2] + P.glider_z + e.qb + P.target_h;  // button link state + BUTTON_DISTANCE_HEIGHT
+    e.tgt[2] = e.bbz + P.glider_z + e.qb + P.target_h;  // button link state + BUTTON_DISTANCE_HEIGHT
     e.counter = 0; e.n_contacts = 0; e.n_outside = 0; e.terminated = 0;
     e.ep_ret = 0.f; e.ep_len = 0;
     e.episode += 1;
@@ -164,14 +172,14 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     float dx = 0.f, dy = 0.f, dz = 0.f;
     const double* d17 = nullptr;
     if (op == KUKA_OP_RESET) {
-        d17 = draws ? draws + (size_t)i * 17 : nullptr;
+        d17 = draws ? draws + (size_t)i * 18 : nullptr;
         reset_begin(P, e, d17, genv);
         in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
     } else if (op == KUKA_OP_SETTLE) {
 #pragma unroll
         for (int j = 0; j < KK_NB; ++j) { e.q[j] = P.snap_q[j]; e.qd[j] = 0.f; }  // resetJointState (kuka.py:68-69)
         e.ee[0] = P.ee_init[0]; e.ee[1] = P.ee_init[1]; e.ee[2] = P.ee_init[2];
-        e.qb = 0.f; e.qdb = 0.f; e.bbx = P.btn_base[0]; e.bby = P.btn_base[1];
+        e.qb = 0.f; e.qdb = 0.f; e.bbx = P.btn_base[0]; e.bby = P.btn_base[1]; e.bbz = P.btn_base[2]; e.bspeed = 0.f; e.by64 = 0.0;
         in_reset = true; reset_left = 500;
     }
     for (;;) {
@@ -270,6 +278,14 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                     dz = P.force_down ? -fabsf(a2 * dv) : a2 * dv;
                 }
                 e.total_steps += 1;
+                if (P.moving_button) {
+                    // kuka_moving_button_gym_env.py:109-119: bounce at the table edge, slide the target, teleport the button base
+                    // to (button_pos - BUTTON_DISTANCE_HEIGHT): x, y follow the target, z becomes the button LINK height of reset
+                    if (e.by64 > 0.3 || e.by64 < -0.3) e.bspeed = -e.bspeed;
+                    e.by64 = __dadd_rn(e.by64, e.bspeed > 0.f ? 0.001 : -0.001);   // float64, like the reference's numpy array
+                    e.tgt[1] = (float)e.by64;
+                    e.bbx = e.tgt[0]; e.bby = e.tgt[1]; e.bbz = e.tgt[2] - P.target_h;
+                }
             }
             armed = true;
         }
@@ -352,6 +368,7 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
     P.is_discrete = s->cfg.is_discrete; P.random_target = s->cfg.random_target; P.force_down = s->cfg.force_down;
     P.shape_reward = s->cfg.shape_reward; P.action_repeat = s->cfg.action_repeat; P.max_steps = s->max_steps;
     P.auto_reset = s->auto_reset; P.max_distance = s->cfg.max_distance;
+    P.moving_button = s->kind == SRL_ENV_KUKA_MOVING_BUTTON;
     P.seed = s->seed; P.env_offset = s->cfg.global_env_offset;
     return true;
 }
@@ -365,8 +382,8 @@ void grid_for(const srl_sim* s, const KukaDev* d, int& grid, int& block) {
 }  // namespace
 
 int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
-    if (s->kind != SRL_ENV_KUKA_BUTTON && s->kind != SRL_ENV_KUKA_RAND_BUTTON) {
-        srl_set_error("kuka: env kind %d is not implemented yet", s->kind); return 1;
+    if (s->kind == SRL_ENV_KUKA_2BUTTON) {
+        srl_set_error("Kuka2ButtonGymEnv-v0 (two buttons, null-space IK) is not implemented"); return 1;
     }
     KukaDev* d = new KukaDev();
     memset(d, 0, sizeof(*d));
@@ -468,7 +485,8 @@ int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
     case SRL_F_BUTTON_BASE:
         if (!need(3, 8)) return 1;
         SRL_CUDA_OK(pull(b, d->misc1));
-        for (size_t i = 0; i < N; ++i) { D[3 * i] = b[i].y; D[3 * i + 1] = b[i].z; D[3 * i + 2] = d->P.btn_base[2]; }
+        SRL_CUDA_OK(pull(a, d->tgt));
+        for (size_t i = 0; i < N; ++i) { D[3 * i] = b[i].y; D[3 * i + 1] = b[i].z; D[3 * i + 2] = a[i].w; }
         return 0;
     case SRL_F_STEP_COUNTER:
         if (!need(1, 4)) return 1;
@@ -525,7 +543,8 @@ int kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes) {
         return 0;
     case SRL_F_TARGET_POS:
         if (!need(3, 8)) return 1;
-        for (size_t i = 0; i < N; ++i) a[i] = make_float4((float)D[3 * i], (float)D[3 * i + 1], (float)D[3 * i + 2], 0.f);
+        SRL_CUDA_OK(pull(a, d->tgt));
+        for (size_t i = 0; i < N; ++i) { a[i].x = (float)D[3 * i]; a[i].y = (float)D[3 * i + 1]; a[i].z = (float)D[3 * i + 2]; }
         SRL_CUDA_OK(push(a, d->tgt));
         return 0;
     case SRL_F_BUTTON_GLIDER:

@@ -78,6 +78,7 @@ class KukaButtonGymEnv(SRLGymEnv):
     :param device: (int) CUDA device ordinal (extension; default 0)
     """
     _ENV_ID = "KukaButtonGymEnv-v0"
+    _MAX_STEPS = MAX_STEPS
 
     def __init__(self, urdf_root=None, renders=False, is_discrete=True, multi_view=False, name="kuka_button_gym",
                  max_distance=0.8, action_repeat=1, shape_reward=False, action_joints=False, record_data=False,
@@ -141,7 +142,7 @@ class KukaButtonGymEnv(SRLGymEnv):
         self._sim = self._backend.make_sim(self._ENV_ID, 1, seed=0, model_blob=load_kuka_scene().blob,
                                            is_discrete=is_discrete, random_target=random_target, force_down=force_down,
                                            shape_reward=shape_reward, action_repeat=action_repeat,
-                                           max_distance=max_distance, max_steps=self.max_steps, no_auto_reset=True)
+                                           max_distance=max_distance, max_steps=self._MAX_STEPS, no_auto_reset=True)
         be = self._backend
         self._obs_buf = be.zeros((1, 3), np.float32)
         self._rew_buf = be.zeros((1,), np.float32)
@@ -199,7 +200,8 @@ class KukaButtonGymEnv(SRLGymEnv):
                                       "use srl_model='ground_truth'")
 
     def _reset_draws(self):
-        """np_random draws of reset() in the reference's order (:227-231, :250-266) -> the 17 reset values."""
+        """np_random draws of reset() in the reference's order (:227-231, :250-266) -> the 18 reset values
+        (button x, y; 5 x (dx, dy, dz); signed button speed, 0 except for the moving-button variant)."""
         x_pos, y_pos = 0.5, 0
         if self._random_target:
             x_pos += 0.15 * self.np_random.uniform(-1, 1)
@@ -217,7 +219,7 @@ class KukaButtonGymEnv(SRLGymEnv):
                 rand_direction /= np.linalg.norm(rand_direction, 2)
                 action = list(np.zeros(3) + DELTA_V_CONTINUOUS * rand_direction)
             draws += [float(a) for a in action]
-        return draws
+        return draws + [0.0]
 
     def reset(self):
         self._require_state_obs()

@@ -42,7 +42,7 @@ _FIELD_SPEC = {
 }
 
 MOBILE_RESET_DRAWS = 6
-KUKA_RESET_DRAWS = 17
+KUKA_RESET_DRAWS = 18
 
 
 class SrlCfg(Structure):

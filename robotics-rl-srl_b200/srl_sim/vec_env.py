@@ -21,10 +21,10 @@ import numpy as np
 from . import _abi, spaces
 from .backend import default_backend
 
-_KUKA_IDS = ("KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0")
+_KUKA_IDS = ("KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0", "KukaMovingButtonGymEnv-v0")
 _OBS_DIM = {"MobileRobot1DGymEnv-v0": 1}
 _N_ACTIONS = {"MobileRobot1DGymEnv-v0": 2, "MobileRobotGymEnv-v0": 4, "MobileRobot2TargetGymEnv-v0": 4,
-              "MobileRobotLineTargetGymEnv-v0": 4, "KukaButtonGymEnv-v0": 6, "KukaRandButtonGymEnv-v0": 6}
+              "MobileRobotLineTargetGymEnv-v0": 4, "KukaButtonGymEnv-v0": 6, "KukaRandButtonGymEnv-v0": 6, "KukaMovingButtonGymEnv-v0": 6}
 
 
 class BatchedSRLVecEnv(object):

@@ -36,6 +36,7 @@ class _World(object):
         self.lib.okb_create.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         for name, args in (("okb_reset_world", [ctypes.c_void_p]), ("okb_set_iterations", [ctypes.c_void_p, ctypes.c_int]),
                            ("okb_set_button_base", [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]),
+                           ("okb_set_button_base3", [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
                            ("okb_reset_joint", [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]),
                            ("okb_ik", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
                            ("okb_step", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4),
@@ -125,8 +126,11 @@ def loadSDF(path, *a, **k):
 
 
 def resetBasePositionAndOrientation(uid, pos, orn):
-    if _world().uids.get(uid) == "kuka":
+    w = _world()
+    if w.uids.get(uid) == "kuka":
         assert np.allclose(pos, [-0.1, 0.0, -0.15])
+    elif w.uids.get(uid) == "button":       # KukaMovingButtonGymEnv teleports the button every step (:116-117)
+        w.lib.okb_set_button_base3(w.h, float(pos[0]), float(pos[1]), float(pos[2]))
 
 
 def getNumJoints(uid):

@@ -26,6 +26,7 @@ import torch  # noqa: E402,F401  (the reference imports it)
 
 from environments.kuka_gym.kuka_button_gym_env import KukaButtonGymEnv  # noqa: E402
 from environments.kuka_gym.kuka_rand_button_gym_env import KukaRandButtonGymEnv  # noqa: E402
+from environments.kuka_gym.kuka_moving_button_gym_env import KukaMovingButtonGymEnv  # noqa: E402
 
 assert "/root/reference" in sys.modules[KukaButtonGymEnv.__module__].__file__, "must import the reference classes"
 
@@ -38,8 +39,11 @@ CASES = [
     ("disc_rep3_none", "KukaButtonGymEnv", dict(is_discrete=True, action_repeat=3), 4, 300),
     ("rand_button_cont", "KukaRandButtonGymEnv", dict(is_discrete=False, random_target=True), 5, 400),
     ("rand_button_disc", "KukaRandButtonGymEnv", dict(is_discrete=True, random_target=True), 6, 500),
+    ("moving_disc", "KukaMovingButtonGymEnv", dict(is_discrete=True), 7, 500),
+    ("moving_cont_rand", "KukaMovingButtonGymEnv", dict(is_discrete=False, random_target=True), 8, 400),
 ]
-CLASSES = {"KukaButtonGymEnv": KukaButtonGymEnv, "KukaRandButtonGymEnv": KukaRandButtonGymEnv}
+CLASSES = {"KukaButtonGymEnv": KukaButtonGymEnv, "KukaRandButtonGymEnv": KukaRandButtonGymEnv,
+           "KukaMovingButtonGymEnv": KukaMovingButtonGymEnv}
 
 
 def make_actions(tag, kwargs, n, seed):
@@ -65,7 +69,7 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
     t = 0
     while t < nsteps:
         o = env.reset()
-        rec["reset_obs"].append(np.asarray(o, np.float64)); rec["reset_target"].append(np.asarray(env.getTargetPos(), np.float64))
+        rec["reset_obs"].append(np.asarray(o, np.float64)); rec["reset_target"].append(np.array(env.getTargetPos(), dtype=np.float64, copy=True))
         rec["reset_at"].append(t)
         done = False
         while not done and t < nsteps:
@@ -75,7 +79,7 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
                 a = actions[t].astype(np.float32)
             o, r, done, _ = env.step(a)
             rec["obs"].append(np.asarray(o, np.float64)); rec["reward"].append(float(r)); rec["done"].append(bool(done))
-            rec["arm"].append(np.asarray(env.getArmPos(), np.float64)); rec["target"].append(np.asarray(env.getTargetPos(), np.float64))
+            rec["arm"].append(np.array(env.getArmPos(), dtype=np.float64, copy=True)); rec["target"].append(np.array(env.getTargetPos(), dtype=np.float64, copy=True))
             t += 1
     return {k: np.asarray(v) for k, v in rec.items()}
 

@@ -220,7 +220,7 @@ def test_single_env_classes_on_cuda(cuda_lib):
     env.close()
 
 
-@pytest.mark.parametrize("tag", ["disc", "cont", "disc_rep3_none", "rand_button_disc", "disc_rand_shaped"])
+@pytest.mark.parametrize("tag", ["disc", "cont", "disc_rep3_none", "rand_button_disc", "disc_rand_shaped", "moving_disc", "moving_cont_rand"])
 def test_reference_class_logic_golden_through_cuda(tag, cuda_lib):
     """Trajectories recorded from the REFERENCE Kuka classes (on the oracle's physics, tests/golden/fake_pybullet.py)
     replayed through our env classes -> C-ABI -> the fp32 kernel: flags exact, positions within 1e-3 m."""
@@ -228,3 +228,38 @@ def test_reference_class_logic_golden_through_cuda(tag, cuda_lib):
     from test_kuka_cpu import replay_ref_logic_case
     backend.use_library(None, None)
     replay_ref_logic_case(tag, POS_TOL)
+
+
+def _parity_until_first_flag_shift(c, o, max_shifted_envs):
+    """fp32 vs fp64 can move a contact ONSET by one step when the sphere-shape distance lands within float32 rounding
+    (~3e-6 m, against ~1.2 mm of approach per step) of the 0.02 m manifold margin.  After such a shift the episode ends one
+    step earlier/later and the env legitimately sees different actions, so each env is compared up to its first flag
+    difference, which must be exactly such a one-step shift; only a few envs may have one."""
+    T, n = o["rew"].shape
+    shifted = 0
+    for i in range(n):
+        bad = np.nonzero((c["rew"][:, i] != o["rew"][:, i]) | (c["done"][:, i] != o["done"][:, i]))[0]
+        t_end = T if len(bad) == 0 else int(bad[0])
+        assert np.abs(c["obs"][:t_end, i] - o["obs"][:t_end, i]).max(initial=0.0) < POS_TOL
+        if len(bad):
+            shifted += 1
+            t = t_end
+            assert {float(c["rew"][t, i]), float(o["rew"][t, i])} == {0.0, 1.0}          # a contact flag, on one side only ...
+            early, late = (c, o) if c["rew"][t, i] == 1.0 else (o, c)
+            assert late["rew"][t + 1, i] == 1.0 and early["rew"][t + 1, i] == 1.0          # ... that the other side raises one step later
+            assert np.abs(c["obs"][t, i] - o["obs"][t, i]).max() < POS_TOL
+    assert shifted <= max_shifted_envs, shifted
+    return shifted
+
+
+def test_moving_button_kind_vs_oracle(cuda_backend, oracle_backend):
+    """KukaMovingButtonGymEnv-v0: the button (and the target) slides +-0.001 per step and bounces at |y| = 0.3."""
+    n, T = 24, 900
+    rs = np.random.RandomState(6)
+    acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
+    cfg = dict(seed=4, random_target=True)
+    c = _run(cuda_backend, "KukaMovingButtonGymEnv-v0", n, T, acts, noise, **cfg)
+    o = _run(oracle_backend, "KukaMovingButtonGymEnv-v0", n, T, acts, noise, **cfg)
+    assert np.abs(c["obs0"] - o["obs0"]).max() < POS_TOL
+    _parity_until_first_flag_shift(c, o, max_shifted_envs=3)
+    assert o["done"].sum() >= n // 2 and np.abs(o["target"][:, 1]).max() <= 0.3011

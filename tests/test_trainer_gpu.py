@@ -17,7 +17,7 @@ def test_ppo2_learns_mobile_robot(cuda_lib):
     assert rets[-1] > rets[0] + 60, rets
 
 
-@pytest.mark.parametrize("env_id", ["KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0", "MobileRobotGymEnv-v0", "MobileRobot2TargetGymEnv-v0",
+@pytest.mark.parametrize("env_id", ["KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0", "KukaMovingButtonGymEnv-v0", "MobileRobotGymEnv-v0", "MobileRobot2TargetGymEnv-v0",
                                     "MobileRobot1DGymEnv-v0", "MobileRobotLineTargetGymEnv-v0"])
 def test_train_entry_point_runs_for_every_env(env_id, cuda_lib, tmp_path):
     from srl_sim import backend
