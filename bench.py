@@ -250,7 +250,6 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
     barrier()
     wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -258,12 +257,10 @@ def run_b200(args):
         ev[k][0].record()
         step()
         ev[k][1].record()
-        kernel_ms.append(None)
     barrier()
     wall = time.perf_counter() - wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
-    kernel_last_ms = sim.last_kernel_ms()
     launches = sim.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
 

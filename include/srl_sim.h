@@ -161,6 +161,8 @@ int srl_sim_rollout(srl_sim* sim, int T, const void* actions, const float* noise
 int srl_sim_rollout_host(srl_sim* sim, int T, const void* actions, const float* noise,
                          float* obs_out, float* rew_out, uint8_t* done_out);
 
+/* Debug / single-env accessors (host arrays, synchronising; not on the hot path).  Derived link-state fields
+ * (SRL_F_ROBOT_POS, SRL_F_EE_POS) reflect the last step or reset; they are not recomputed by set_state. */
 int srl_sim_get_state(srl_sim* sim, int field, void* dst, size_t bytes);
 int srl_sim_set_state(srl_sim* sim, int field, const void* src, size_t bytes);
 

@@ -44,7 +44,6 @@ KK_DEV f3 symv(const float* I, f3 v) {
 }
 
 // parent of each body: chain 0..7, fingers 8->9 and 10->11 hanging off the gripper base (7)
-__device__ __constant__ const int KK_PARENT[KK_NB] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 7, 10};
 #define KK_PAR(i) ((i) == 0 ? -1 : (i) == 10 ? 7 : (i) - 1)
 
 // ---- per-env dynamic state, register resident across the steps of a fused rollout ----
