@@ -29,6 +29,14 @@
 #ifndef KK_ROLL_DYN
 #define KK_ROLL_DYN 0
 #endif
+// Packed-FP32 sweep (Blackwell FFMA2, `fma.rn.f32x2` / __ffma2_rn): v += A[:, i] * delta as 6 two-wide FMAs instead of 12.
+// It needs the FULL matrix in pair-column layout (144 registers instead of the 78 of the symmetric half).  Tried in round 1 and
+// left OFF: ptxas emits the 61 FFMA2 but also 66 MOVs to build the (delta, delta) pairs and align register pairs, and with
+// 255 registers exhausted 14 spill loads land inside the sweep -- 303 SASS instructions per sweep against 256 for the scalar
+// form (static count, cuobjdump), so the issue-bound sweep would get slower, not faster.
+#ifndef KK_SWEEP_FFMA2
+#define KK_SWEEP_FFMA2 0
+#endif
 
 struct f3 { float x, y, z; };
 KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -750,6 +758,51 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         // by folding the previous row's contribution to v_i into the impulse update algebraically:
         //   lam_i + (tgt_i - v_i) / D_i  =  [lam_i + tgt_i/D_i - v'_i/D_i]  -  (A_{i,i-1}/D_i) * delta_{i-1}
         // where v'_i lacks only the previous row's update (applied off the critical path afterwards).
+#if KK_SWEEP_FFMA2
+        float tk[KK_NB];
+        float2 Ac[KK_NB][KK_NB / 2];   // column i of the symmetric A, as (row 2p, row 2p+1) pairs
+        float2 vp[KK_NB / 2];
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {
+            tk[i] = tgt[i] * invd[i];
+#pragma unroll
+            for (int p2 = 0; p2 < KK_NB / 2; ++p2) Ac[i][p2] = make_float2(KK_A(2 * p2, i), KK_A(2 * p2 + 1, i));
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < KK_NB / 2; ++p2) vp[p2] = make_float2(v[2 * p2], v[2 * p2 + 1]);
+#define KK_V(j) (((j) & 1) ? vp[(j) >> 1].y : vp[(j) >> 1].x)
+#define KK_AC(j, i) (((j) & 1) ? Ac[i][(j) >> 1].y : Ac[i][(j) >> 1].x)
+#pragma unroll 1
+        for (int it = 0; it < P.iters; ++it) {
+            {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
+                float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
+                s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
+                v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
+                s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
+                v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
+            }
+            float dprev = 0.f;
+#pragma unroll
+            for (int i = 0; i < KK_NB; ++i) {
+                const float e = fmaf(-invd[i], KK_V(i), lam[i] + tk[i]);                                  // off the critical path
+                const float sraw = i > 0 ? fmaf(-(invd[i] * KK_AC(i - 1 < 0 ? 0 : i - 1, i)), dprev, e) : e;   // critical path
+                if (i > 0) KK_V(i) = fmaf(KK_AC(i - 1 < 0 ? 0 : i - 1, i), dprev, KK_V(i));               // deferred update from row i-1
+                const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
+                const float d = s - lam[i];
+                lam[i] = s;
+                const float2 d2 = make_float2(d, d);
+#pragma unroll
+                for (int p2 = 0; p2 < KK_NB / 2; ++p2) {
+                    if (2 * p2 == i + 1) vp[p2].y = fmaf(Ac[i][p2].y, d, vp[p2].y);          // (i+1, i+2): i+1 is updated by the next row
+                    else if (2 * p2 + 1 == i + 1) vp[p2].x = fmaf(Ac[i][p2].x, d, vp[p2].x);   // (i, i+1)
+                    else vp[p2] = __ffma2_rn(Ac[i][p2], d2, vp[p2]);
+                }
+                dprev = d;
+            }
+#define KK_SYNC_V() { _Pragma("unroll") for (int p3 = 0; p3 < KK_NB / 2; ++p3) { v[2 * p3] = vp[p3].x; v[2 * p3 + 1] = vp[p3].y; } }
+            if (nc > 0) KK_SYNC_V();
+#else
         float tk[KK_NB], kk[KK_NB];
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) { tk[i] = tgt[i] * invd[i]; kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f; }
@@ -777,6 +830,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                     if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
                 dprev = d;
             }
+#endif
             if (nc > 0) {
                 bool act = false;
 #pragma unroll 1
@@ -790,6 +844,9 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             }
             it0 = it + 1;
         }
+#if KK_SWEEP_FFMA2
+        KK_SYNC_V();
+#endif
     }
     if (it0 < P.iters) {
         // GENERAL PATH (a joint on its limit and / or an active contact): same row order, plain form.
