@@ -36,7 +36,9 @@ struct srl_sim {
     uint64_t seed;
     int auto_reset;
     int max_steps;
-    MobileDev mob;
+    MobileDev mob;      // current state
+    MobileDev mob_alt;  // the other half of the double buffer (rollouts write here, then swap)
+    int mobile_block;   // CTA-size override (0 = heuristic)
     KukaDev* kuka;
     uint64_t launches;
     cudaEvent_t ev0, ev1;

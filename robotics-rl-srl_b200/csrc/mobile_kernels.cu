@@ -15,6 +15,8 @@
 // round-to-nearest intrinsics (__dadd_rn/__dmul_rn/__dsqrt_rn) so that no multiply-add is fused:
 // positions, rewards and done flags are BIT-EXACT against the CPU restatement.
 #include <stdio.h>
+#include <stdlib.h>
+#include <initializer_list>
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -147,204 +149,282 @@ __global__ void __launch_bounds__(128) mobile_reset_kernel(MobileDev m, int n, c
 // It lets the unshaped reward test `np.linalg.norm(.) <= REWARD_DIST_THRESHOLD` (:353) skip the square root BIT-EXACTLY.
 constexpr double S_THR_04 = 0x1.47ae147ae147cp-3;
 
-// Fused T-step rollout; T = 1 is the plain lockstep step.  Auto-reset on done reproduces the
+// ------------------------------------------------------------------------------------------------------------------
+// Fused T-step rollout, EPISODE-PARALLEL.  T = 1 is the plain lockstep step.  Auto-reset on done reproduces the
 // SubprocVecEnv worker loop (rl_baselines/utils.py:216-220): the stored obs is the post-reset one.
 //
-// Throughput structure (ncu round 1: one dependent global load + a ~900-cycle dependent fp64 chain per step, `long_sb` 56 %):
-//  * the action / noise streams do not depend on the state: they are PREFETCHED a chunk of MOBILE_PF steps ahead into
-//    registers (double buffering), MOBILE_PF independent 128-byte loads per warp in flight;
-//  * each chunk is stepped in TWO PASSES.  Pass 1 is the only truly serial part -- position += action, bump test, revert,
-//    step counter, episode end / reset -- and records (target - position) per step.  Pass 2 turns those into distance,
-//    reward, observation and the HBM stores; its MOBILE_PF steps are independent, so the long-latency fp64 work
-//    (sqrt, conversions) overlaps instead of serialising.
-//  * the chunk is kept SHORT (4 steps): with one or two warps per SM nothing hides instruction fetch, and a 16-step
-//    unrolled body (54 KB of SASS) ran from L2 -- `no_inst` 29 %, 0.50 ms; 8 steps 0.44 ms; 4 steps 0.33 ms (measured; an extra
-//    `prefetch.global.L2` 32 steps ahead made it slower, 0.42 ms, and was dropped).
-// Arithmetic per step is unchanged (same operations, same order), so results stay bit-exact.
-constexpr int MOBILE_PF = 4;        // steps per chunk: the unrolled chunk body must stay small (see below)
+// Why (env, episode) and not (env) is the unit of parallel work.  `terminated` is never set in the reference
+// (mobile_robot_env.py:355 is commented out), so an episode ends exactly when `_env_step_counter > max_steps` (:336-343):
+// every episode is max_steps + 1 = 251 steps long, and the state an episode starts from is a pure function of the env's
+// counter-based RNG stream (seed, global env index, episode index) -- it does not depend on the previous episode.  A
+// T-step rollout of env i is therefore a sequence of INDEPENDENT segments whose boundaries are known before the first
+// step runs:
+//     segment 0   : steps [0, max_steps - counter]              starts from the state in HBM
+//     segment s>0 : the next max_steps + 1 steps each           starts from reset(episode0 + s - 1)
+// One thread runs one segment (blockIdx.y = segment): an 8192-env x 1024-step rollout becomes ~41 000 threads instead
+// of 8192 (round 1: 256 warps for 592 schedulers, a ~600-cycle latency chain per step with nothing to overlap it).  The
+// thread of a finished segment also produces the post-reset observation of the next one (it re-derives that reset),
+// the thread whose segment reaches step T writes the state back.  State is double-buffered (`in` -> `out`): the
+// segment-0 thread of an env may be scheduled after the thread that writes that env's final state.
+// Arithmetic per step is the round-1 kernel's (same operations, same order): results stay bit-exact.
+//
+// Inside a segment (per chunk of MOBILE_PF steps):
+//  * the action / noise streams do not depend on the state: PREFETCHED one chunk ahead into registers;
+//  * pass 1 is the only serial part -- position += action, bump test, revert -- and records (target - position);
+//  * pass 2 turns those into distance, reward, observation and the HBM stores; its steps are independent;
+//  * nothing per-step is spent on episode bookkeeping: the step counter, `done`, the episode length follow from t, and
+//    the unshaped episode return is an integer sum (rewards are -1 / 0 / 1: the float64 accumulation is exact either way).
+#ifndef MOBILE_PF
+#define MOBILE_PF 8                 // steps per chunk (measured on B200, 8192 envs x 1024 steps: 2 -> 96 us, 4 -> 67 us, 8 -> 54-58 us)
+#endif
 
-template <bool DISCRETE>
+template <bool DISCRETE, int NS>
 struct ActionChunk {
-    int a[DISCRETE ? MOBILE_PF : 1];
-    float x[DISCRETE ? 1 : MOBILE_PF], y[DISCRETE ? 1 : MOBILE_PF];
-    float nz[MOBILE_PF];
+    int a[DISCRETE ? NS : 1];
+    float x[DISCRETE ? 1 : NS], y[DISCRETE ? 1 : NS];
+    float nz[NS];
 };
 
-template <bool DISCRETE>
-__device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE>& c, const void* __restrict__ actions, const float* __restrict__ noise,
-                                           int t0, int T, size_t N, size_t i) {
+// actions of steps [t0, t0 + NS) of env i: from HBM, or (GEN) the env's own stream -- the reference's random agent
+template <int KIND, bool DISCRETE, bool GEN, int NS>
+__device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE, NS>& c, const void* __restrict__ actions, const float* __restrict__ noise,
+                                           int t0, size_t N, size_t i, uint64_t seed, uint64_t genv, uint32_t total_steps0) {
+    constexpr uint32_t NA = (KIND == SRL_ENV_MOBILE_1D) ? 2u : 4u;
 #pragma unroll
-    for (int k = 0; k < MOBILE_PF; ++k) {
-        const int t = t0 + k;
-        if (t < T) {
-            const size_t off = (size_t)t * N + i;
-            if (actions) {
-                if (DISCRETE) c.a[DISCRETE ? k : 0] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
-                else { const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + off); c.x[DISCRETE ? 0 : k] = v.x; c.y[DISCRETE ? 0 : k] = v.y; }
+    for (int k = 0; k < NS; ++k) {
+        const size_t off = (size_t)(t0 + k) * N + i;
+        if (GEN) {
+            const uint4 r = philox4x32_10(seed, genv, total_steps0 + (uint32_t)k, PHILOX_PURPOSE_ACTION);
+            if (DISCRETE) c.a[DISCRETE ? k : 0] = (int)__umulhi(r.x, NA);
+            else {
+                c.x[DISCRETE ? 0 : k] = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0);
+                c.y[DISCRETE ? 0 : k] = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0);
             }
-            if (noise) c.nz[k] = __ldg(noise + off);
+        } else if (DISCRETE) {
+            c.a[DISCRETE ? k : 0] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
+        } else {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + off);
+            c.x[DISCRETE ? 0 : k] = v.x; c.y[DISCRETE ? 0 : k] = v.y;
+        }
+        c.nz[k] = noise ? __ldg(noise + off) : 0.f;
+    }
+}
+
+struct SegmentAcc {        // per-segment running values that are not part of the serial position chain
+    int ret_i;             // unshaped: integer sum of the -1 / 0 / 1 rewards of this segment
+    double ret_d;          // shaped: the float64 episode return, accumulated in step order
+};
+
+template <int KIND, bool DISCRETE, bool SHAPED, int NS>
+__device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, const ActionChunk<DISCRETE, NS>& cur,
+                                           int t0, int t_done, int t_start, size_t N, size_t i, double ep_ret0, double ep_len0,
+                                           float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                           float* __restrict__ ep_ret, int32_t* __restrict__ ep_len) {
+    constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
+    constexpr int D = (KIND == SRL_ENV_MOBILE_1D) ? 1 : 2;
+    constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;  // :257-258
+    // ---------------- pass 1: the serial state chain (mobile_robot_env.py:237-268) ----------------
+    double ddx[NS], ddy[NS];   // what _reward() and getSRLState() are made of: target - position
+    float ox[TWO ? NS : 1], oy[TWO ? NS : 1];   // 2-target: the observation is relative to the target AFTER a switch
+    uint32_t bump_mask = 0u, reach_mask = 0u;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241); nz is 0.0f without a noise
+        // stream and DELTA_POS + 0.0 is exact
+        const double dv = __dadd_rn(DELTA_POS, (double)cur.nz[k]);
+        double ax = 0.0, ay = 0.0;
+        if (DISCRETE) {
+            // dx = [-dv, dv, 0, 0][a], dy = [0, 0, -dv, dv][a] (:242-243; 1D_env.py:115), branch-free: even actions flip the
+            // sign bit, the axis that does not move gets +0.0
+            const int a = cur.a[DISCRETE ? k : 0];
+            const int hi = __double2hiint(dv) ^ ((a & 1) ? 0 : (int)0x80000000u), lo = __double2loint(dv);
+            if (KIND == SRL_ENV_MOBILE_1D) ax = __hiloint2double(hi, lo);
+            else {
+                const bool along_x = (a & 2) == 0;
+                ax = __hiloint2double(along_x ? hi : 0, along_x ? lo : 0);
+                ay = __hiloint2double(along_x ? 0 : hi, along_x ? 0 : lo);
+            }
+        } else {
+            // float32 action array * python float -> float32 product, then += into float64 (:250,255)
+            const float fdv = (float)dv;
+            ax = (double)__fmul_rn(fmaxf(fminf(cur.x[DISCRETE ? 0 : k], 1.0f), -1.0f), fdv);
+            ay = (double)__fmul_rn(fmaxf(fminf(cur.y[DISCRETE ? 0 : k], 1.0f), -1.0f), fdv);
+        }
+        const double nx = __dadd_rn(e.px, ax);                             // :254-255
+        const double ny = (KIND != SRL_ENV_MOBILE_1D) ? __dadd_rn(e.py, ay) : e.py;
+        bool bumped = (nx < mx) || (nx > MAX_X - mx);                      // :257-263
+        if (KIND != SRL_ENV_MOBILE_1D) bumped = bumped || (ny < my) || (ny > MAX_Y - my);
+        e.px = bumped ? e.px : nx;                                         // has_bumped: revert the whole position
+        e.py = bumped ? e.py : ny;
+        bump_mask |= (bumped ? 1u : 0u) << k;
+        const double tx = e.current_target ? e.t1x : e.t0x, ty = e.current_target ? e.t1y : e.t0y;
+        if (KIND == SRL_ENV_MOBILE_LINE_TARGET) {
+            const double lx = __dsub_rn(tx, LINE_ROBOT_OFFSET);      // line_target_env.py:35-40,113
+            ddx[k] = __dsub_rn(lx, e.px); ddy[k] = __dsub_rn(lx, e.py);
+        } else {
+            ddx[k] = __dsub_rn(tx, e.px); ddy[k] = (KIND == SRL_ENV_MOBILE_1D) ? 0.0 : __dsub_rn(ty, e.py);
+        }
+        if (TWO) {  // the target switch feeds later steps: decide it here (2target_env.py:170-173)
+            const double sq = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k]));
+            if (sq <= S_THR_04) {
+                reach_mask |= 1u << k;
+                if (e.current_target < 1) e.current_target += 1;   // the observation of THIS step is already relative to the new target
+            }
+            const double ux = e.current_target ? e.t1x : e.t0x, uy = e.current_target ? e.t1y : e.t0y;
+            ox[TWO ? k : 0] = (float)__dsub_rn(e.px, ux); oy[TWO ? k : 0] = (float)__dsub_rn(e.py, uy);
+        }
+    }
+    e.has_bumped = (bump_mask >> (NS - 1)) & 1u;
+    // ---------------- pass 2: rewards and outputs, independent across the chunk (:345-363) ----------------
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int t = t0 + k;
+        const size_t off = (size_t)t * N + i;
+        const bool bumped = (bump_mask >> k) & 1u, is_done = t >= t_done;   // _termination (:336-343); `terminated` is never set
+        float reward_f;
+        if (SHAPED) {
+            double distance;
+            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) distance = fabs(ddx[k]);
+            else if (KIND == SRL_ENV_MOBILE_1D) distance = __dsqrt_rn(__dmul_rn(ddx[k], ddx[k]));
+            else distance = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])));  // np.linalg.norm = sqrt(x.dot(x))
+            acc.ret_d = __dadd_rn(acc.ret_d, -distance);
+            reward_f = (float)(-distance);
+        } else {
+            bool reached;
+            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) reached = fabs(ddx[k]) <= LINE_REWARD_DIST_THRESHOLD;
+            else if (TWO) reached = (reach_mask >> k) & 1u;
+            else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(ddx[k], ddx[k]) <= S_THR_04;
+            else reached = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])) <= S_THR_04;
+            const int r = bumped ? -1 : (reached ? 1 : 0);
+            acc.ret_i += r;
+            reward_f = (float)r;
+        }
+        if (rew) rew[off] = reward_f;
+        if (done) done[off] = is_done ? 1 : 0;
+        if (is_done) {   // Monitor-style episode statistics (environments/utils.py:53-54)
+            if (ep_ret) ep_ret[off] = (float)(SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i));
+            if (ep_len) ep_len[off] = (int32_t)ep_len0 + (t - t_start + 1);
+        }
+        if (obs) {
+            // getSRLState = getGroundTruth() - getTargetPos() = -(target - position): negation is exact
+            if (KIND == SRL_ENV_MOBILE_1D) obs[off] = -(float)ddx[k];
+            else if (TWO) reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(ox[TWO ? k : 0], oy[TWO ? k : 0]);
+            else reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(-(float)ddx[k], -(float)ddy[k]);
         }
     }
 }
 
-template <int KIND, bool DISCRETE>
-__global__ void __launch_bounds__(64) mobile_rollout_kernel(MobileDev m, int n, int T, const void* __restrict__ actions,
-                                                            const float* __restrict__ noise, float* __restrict__ obs,
-                                                            float* __restrict__ rew, uint8_t* __restrict__ done,
-                                                            float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
-                                                            bool random_target, bool shape_reward, bool auto_reset,
-                                                            int max_steps, uint64_t seed, uint64_t env_offset) {
+template <int KIND, bool DISCRETE, bool GEN, bool SHAPED>
+__global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, MobileDev out, int n, int T, const void* __restrict__ actions,
+                                                             const float* __restrict__ noise, float* __restrict__ obs,
+                                                             float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                             float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
+                                                             bool random_target, bool auto_reset,
+                                                             int max_steps, uint64_t seed, uint64_t env_offset) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
     constexpr int D = (KIND == SRL_ENV_MOBILE_1D) ? 1 : 2;
-    constexpr uint32_t NA = (KIND == SRL_ENV_MOBILE_1D) ? 2u : 4u;
-    constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;  // :257-258
+    constexpr int PF = MOBILE_PF;
+    const int seg = blockIdx.y;
     const uint64_t genv = env_offset + (uint64_t)i;
-    MobileEnvRegs e;
-    mobile_load(m, i, e, TWO);
-    bool targets_dirty = false;
     const size_t N = (size_t)n;
-    ActionChunk<DISCRETE> cur, nxt;
-    load_chunk<DISCRETE>(cur, actions, noise, 0, T, N, (size_t)i);
-    for (int t0 = 0; t0 < T; t0 += MOBILE_PF) {
-        load_chunk<DISCRETE>(nxt, actions, noise, t0 + MOBILE_PF, T, N, (size_t)i);   // in flight while `cur` is stepped
-        // ---------------- pass 1: the serial state chain (mobile_robot_env.py:237-268) ----------------
-        double ddx[MOBILE_PF], ddy[MOBILE_PF];   // what _reward() and getSRLState() are made of: target - position
-        uint32_t bump_mask = 0u, done_mask = 0u, obs_done_mask = 0u, reach_mask = 0u;
-        const double ep_ret0 = e.ep_ret, ep_len0 = e.ep_len;   // the episode sums belong to pass 2
-#pragma unroll
-        for (int k = 0; k < MOBILE_PF; ++k) {
-            const int t = t0 + k;
-            if (t < T) {
-                int a_disc = 0;
-                float a0 = 0.f, a1 = 0.f;
-                if (actions) {
-                    if (DISCRETE) a_disc = cur.a[DISCRETE ? k : 0];
-                    else { a0 = cur.x[DISCRETE ? 0 : k]; a1 = cur.y[DISCRETE ? 0 : k]; }
-                } else {
-                    const uint4 r = philox4x32_10(seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
-                    if (DISCRETE) a_disc = (int)__umulhi(r.x, NA);
-                    else { a0 = (float)((double)r.x * (2.0 / 4294967296.0) - 1.0); a1 = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0); }
-                }
-                // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
-                const double dv = noise ? __dadd_rn(DELTA_POS, (double)cur.nz[k]) : DELTA_POS;
-                e.total_steps += 1;
-                double ax = 0.0, ay = 0.0;
-                if (DISCRETE) {
-                    if (KIND == SRL_ENV_MOBILE_1D) ax = (a_disc & 1) ? dv : -dv;  // 1D_env.py:115
-                    else { const int a = a_disc & 3; ax = (a == 0) ? -dv : (a == 1) ? dv : 0.0; ay = (a == 2) ? -dv : (a == 3) ? dv : 0.0; }  // :242-243
-                } else {
-                    // float32 action array * python float -> float32 product, then += into float64 (:250,255)
-                    const float fdv = (float)dv;
-                    ax = (double)__fmul_rn(fmaxf(fminf(a0, 1.0f), -1.0f), fdv);
-                    ay = (double)__fmul_rn(fmaxf(fminf(a1, 1.0f), -1.0f), fdv);
-                }
-                const double prev_x = e.px, prev_y = e.py;  // :254
-                e.px = __dadd_rn(e.px, ax);
-                if (KIND != SRL_ENV_MOBILE_1D) e.py = __dadd_rn(e.py, ay);
-                bool bumped = (e.px < mx) || (e.px > MAX_X - mx);   // :257-263
-                if (KIND != SRL_ENV_MOBILE_1D) bumped = bumped || (e.py < my) || (e.py > MAX_Y - my);
-                if (bumped) { e.px = prev_x; e.py = prev_y; bump_mask |= 1u << k; }
-                e.has_bumped = bumped ? 1 : 0;
-                e.counter += 1;  // :268
-                const double tx = e.current_target ? e.t1x : e.t0x, ty = e.current_target ? e.t1y : e.t0y;
-                if (KIND == SRL_ENV_MOBILE_LINE_TARGET) {
-                    const double lx = __dsub_rn(tx, LINE_ROBOT_OFFSET);      // line_target_env.py:35-40,113
-                    ddx[k] = __dsub_rn(lx, e.px); ddy[k] = __dsub_rn(lx, e.py);
-                } else {
-                    ddx[k] = __dsub_rn(tx, e.px); ddy[k] = (KIND == SRL_ENV_MOBILE_1D) ? 0.0 : __dsub_rn(ty, e.py);
-                }
-                if (TWO) {  // the target switch feeds later steps: decide it here (2target_env.py:170-173)
-                    const double sq = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k]));
-                    if (sq <= S_THR_04) {
-                        reach_mask |= 1u << k;
-                        if (e.current_target < 1) {
-                            e.current_target += 1;   // the observation of THIS step is already relative to the new target
-                            obs_done_mask |= 1u << k;
-                            if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);
-                        }
-                    }
-                }
-                if (e.counter > max_steps) {  // _termination (:336-343); `terminated` is never set
-                    done_mask |= 1u << k;
-                    if (auto_reset) {
-                        mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
-                        targets_dirty = true;
-                        obs_done_mask |= 1u << k;
-                        if (obs) mobile_store_obs<KIND>(e, obs + (size_t)t * N * D, (size_t)i);   // post-reset observation
-                    }
-                }
-            }
-        }
-        // ---------------- pass 2: rewards and outputs, independent across the chunk (:345-363) ----------------
-        e.ep_ret = ep_ret0; e.ep_len = ep_len0;
-#pragma unroll
-        for (int k = 0; k < MOBILE_PF; ++k) {
-            const int t = t0 + k;
-            if (t < T) {
-                const size_t off = (size_t)t * N + (size_t)i;
-                const bool bumped = (bump_mask >> k) & 1u, is_done = (done_mask >> k) & 1u;
-                double reward;
-                if (shape_reward) {
-                    double distance;
-                    if (KIND == SRL_ENV_MOBILE_LINE_TARGET) distance = fabs(ddx[k]);
-                    else if (KIND == SRL_ENV_MOBILE_1D) distance = __dsqrt_rn(__dmul_rn(ddx[k], ddx[k]));
-                    else distance = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])));  // np.linalg.norm = sqrt(x.dot(x))
-                    reward = -distance;
-                } else {
-                    bool reached;
-                    if (KIND == SRL_ENV_MOBILE_LINE_TARGET) reached = fabs(ddx[k]) <= LINE_REWARD_DIST_THRESHOLD;
-                    else if (TWO) reached = (reach_mask >> k) & 1u;
-                    else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(ddx[k], ddx[k]) <= S_THR_04;
-                    else reached = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])) <= S_THR_04;
-                    reward = reached ? 1.0 : 0.0;
-                    if (bumped) reward = -1.0;
-                }
-                e.ep_ret = __dadd_rn(e.ep_ret, reward);
-                e.ep_len += 1.0;
-                if (rew) rew[off] = (float)reward;
-                if (done) done[off] = is_done ? 1 : 0;
-                if (is_done) {
-                    if (ep_ret) ep_ret[off] = (float)e.ep_ret;
-                    if (ep_len) ep_len[off] = (int32_t)e.ep_len;
-                    if (auto_reset) { e.ep_ret = 0.0; e.ep_len = 0.0; }
-                }
-                if (obs && !((obs_done_mask >> k) & 1u)) {
-                    // getSRLState = getGroundTruth() - getTargetPos() = -(target - position): negation is exact
-                    if (KIND == SRL_ENV_MOBILE_1D) obs[(size_t)t * N + (size_t)i] = -(float)ddx[k];
-                    else reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(-(float)ddx[k], -(float)ddy[k]);
-                }
-            }
-        }
-        cur = nxt;
+    // ---- segment boundaries from the env's step counter alone ----
+    const int4 mt = in.meta[i];
+    int t_done0 = max_steps - mt.x;                 // step at which `counter > max_steps` first holds
+    t_done0 = t_done0 < 0 ? 0 : (t_done0 > T ? T : t_done0);
+    int t_start = 0, t_done = t_done0;
+    if (seg > 0) {                                  // only launched with auto_reset
+        const long long ts = (long long)t_done0 + 1 + (long long)(seg - 1) * ((long long)max_steps + 1);
+        if (ts >= T) return;
+        t_start = (int)ts;
+        t_done = (ts + max_steps > T) ? T : (int)(ts + max_steps);
     }
-    mobile_store(m, i, e, targets_dirty, TWO);
+    if (t_start >= T) return;
+    const int t_end = auto_reset ? (t_done + 1 < T ? t_done + 1 : T) : T;
+    MobileEnvRegs e;
+    if (seg == 0) mobile_load(in, i, e, TWO);
+    else {
+        e.episode = (uint32_t)mt.z + (uint32_t)(seg - 1);
+        e.total_steps = (uint32_t)mt.w + (uint32_t)t_start;
+        mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
+    }
+    const int c_start = e.counter;
+    const uint32_t ts_start = e.total_steps;
+    const double ep_ret0 = e.ep_ret, ep_len0 = e.ep_len;
+    SegmentAcc acc; acc.ret_i = 0; acc.ret_d = e.ep_ret;
+    int t0 = t_start;
+    if (t0 + PF <= t_end) {
+        ActionChunk<DISCRETE, PF> cur, nxt;
+        load_chunk<KIND, DISCRETE, GEN, PF>(cur, actions, noise, t0, N, (size_t)i, seed, genv, ts_start);
+#pragma unroll 1
+        for (; t0 + PF <= t_end; t0 += PF) {
+            if (GEN) {
+                if (t0 != t_start) load_chunk<KIND, DISCRETE, GEN, PF>(cur, actions, noise, t0, N, (size_t)i, seed, genv, ts_start + (uint32_t)(t0 - t_start));
+            } else if (t0 + 2 * PF <= t_end) {
+                load_chunk<KIND, DISCRETE, GEN, PF>(nxt, actions, noise, t0 + PF, N, (size_t)i, seed, genv, 0u);   // in flight while `cur` is stepped
+            }
+            step_chunk<KIND, DISCRETE, SHAPED, PF>(e, acc, cur, t0, t_done, t_start, N, (size_t)i, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+            if (!GEN) cur = nxt;
+        }
+    }
+#pragma unroll 1
+    for (; t0 < t_end; ++t0) {   // tail: fewer than PF steps left in the segment
+        ActionChunk<DISCRETE, 1> one;
+        load_chunk<KIND, DISCRETE, GEN, 1>(one, actions, noise, t0, N, (size_t)i, seed, genv, ts_start + (uint32_t)(t0 - t_start));
+        step_chunk<KIND, DISCRETE, SHAPED, 1>(e, acc, one, t0, t_done, t_start, N, (size_t)i, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+    }
+    const int steps = t_end - t_start;
+    e.counter = c_start + steps;                                   // :268
+    e.total_steps = ts_start + (uint32_t)steps;
+    e.ep_ret = SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i);
+    e.ep_len = ep_len0 + (double)steps;
+    if (auto_reset && t_end - 1 >= t_done) {
+        // the segment ended its episode: SubprocVecEnv resets and returns the POST-RESET observation for that step
+        mobile_reset_env<KIND>(e, nullptr, random_target, seed, genv);
+        if (obs) mobile_store_obs<KIND>(e, obs + (size_t)(t_end - 1) * N * D, (size_t)i);   // same thread, same address: overwrites the terminal one
+    }
+    if (t_end == T) mobile_store(out, i, e, true, TWO);
+}
+
+template <int KIND, bool DISCRETE, bool GEN, bool SHAPED>
+int launch_rollout_variant(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
+                           float* ep_ret, int32_t* ep_len, cudaStream_t st) {
+    // segments per env: 1 + the episodes that can start inside T steps (worst case: the first step ends an episode)
+    const long long per = (long long)s->max_steps + 1;
+    const int nseg = s->auto_reset ? (int)(1 + ((long long)T - 1 + per - 1) / per) : 1;
+    // one warp per CTA while the whole launch is a few warps per SM: spreads the (latency-bound) warps over all 148 SMs
+    const long long warps = (long long)nseg * ((s->n + 31) / 32);
+    int block = warps <= 148 * 16 ? 32 : warps <= 148 * 32 ? 64 : 128;
+    if (s->mobile_block > 0) block = s->mobile_block;
+    const dim3 grid((unsigned)((s->n + block - 1) / block), (unsigned)nseg);
+    mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED><<<grid, block, 0, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
+                                                                                 s->cfg.random_target != 0, s->auto_reset != 0, s->max_steps, s->seed, s->cfg.global_env_offset);
+    SRL_CUDA_OK(cudaGetLastError());
+    const MobileDev tmp = s->mob; s->mob = s->mob_alt; s->mob_alt = tmp;   // stream-ordered: later launches read what this one wrote
+    return 0;
+}
+
+template <int KIND, bool DISCRETE>
+int launch_rollout_da(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
+                      float* ep_ret, int32_t* ep_len, cudaStream_t st) {
+    if (s->cfg.shape_reward)
+        return actions ? launch_rollout_variant<KIND, DISCRETE, false, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                       : launch_rollout_variant<KIND, DISCRETE, true, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
+    return actions ? launch_rollout_variant<KIND, DISCRETE, false, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                   : launch_rollout_variant<KIND, DISCRETE, true, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
 }
 
 template <int KIND>
 int launch_rollout_kind(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
-    // one warp per CTA below ~19k envs: spreads the (latency-bound) warps over all 148 SMs
-    const int block = s->n <= 148 * 128 ? 32 : 64;
-    const int grid = (s->n + block - 1) / block;
-    if (s->cfg.is_discrete)
-        mobile_rollout_kernel<KIND, true><<<grid, block, 0, st>>>(s->mob, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
-                                                                   s->cfg.random_target != 0, s->cfg.shape_reward != 0,
-                                                                   s->auto_reset != 0, s->max_steps, s->seed, s->cfg.global_env_offset);
-    else
-        mobile_rollout_kernel<KIND, false><<<grid, block, 0, st>>>(s->mob, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
-                                                                    s->cfg.random_target != 0, s->cfg.shape_reward != 0,
-                                                                    s->auto_reset != 0, s->max_steps, s->seed, s->cfg.global_env_offset);
-    SRL_CUDA_OK(cudaGetLastError());
-    return 0;
+    return s->cfg.is_discrete ? launch_rollout_da<KIND, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                              : launch_rollout_da<KIND, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
 }
 
 }  // namespace
 
-int mobile_alloc(srl_sim* s) {
-    const size_t N = (size_t)s->n;
-    MobileDev& m = s->mob;
+static int mobile_alloc_one(MobileDev& m, size_t N) {
     SRL_CUDA_OK(cudaMalloc(&m.pos, N * sizeof(double2)));
     SRL_CUDA_OK(cudaMalloc(&m.tgt0, N * sizeof(double2)));
     SRL_CUDA_OK(cudaMalloc(&m.tgt1, N * sizeof(double2)));
@@ -358,10 +438,22 @@ int mobile_alloc(srl_sim* s) {
     return 0;
 }
 
+// Two copies of the 80 B/env state: a rollout reads `mob` and writes `mob_alt`, then the two swap (see the kernel header).
+int mobile_alloc(srl_sim* s) {
+    const size_t N = (size_t)s->n;
+    if (mobile_alloc_one(s->mob, N)) return 1;
+    if (mobile_alloc_one(s->mob_alt, N)) return 1;
+    const char* blk = getenv("SRL_MOBILE_BLOCK");   // CTA-size override for A/B measurements (32 / 64 / 128)
+    s->mobile_block = blk ? atoi(blk) : 0;
+    if (s->mobile_block != 32 && s->mobile_block != 64 && s->mobile_block != 128) s->mobile_block = 0;
+    return 0;
+}
+
 void mobile_free(srl_sim* s) {
-    MobileDev& m = s->mob;
-    cudaFree(m.pos); cudaFree(m.tgt0); cudaFree(m.tgt1); cudaFree(m.meta); cudaFree(m.ep);
-    m = MobileDev{};
+    for (MobileDev* m : {&s->mob, &s->mob_alt}) {
+        cudaFree(m->pos); cudaFree(m->tgt0); cudaFree(m->tgt1); cudaFree(m->meta); cudaFree(m->ep);
+        *m = MobileDev{};
+    }
 }
 
 int mobile_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st) {

@@ -138,3 +138,38 @@ def test_rollout_host_matches_device_rollout(cuda_backend):
     sim.rollout_host(T, acts, None, obs, rew, done)
     assert np.array_equal(obs, dev["obs"]) and np.array_equal(rew, dev["rew"]) and np.array_equal(done, dev["done"])
     assert sim.last_kernel_ms() > 0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("no_auto_reset", [False, True])
+def test_cuda_ragged_counters_and_consecutive_rollouts(kind, no_auto_reset, cuda_backend, oracle_backend):
+    """The episode-parallel rollout derives every segment boundary from the env's step counter: give each env a
+    different counter (including values at and beyond max_steps), run three back-to-back rollouts whose lengths are
+    not multiples of the episode length, and compare everything with the oracle's plain step loop (bit-exact)."""
+    n, Ts = 333, (1, 260, 517)
+    na = 2 if "1D" in kind else 4
+    rs = np.random.RandomState(11)
+    counters = rs.randint(0, 251, size=(n, 1)).astype(np.int32)
+    counters[:8, 0] = [0, 1, 249, 250, 251, 252, 300, 125]
+    outs = []
+    for be in (cuda_backend, oracle_backend):
+        sim = be.make_sim(kind, n, seed=21, random_target=True, shape_reward=(kind == KINDS[0]), no_auto_reset=no_auto_reset)
+        D = sim.obs_dim
+        sim.reset(stream=be.stream())
+        sim.set_state(2, counters)
+        res = []
+        for T in Ts:
+            acts = np.random.RandomState(T).randint(0, na, size=(T, n)).astype(np.int32)
+            obs = be.zeros((T, n, D), np.float32); rew = be.zeros((T, n), np.float32); done = be.zeros((T, n), np.uint8)
+            ep_ret = be.zeros((T, n), np.float32); ep_len = be.zeros((T, n), np.int32)
+            sim.rollout(T, be.from_host(acts), None, obs, rew, done, ep_ret, ep_len, stream=be.stream())
+            res.append([be.to_host(x).copy() for x in (obs, rew, done, ep_ret, ep_len)] +
+                       [sim.get_state(f) for f in (0, 1, 2, 8, 9)])
+        sim.close()
+        outs.append(res)
+    for a, b in zip(*outs):
+        d = a[2].astype(bool)
+        assert np.array_equal(a[2], b[2])
+        for k in (0, 1, 5, 6, 7, 8, 9):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[3][d], b[3][d]) and np.array_equal(a[4][d], b[4][d])
