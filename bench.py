@@ -233,6 +233,8 @@ def run_b200(args):
     obs = be.zeros((T, n, D), np.float32); rew = be.zeros((T, n), np.float32); done = be.zeros((T, n), np.uint8)
     ep_ret = be.zeros((T, n), np.float32); ep_len = be.zeros((T, n), np.int32)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=be.torch_device)  # > 126 MB L2
+    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=be.torch_device)  # 256 MB, only ever read
+    sink = torch.zeros((), dtype=torch.float32, device=be.torch_device)
 
     def step():
         sim.rollout(T, acts, noise, obs, rew, done, ep_ret, ep_len, stream=st)
@@ -253,7 +255,11 @@ def run_b200(args):
     barrier()
     wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.fill_(k & 0xff)            # evict L2 between timed iterations (outside the event bracket)
+        # evict L2 between timed iterations (outside the event bracket): WRITE a buffer larger than L2, then READ another
+        # one so that the timed kernel starts from a cold L2 holding clean lines -- otherwise it would also pay the DRAM
+        # write-back of up to 126 MB of the flush buffer's dirty lines, which is not its traffic
+        flush.fill_(k & 0xff)
+        sink += flush_rd.sum()
         ev[k][0].record()
         step()
         ev[k][1].record()
@@ -319,7 +325,7 @@ def run_b200(args):
             "dtype": "f32" if args.workload == "kuka" else "f64", "data": "synthetic",
             "config": {"workload": "%s ground_truth, %d envs/GPU, one bench step = one fused rollout of T=%d env steps (random discrete actions%s)"
                                    % (spec["env_id"], n, T, " + N(0,0.01) step noise" if args.workload == "kuka" else ""),
-                       "envs_per_gpu": n, "env_steps_per_bench_step": n * T, "l2_flush_between_steps": True, "parallelism": "env-shard x%d" % world},
+                       "envs_per_gpu": n, "env_steps_per_bench_step": n * T, "l2_flush_between_steps": "write 256 MB + read 256 MB between timed steps, outside the event bracket", "parallelism": "env-shard x%d" % world},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": units * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof,

@@ -77,7 +77,7 @@ typedef struct srl_cfg {
     int32_t  random_target;     /* randomise button / target position at reset                 */
     int32_t  force_down;        /* Kuka: remove the "up" action                                */
     int32_t  shape_reward;      /* reward = -distance (and 50/-250 on continuous Kuka)         */
-    int32_t  action_joints;     /* Kuka joint-space actions (not implemented: create() fails)  */
+    int32_t  action_joints;     /* Kuka joint-space actions f32[N,7] (continuous only)         */
     int32_t  action_repeat;     /* Kuka physics sub-steps per env step (>=1)                   */
     int32_t  max_steps;         /* 0 = reference default for the env kind (1000 / 250)         */
     int32_t  solver_iterations; /* 0 = 150 (setPhysicsEngineParameter)                        */
@@ -123,7 +123,8 @@ int srl_sim_create(srl_sim** out, int env_kind, int num_envs, int device, const 
  *   MobileRobot R=6: x_start, y_start, x_target, y_target, x_target2, y_target2 -- the final
  *                    values, not the raw uniforms (mobile_robot_env.py:168-181,
  *                    mobile_robot_2target_env.py:52-69); unused slots are ignored
- *   Kuka        R=18: button x_pos, y_pos, then 5 x (dx,dy,dz) random init actions
+ *   Kuka        R=18: button x_pos, y_pos, then 5 x (dx,dy,dz) random init actions (action_joints: the common joint
+ *                     set-point offset DELTA_THETA * normal in the dx slot, kuka_button_gym_env.py:257-260)
  *                     (kuka_button_gym_env.py:227-234,250-268), then the signed button speed of
  *                     KukaMovingButtonGymEnv (kuka_moving_button_gym_env.py:33; 0 for the other kinds)
  * `obs_out` (nullable): f32[N, D] observation after reset (rows of unmasked envs untouched). */
@@ -132,7 +133,7 @@ int srl_sim_reset(srl_sim* sim, const uint8_t* mask, const double* reset_draws, 
 
 /* One env step for every env (lockstep), with SubprocVecEnv auto-reset semantics: where
  * done, the env is reset and `obs_out` holds the post-reset observation.
- *   actions : i32[N] (discrete) or f32[N, A] (continuous; A = 3 Kuka, 2 Mobile); a negative
+ *   actions : i32[N] (discrete) or f32[N, A] (continuous; A = 3 Kuka, 7 Kuka with action_joints, 2 Mobile); a negative
  *             discrete action is the reference's `step(None)` (zero action, Kuka only)
  *   noise   : nullable f32[N], the value of the `np_random.normal(0, NOISE_STD)` draw of this
  *             step (kuka_button_gym_env.py:305,327; mobile_robot_env.py:241,248); NULL =

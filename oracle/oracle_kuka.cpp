@@ -624,12 +624,14 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
 }
 
 /* One p.stepSimulation() preceded by Kuka.applyAction's IK + motor set-points (kuka.py:142-187). */
-static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterations, StepScratch& sc) {
+static void physics_step(const KModel& m, KEnv& e, int button_armed, int iterations, StepScratch& sc, const double* q_joints = NULL) {
     Kin k;
     forward_kinematics(m, e.q, k);
-    /* applyAction: IK at the current joint state, then the 12 POSITION_CONTROL set-points */
+    /* applyAction: IK at the current joint state, then the 12 POSITION_CONTROL set-points;
+       use_inverse_kinematics=False (action_joints, kuka.py:158-161): the 7 arm set-points are the motor commands themselves */
     double q_ik[NB];
-    inverse_kinematics(m, k, e.q, e.ee, q_ik);
+    if (q_joints) { for (int i = 0; i < NB; ++i) q_ik[i] = i < 7 ? q_joints[i] : 0.0; }
+    else inverse_kinematics(m, k, e.q, e.ee, q_ik);
     const double finger_angle = 0.0; /* kuka_button_gym_env.py:313,334 */
     MotorCmd cmd[NB];
     for (int i = 0; i < NB; ++i) {
@@ -684,9 +686,11 @@ static void make_snapshot(KukaWorld& w, const srl_sim* s) {
     for (int a = 0; a < 3; ++a) { e.ee[a] = w.m.sc[KM_SC_EE_INIT + a]; e.button_base[a] = w.m.sc[KM_SC_BUTTON_BASE + a]; }
     e.ee_angle = 0.0;
     const double zero[3] = {0, 0, 0};
+    double qj[7];
+    for (int j = 0; j < 7; ++j) qj[j] = w.m.b[j].qinit; /* self._kuka.joint_positions[:7] (:244) */
     for (int t = 0; t < 500; ++t) { /* :242-247 */
-        apply_ee_delta(w, s, e, zero);
-        physics_step(w.m, e, 0, w.iterations, w.scratch);
+        if (s->cfg.action_joints) physics_step(w.m, e, 0, w.iterations, w.scratch, qj);
+        else { apply_ee_delta(w, s, e, zero); physics_step(w.m, e, 0, w.iterations, w.scratch); }
     }
     w.snapshot = e;
 }
@@ -729,7 +733,11 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
         for (int k = 0; k < 5; ++k) { /* :250-266 */
             philox4x32_10(s->seed, genv, episode, PHILOX_PURPOSE_RESET0 + 1 + k, r);
             d[2 + 3 * k] = d[3 + 3 * k] = d[4 + 3 * k] = 0.0;
-            if (s->cfg.is_discrete) {
+            if (s->cfg.action_joints) {
+                /* joints += DELTA_THETA * np_random.normal(joints.shape): ONE draw from N(loc=7, 1), broadcast to the 7 joints (:257-260) */
+                const double u1 = philox_u01(r[0], r[1]), u2 = philox_u01(r[2], r[3]);
+                d[2 + 3 * k] = 0.1 * (7.0 + sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * M_PI * u2));
+            } else if (s->cfg.is_discrete) {
                 const double sign = philox_u01(r[0], r[1]) > 0.5 ? 1.0 : -1.0; /* np_random.rand() > 0.5 */
                 const int idx = (int)(((uint64_t)r[2] * 3u) >> 32);            /* np_random.randint(3) */
                 d[2 + 3 * k + idx] = sign * 0.03;                               /* DELTA_V */
@@ -752,8 +760,14 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
     e.btn_speed = (s->kind == SRL_ENV_KUKA_MOVING_BUTTON) ? d[17] : 0.0;
     if (s->cfg.random_target) { e.button_base[0] = d[0]; e.button_base[1] = d[1]; }
     for (int k = 0; k < 5; ++k) { /* N_RANDOM_ACTIONS_AT_INIT, :250-269 */
-        apply_ee_delta(w, s, e, d + 2 + 3 * k);
-        physics_step(w.m, e, 0, w.iterations, w.scratch);
+        if (s->cfg.action_joints) {
+            double qj[7];
+            for (int j = 0; j < 7; ++j) qj[j] = w.m.b[j].qinit + d[2 + 3 * k];
+            physics_step(w.m, e, 0, w.iterations, w.scratch, qj);
+        } else {
+            apply_ee_delta(w, s, e, d + 2 + 3 * k);
+            physics_step(w.m, e, 0, w.iterations, w.scratch);
+        }
     }
     /* :273-274  button_pos = link state of the button link (COM = link origin) + BUTTON_DISTANCE_HEIGHT */
     e.button_pos[0] = e.button_base[0];
@@ -776,7 +790,9 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
     /* ---- step(): action decoding + noise (:293-340) ---- */
     double d[3] = {0, 0, 0};
     double nz = 0.0;
-    const double noise_std = s->cfg.is_discrete ? 0.01 : 0.0001; /* NOISE_STD, NOISE_STD_CONTINUOUS (:31-32) */
+    const double noise_std = s->cfg.action_joints ? 0.002 : s->cfg.is_discrete ? 0.01 : 0.0001; /* NOISE_STD_JOINTS, NOISE_STD, NOISE_STD_CONTINUOUS (:31-33) */
+    double qj[7];
+    const bool joints = s->cfg.action_joints != 0;
     if (noise) nz = (double)noise[i];
     else {
         uint32_t r[4];
@@ -786,7 +802,20 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
     }
     uint32_t ra[4] = {0, 0, 0, 0};
     if (!actions) philox4x32_10(s->seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION, ra);
-    if (s->cfg.is_discrete) {
+    if (joints) {
+        /* real_action = action * (DELTA_THETA + N(0, NOISE_STD_JOINTS)) + joint_positions[:7]  (:317-323); the set-points are
+           relative to the INITIAL joint vector, which the reference never updates (kuka.py:65-66) */
+        float a[7];
+        if (actions) { for (int k = 0; k < 7; ++k) a[k] = ((const float*)actions)[7 * (size_t)i + k]; }
+        else {
+            uint32_t rb[4];
+            philox4x32_10(s->seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION + 1, rb);
+            for (int k = 0; k < 4; ++k) a[k] = (float)((double)ra[k] * (2.0 / 4294967296.0) - 1.0);
+            for (int k = 0; k < 3; ++k) a[4 + k] = (float)((double)rb[k] * (2.0 / 4294967296.0) - 1.0);
+        }
+        const double d_theta = 0.1 + nz;
+        for (int k = 0; k < 7; ++k) qj[k] = (double)a[k] * d_theta + w.m.b[k].qinit;
+    } else if (s->cfg.is_discrete) {
         const int a = actions ? ((const int32_t*)actions)[i] : (int)(((uint64_t)ra[0] * 6u) >> 32);
         if (a >= 0) { /* a < 0: step(None) -> zero action, no noise (:295-299) */
             const double dv = 0.03 + nz; /* DELTA_V + N(0, NOISE_STD) */
@@ -813,8 +842,8 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
     }
     /* ---- step2() (:342-368) ---- */
     for (int rep = 0; rep < s->cfg.action_repeat; ++rep) {
-        apply_ee_delta(w, s, e, d);
-        physics_step(w.m, e, 1, w.iterations, w.scratch);
+        if (joints) physics_step(w.m, e, 1, w.iterations, w.scratch, qj);
+        else { apply_ee_delta(w, s, e, d); physics_step(w.m, e, 1, w.iterations, w.scratch); }
         if (e.terminated || e.counter > w.max_steps) break; /* _termination() */
         e.counter += 1;
     }

@@ -637,10 +637,15 @@ KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
 
 // One applyAction + stepSimulation.  `k`/`ct` hold the kinematics / contacts of the CURRENT configuration
 // (computed by the caller with kuka_fk<true>); on return q, qd, qb, qdb are advanced by one time step.
-KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed) {
+// JOINTS: use_inverse_kinematics = False (action_joints): the 7 arm set-points are given (`q_joints`), no IK (kuka.py:158-161).
+template <bool JOINTS>
+KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed, const float* q_joints) {
     // ---- applyAction: IK + motor set-points (kuka.py:142-187) ----
     float q_ik[7];
-    kuka_ik(P, e, k, q_ik);
+    if (JOINTS) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) q_ik[j] = q_joints[j];
+    } else kuka_ik(P, e, k, q_ik);
     // ---- dynamics ----
     float A[KK_NB][KK_NB], bias[KK_NB];
 #if KK_ROLL_DYN

@@ -33,8 +33,8 @@ struct KukaDev {
 
 namespace {
 
-constexpr float DELTA_V = 0.03f, DELTA_V_CONTINUOUS = 0.0035f;            // kuka_button_gym_env.py:27-28
-constexpr double NOISE_STD = 0.01, NOISE_STD_CONTINUOUS = 0.0001;          // :31-32
+constexpr float DELTA_V = 0.03f, DELTA_V_CONTINUOUS = 0.0035f, DELTA_THETA = 0.1f;   // kuka_button_gym_env.py:27-29
+constexpr double NOISE_STD = 0.01, NOISE_STD_CONTINUOUS = 0.0001, NOISE_STD_JOINTS = 0.002;   // :31-33
 constexpr int N_CONTACTS_BEFORE_TERMINATION = 5, N_STEPS_OUTSIDE_SAFETY_SPHERE = 5000, N_RANDOM_ACTIONS_AT_INIT = 5;
 
 KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
@@ -85,7 +85,12 @@ KK_DEV void reset_action(const KukaParams& P, const double* __restrict__ d17, ui
     dx = dy = dz = 0.f;
     if (d17) { dx = (float)d17[2 + 3 * s]; dy = (float)d17[3 + 3 * s]; dz = (float)d17[4 + 3 * s]; return; }
     const uint4 r = philox4x32_10(P.seed, genv, episode, PHILOX_PURPOSE_RESET0 + 1 + s);
-    if (P.is_discrete) {
+    if (P.action_joints) {
+        // joints += DELTA_THETA * np_random.normal(joints.shape): ONE draw from N(loc=7, 1), broadcast to the 7 joints (:257-260);
+        // carried in dx as the common set-point offset
+        const double u1 = philox_u01(r.x, r.y), u2 = philox_u01(r.z, r.w);
+        dx = (float)(0.1 * (7.0 + sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2)));
+    } else if (P.is_discrete) {
         const float sign = philox_u01(r.x, r.y) > 0.5 ? 1.f : -1.f;     // np_random.rand() > 0.5
         const uint32_t idx = __umulhi(r.z, 3u);                          // np_random.randint(3)
         dx = idx == 0 ? sign * DELTA_V : 0.f; dy = idx == 1 ? sign * DELTA_V : 0.f; dz = idx == 2 ? sign * DELTA_V : 0.f;
@@ -149,6 +154,7 @@ enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2 };
 //   op = ROLLOUT: T env steps (step() + step2() + _reward() + _termination() + VecEnv auto-reset)
 //   op = RESET  : reset() of the masked envs with optional host-supplied draws
 //   op = SETTLE : the 500 zero-action steps of reset() (:242-247), identical for every episode -> snapshot
+template <bool JOINTS>
 __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
                                                        const void* __restrict__ actions, const float* __restrict__ noise,
                                                        const uint8_t* __restrict__ mask, const double* __restrict__ draws,
@@ -170,6 +176,9 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     int rep = 0, t = 0;
     int saved_cb = 0, saved_ct = 0;
     float dx = 0.f, dy = 0.f, dz = 0.f;
+    float qj[JOINTS ? 7 : 1];   // joint-space micro action: the 7 arm set-points (action_joints)
+#pragma unroll
+    for (int j = 0; j < (JOINTS ? 7 : 1); ++j) qj[j] = 0.f;
     const double* d17 = nullptr;
     if (op == KUKA_OP_RESET) {
         d17 = draws ? draws + (size_t)i * 18 : nullptr;
@@ -238,6 +247,10 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         if (in_reset) {
             if (op == KUKA_OP_SETTLE) { dx = dy = dz = 0.f; }
             else reset_action(P, d17, genv, e.episode, N_RANDOM_ACTIONS_AT_INIT - reset_left, dx, dy, dz);
+            if (JOINTS) {   // settle: the initial joint vector (:244); random init: the same vector + one common offset (:257-260)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) qj[JOINTS ? j : 0] = P.qinit[j] + dx;
+            }
             --reset_left;
             armed = false;  // the button motor is only commanded from step2() (:347)
         } else {
@@ -249,12 +262,29 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 else {
                     const uint4 r = philox4x32_10(P.seed, genv, e.total_steps, PHILOX_PURPOSE_NOISE);
                     const double u1 = philox_u01(r.x, r.y), u2 = philox_u01(r.z, r.w);
-                    nz = (float)((P.is_discrete ? NOISE_STD : NOISE_STD_CONTINUOUS) * sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2));
+                    nz = (float)((JOINTS ? NOISE_STD_JOINTS : P.is_discrete ? NOISE_STD : NOISE_STD_CONTINUOUS) * sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2));
                 }
                 dx = dy = dz = 0.f;
                 uint4 ra = make_uint4(0, 0, 0, 0);
                 if (!actions) ra = philox4x32_10(P.seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION);
-                if (P.is_discrete) {
+                if (JOINTS) {
+                    // real_action = action * (DELTA_THETA + N(0, NOISE_STD_JOINTS)) + joint_positions[:7] (:317-323): set-points
+                    // relative to the INITIAL joint vector, which the reference never updates (kuka.py:65-66)
+                    float a7[7];
+                    if (actions) {
+                        const float* ap = reinterpret_cast<const float*>(actions) + 7 * off;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) a7[j] = __ldg(ap + j);
+                    } else {
+                        const uint4 rb = philox4x32_10(P.seed, genv, e.total_steps, PHILOX_PURPOSE_ACTION + 1);
+                        const uint32_t w[7] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z};
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) a7[j] = (float)((double)w[j] * (2.0 / 4294967296.0) - 1.0);
+                    }
+                    const float d_theta = DELTA_THETA + nz;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) qj[JOINTS ? j : 0] = fmaf(a7[j], d_theta, P.qinit[j]);
+                } else if (P.is_discrete) {
                     const int a = actions ? __ldg(reinterpret_cast<const int32_t*>(actions) + off) : (int)__umulhi(ra.x, 6u);
                     if (a >= 0) {  // a < 0 is the reference's step(None): zero action (:295-299)
                         const float dv = DELTA_V + nz;
@@ -290,9 +320,9 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             armed = true;
         }
         // ---- applyAction + stepSimulation ----
-        apply_ee_delta(P, e, dx, dy, dz);
+        if (!JOINTS) apply_ee_delta(P, e, dx, dy, dz);
         saved_cb = new_cb; saved_ct = new_ct;
-        kuka_physics_step(P, e, k, ct, armed);
+        kuka_physics_step<JOINTS>(P, e, k, ct, armed, qj);
         if (!in_reset) {
             // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
             if (e.terminated || e.counter > P.max_steps) { pending = true; rep = 0; }
@@ -369,6 +399,8 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
     P.shape_reward = s->cfg.shape_reward; P.action_repeat = s->cfg.action_repeat; P.max_steps = s->max_steps;
     P.auto_reset = s->auto_reset; P.max_distance = s->cfg.max_distance;
     P.moving_button = s->kind == SRL_ENV_KUKA_MOVING_BUTTON;
+    P.action_joints = s->cfg.action_joints != 0;
+    for (int j = 0; j < 7; ++j) P.qinit[j] = P.snap_q[j];   // snap_q still holds the initial joint vector here
     P.seed = s->seed; P.env_offset = s->cfg.global_env_offset;
     return true;
 }
@@ -408,7 +440,8 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
     float* snap = nullptr;
     SRL_CUDA_OK(cudaMalloc(&snap, 32 * sizeof(float)));
     { const int save_epw = d->epw; d->epw = 1;
-      kuka_kernel<<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
+      if (d->P.action_joints) kuka_kernel<true><<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
+      else kuka_kernel<false><<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
       d->epw = save_epw; }
     SRL_CUDA_OK(cudaGetLastError());
     float h[32];
@@ -432,7 +465,8 @@ void kuka_free(srl_sim* s) {
 int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st) {
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
-    kuka_kernel<<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (d->P.action_joints) kuka_kernel<true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else kuka_kernel<false><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -441,7 +475,8 @@ int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noi
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
-    kuka_kernel<<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
+    if (d->P.action_joints) kuka_kernel<true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
+    else kuka_kernel<false><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -55,6 +55,8 @@ struct KukaParams {
     float snap_q[KK_NB], snap_qd[KK_NB], snap_ee[3], snap_qb, snap_qdb;
     // ---- env configuration ----
     int   is_discrete, random_target, force_down, shape_reward, action_repeat, max_steps, auto_reset;
+    int   action_joints;   // joint-space actions: use_inverse_kinematics = False (kuka_button_gym_env.py:238, kuka.py:158-161)
+    float qinit[7];        // initial arm joint vector (kuka.py:65-66): what joint-space set-points are relative to
     int   moving_button;   // KukaMovingButtonGymEnv: the button slides along y (kuka_moving_button_gym_env.py:109-119)
     float max_distance;
     uint64_t seed, env_offset;

@@ -178,22 +178,24 @@ constexpr double S_THR_04 = 0x1.47ae147ae147cp-3;
 #define MOBILE_PF 8                 // steps per chunk (measured on B200, 8192 envs x 1024 steps: 2 -> 96 us, 4 -> 67 us, 8 -> 54-58 us)
 #endif
 
-template <bool DISCRETE, int NS>
+template <bool DISCRETE, bool NOISE, int NS>
 struct ActionChunk {
     int a[DISCRETE ? NS : 1];
     float x[DISCRETE ? 1 : NS], y[DISCRETE ? 1 : NS];
-    float nz[NS];
+    float nz[NOISE ? NS : 1];
 };
 
-// actions of steps [t0, t0 + NS) of env i: from HBM, or (GEN) the env's own stream -- the reference's random agent
-template <int KIND, bool DISCRETE, bool GEN, int NS>
-__device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE, NS>& c, const void* __restrict__ actions, const float* __restrict__ noise,
-                                           int t0, size_t N, size_t i, uint64_t seed, uint64_t genv, uint32_t total_steps0) {
+// actions of steps [t0, t0 + NS) of env i (idx0 = t0 * N + i): from HBM, or (GEN) the env's own stream -- the reference's random agent
+template <int KIND, bool DISCRETE, bool GEN, bool NOISE, int NS>
+__device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE, NOISE, NS>& c, const void* __restrict__ actions, const float* __restrict__ noise,
+                                           size_t N, size_t idx0, uint64_t seed, uint64_t genv, uint32_t total_steps0, int nvalid = NS) {
     constexpr uint32_t NA = (KIND == SRL_ENV_MOBILE_1D) ? 2u : 4u;
+    size_t idx = idx0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const size_t off = (size_t)(t0 + k) * N + i;
-        if (GEN) {
+        if (k >= nvalid) {   // past the end of the segment: never stepped, never dereferenced
+            c.a[DISCRETE ? k : 0] = 0; c.x[DISCRETE ? 0 : k] = 0.f; c.y[DISCRETE ? 0 : k] = 0.f; if (NOISE) c.nz[NOISE ? k : 0] = 0.f;
+        } else if (GEN) {
             const uint4 r = philox4x32_10(seed, genv, total_steps0 + (uint32_t)k, PHILOX_PURPOSE_ACTION);
             if (DISCRETE) c.a[DISCRETE ? k : 0] = (int)__umulhi(r.x, NA);
             else {
@@ -201,12 +203,13 @@ __device__ __forceinline__ void load_chunk(ActionChunk<DISCRETE, NS>& c, const v
                 c.y[DISCRETE ? 0 : k] = (float)((double)r.y * (2.0 / 4294967296.0) - 1.0);
             }
         } else if (DISCRETE) {
-            c.a[DISCRETE ? k : 0] = __ldg(reinterpret_cast<const int32_t*>(actions) + off);
+            c.a[DISCRETE ? k : 0] = __ldg(reinterpret_cast<const int32_t*>(actions) + idx);
         } else {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + off);
+            const float2 v = __ldg(reinterpret_cast<const float2*>(actions) + idx);
             c.x[DISCRETE ? 0 : k] = v.x; c.y[DISCRETE ? 0 : k] = v.y;
         }
-        c.nz[k] = noise ? __ldg(noise + off) : 0.f;
+        if (NOISE && k < nvalid) c.nz[NOISE ? k : 0] = noise ? __ldg(noise + idx) : 0.f;
+        idx += N;
     }
 }
 
@@ -215,23 +218,28 @@ struct SegmentAcc {        // per-segment running values that are not part of th
     double ret_d;          // shaped: the float64 episode return, accumulated in step order
 };
 
-template <int KIND, bool DISCRETE, bool SHAPED, int NS>
-__device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, const ActionChunk<DISCRETE, NS>& cur,
-                                           int t0, int t_done, int t_start, size_t N, size_t i, double ep_ret0, double ep_len0,
+// NS steps of one env.  FAST = no noise stream and obs / rew / done all present (the rollout a trainer asks for): no per-step
+// pointer tests, dv is the constant DELTA_POS.  MAYDONE = false: the caller guarantees that no step of the chunk ends an
+// episode (true for every full chunk of a segment: an episode can only end on the segment's last step), so `done` is a
+// constant 0 and the episode statistics are not touched.
+template <int KIND, bool DISCRETE, bool SHAPED, bool FAST, bool MAYDONE, int NS>
+__device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, const ActionChunk<DISCRETE, !FAST, NS>& cur,
+                                           int t0, int t_done, int t_start, size_t N, size_t idx0, double ep_ret0, double ep_len0,
                                            float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
-                                           float* __restrict__ ep_ret, int32_t* __restrict__ ep_len) {
+                                           float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int nvalid = NS) {
     constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
-    constexpr int D = (KIND == SRL_ENV_MOBILE_1D) ? 1 : 2;
     constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;  // :257-258
     // ---------------- pass 1: the serial state chain (mobile_robot_env.py:237-268) ----------------
-    double ddx[NS], ddy[NS];   // what _reward() and getSRLState() are made of: target - position
+    // odx / ody = position - target: the observation (getSRLState = getGroundTruth() - getTargetPos(), srl_env.py:39-42) and,
+    // up to an exact sign flip, the vector _reward() takes the norm of (:345-353)
+    double odx[NS], ody[NS];
     float ox[TWO ? NS : 1], oy[TWO ? NS : 1];   // 2-target: the observation is relative to the target AFTER a switch
     uint32_t bump_mask = 0u, reach_mask = 0u;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241); nz is 0.0f without a noise
-        // stream and DELTA_POS + 0.0 is exact
-        const double dv = __dadd_rn(DELTA_POS, (double)cur.nz[k]);
+        if (MAYDONE && k >= nvalid) { odx[k] = 0.0; ody[k] = 0.0; if (TWO) { ox[TWO ? k : 0] = 0.f; oy[TWO ? k : 0] = 0.f; } continue; }   // tail chunk: only its first nvalid steps exist
+        // dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD), NOISE_STD = 0.0 (:239-241)
+        const double dv = FAST ? DELTA_POS : __dadd_rn(DELTA_POS, (double)cur.nz[FAST ? 0 : k]);
         double ax = 0.0, ay = 0.0;
         if (DISCRETE) {
             // dx = [-dv, dv, 0, 0][a], dy = [0, 0, -dv, dv][a] (:242-243; 1D_env.py:115), branch-free: even actions flip the
@@ -259,13 +267,13 @@ __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, co
         bump_mask |= (bumped ? 1u : 0u) << k;
         const double tx = e.current_target ? e.t1x : e.t0x, ty = e.current_target ? e.t1y : e.t0y;
         if (KIND == SRL_ENV_MOBILE_LINE_TARGET) {
-            const double lx = __dsub_rn(tx, LINE_ROBOT_OFFSET);      // line_target_env.py:35-40,113
-            ddx[k] = __dsub_rn(lx, e.px); ddy[k] = __dsub_rn(lx, e.py);
+            const double lx = __dsub_rn(tx, LINE_ROBOT_OFFSET);      // line_target_env.py:35-40,113: a 1-vector, broadcast
+            odx[k] = __dsub_rn(e.px, lx); ody[k] = __dsub_rn(e.py, lx);
         } else {
-            ddx[k] = __dsub_rn(tx, e.px); ddy[k] = (KIND == SRL_ENV_MOBILE_1D) ? 0.0 : __dsub_rn(ty, e.py);
+            odx[k] = __dsub_rn(e.px, tx); ody[k] = (KIND == SRL_ENV_MOBILE_1D) ? 0.0 : __dsub_rn(e.py, ty);
         }
         if (TWO) {  // the target switch feeds later steps: decide it here (2target_env.py:170-173)
-            const double sq = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k]));
+            const double sq = __dadd_rn(__dmul_rn(odx[k], odx[k]), __dmul_rn(ody[k], ody[k]));
             if (sq <= S_THR_04) {
                 reach_mask |= 1u << k;
                 if (e.current_target < 1) e.current_target += 1;   // the observation of THIS step is already relative to the new target
@@ -274,47 +282,50 @@ __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, co
             ox[TWO ? k : 0] = (float)__dsub_rn(e.px, ux); oy[TWO ? k : 0] = (float)__dsub_rn(e.py, uy);
         }
     }
-    e.has_bumped = (bump_mask >> (NS - 1)) & 1u;
+    e.has_bumped = (bump_mask >> ((MAYDONE ? nvalid : NS) - 1)) & 1u;
     // ---------------- pass 2: rewards and outputs, independent across the chunk (:345-363) ----------------
+    size_t idx = idx0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const int t = t0 + k;
-        const size_t off = (size_t)t * N + i;
-        const bool bumped = (bump_mask >> k) & 1u, is_done = t >= t_done;   // _termination (:336-343); `terminated` is never set
+        if (MAYDONE && k >= nvalid) break;
+        const bool bumped = (bump_mask >> k) & 1u;
         float reward_f;
         if (SHAPED) {
             double distance;
-            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) distance = fabs(ddx[k]);
-            else if (KIND == SRL_ENV_MOBILE_1D) distance = __dsqrt_rn(__dmul_rn(ddx[k], ddx[k]));
-            else distance = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])));  // np.linalg.norm = sqrt(x.dot(x))
+            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) distance = fabs(odx[k]);
+            else if (KIND == SRL_ENV_MOBILE_1D) distance = __dsqrt_rn(__dmul_rn(odx[k], odx[k]));
+            else distance = __dsqrt_rn(__dadd_rn(__dmul_rn(odx[k], odx[k]), __dmul_rn(ody[k], ody[k])));  // np.linalg.norm = sqrt(x.dot(x))
             acc.ret_d = __dadd_rn(acc.ret_d, -distance);
             reward_f = (float)(-distance);
         } else {
             bool reached;
-            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) reached = fabs(ddx[k]) <= LINE_REWARD_DIST_THRESHOLD;
+            if (KIND == SRL_ENV_MOBILE_LINE_TARGET) reached = fabs(odx[k]) <= LINE_REWARD_DIST_THRESHOLD;
             else if (TWO) reached = (reach_mask >> k) & 1u;
-            else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(ddx[k], ddx[k]) <= S_THR_04;
-            else reached = __dadd_rn(__dmul_rn(ddx[k], ddx[k]), __dmul_rn(ddy[k], ddy[k])) <= S_THR_04;
-            const int r = bumped ? -1 : (reached ? 1 : 0);
-            acc.ret_i += r;
-            reward_f = (float)r;
+            else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(odx[k], odx[k]) <= S_THR_04;
+            else reached = __dadd_rn(__dmul_rn(odx[k], odx[k]), __dmul_rn(ody[k], ody[k])) <= S_THR_04;
+            acc.ret_i += bumped ? -1 : (reached ? 1 : 0);
+            reward_f = bumped ? -1.f : (reached ? 1.f : 0.f);
         }
-        if (rew) rew[off] = reward_f;
-        if (done) done[off] = is_done ? 1 : 0;
-        if (is_done) {   // Monitor-style episode statistics (environments/utils.py:53-54)
-            if (ep_ret) ep_ret[off] = (float)(SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i));
-            if (ep_len) ep_len[off] = (int32_t)ep_len0 + (t - t_start + 1);
+        if (FAST || rew) rew[idx] = reward_f;
+        if (MAYDONE) {
+            const int t = t0 + k;
+            const bool is_done = t >= t_done;   // _termination (:336-343); `terminated` is never set
+            if (FAST || done) done[idx] = is_done ? 1 : 0;
+            if (is_done) {   // Monitor-style episode statistics (environments/utils.py:53-54)
+                if (ep_ret) ep_ret[idx] = (float)(SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i));
+                if (ep_len) ep_len[idx] = (int32_t)ep_len0 + (t - t_start + 1);
+            }
+        } else if (FAST || done) done[idx] = 0;
+        if (FAST || obs) {
+            if (KIND == SRL_ENV_MOBILE_1D) obs[idx] = (float)odx[k];
+            else if (TWO) reinterpret_cast<float2*>(obs)[idx] = make_float2(ox[TWO ? k : 0], oy[TWO ? k : 0]);
+            else reinterpret_cast<float2*>(obs)[idx] = make_float2((float)odx[k], (float)ody[k]);
         }
-        if (obs) {
-            // getSRLState = getGroundTruth() - getTargetPos() = -(target - position): negation is exact
-            if (KIND == SRL_ENV_MOBILE_1D) obs[off] = -(float)ddx[k];
-            else if (TWO) reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(ox[TWO ? k : 0], oy[TWO ? k : 0]);
-            else reinterpret_cast<float2*>(obs + (size_t)t * N * D)[i] = make_float2(-(float)ddx[k], -(float)ddy[k]);
-        }
+        idx += N;
     }
 }
 
-template <int KIND, bool DISCRETE, bool GEN, bool SHAPED>
+template <int KIND, bool DISCRETE, bool GEN, bool SHAPED, bool FAST>
 __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, MobileDev out, int n, int T, const void* __restrict__ actions,
                                                              const float* __restrict__ noise, float* __restrict__ obs,
                                                              float* __restrict__ rew, uint8_t* __restrict__ done,
@@ -342,8 +353,9 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     }
     if (t_start >= T) return;
     const int t_end = auto_reset ? (t_done + 1 < T ? t_done + 1 : T) : T;
+    const int t_plain = t_done < t_end ? t_done : t_end;   // steps [t_start, t_plain) cannot end an episode
     MobileEnvRegs e;
-    if (seg == 0) mobile_load(in, i, e, TWO);
+    if (seg == 0) mobile_load(in, i, e, TWO);   // independent of the boundary arithmetic above: these loads overlap the meta load
     else {
         e.episode = (uint32_t)mt.z + (uint32_t)(seg - 1);
         e.total_steps = (uint32_t)mt.w + (uint32_t)t_start;
@@ -354,25 +366,38 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     const double ep_ret0 = e.ep_ret, ep_len0 = e.ep_len;
     SegmentAcc acc; acc.ret_i = 0; acc.ret_d = e.ep_ret;
     int t0 = t_start;
-    if (t0 + PF <= t_end) {
-        ActionChunk<DISCRETE, PF> cur, nxt;
-        load_chunk<KIND, DISCRETE, GEN, PF>(cur, actions, noise, t0, N, (size_t)i, seed, genv, ts_start);
+    size_t idx = (size_t)t_start * N + (size_t)i;          // element index of (t0, env i) in the [T, N] streams
+    const size_t chunk_stride = (size_t)PF * N;
+    // The steps after the last full plain chunk -- at most PF - 1 plain ones and the step that ends the episode -- run as ONE
+    // masked chunk; its actions are requested now, so their latency hides behind the whole main loop.
+    const int n_full = (t_plain - t_start) / PF;
+    const int t_tail = t_start + n_full * PF;
+    ActionChunk<DISCRETE, !FAST, PF> tl;
+    int tail_valid = t_end - t_tail < PF ? t_end - t_tail : PF;
+    if (!GEN) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(tl, actions, noise, N, idx + (size_t)n_full * chunk_stride, seed, genv, 0u, tail_valid);
+    if (n_full > 0) {
+        // register ring of three chunks: the loads of chunk c + 2 are issued before chunk c is stepped.  One chunk ahead was
+        // not enough (ncu: 23 % of all stall samples sat on the `cur = nxt` copy waiting for the load -- with ~9 warps per SM
+        // writing 1.4 GB/ms the loaded memory latency exceeds one chunk's ~2000 cycles).
+        ActionChunk<DISCRETE, !FAST, PF> c0, c1, c2;
+        load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start);
+        if (!GEN && n_full > 1) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c1, actions, noise, N, idx + chunk_stride, seed, genv, 0u);
 #pragma unroll 1
-        for (; t0 + PF <= t_end; t0 += PF) {
+        for (; t0 < t_tail; t0 += PF, idx += chunk_stride) {
             if (GEN) {
-                if (t0 != t_start) load_chunk<KIND, DISCRETE, GEN, PF>(cur, actions, noise, t0, N, (size_t)i, seed, genv, ts_start + (uint32_t)(t0 - t_start));
-            } else if (t0 + 2 * PF <= t_end) {
-                load_chunk<KIND, DISCRETE, GEN, PF>(nxt, actions, noise, t0 + PF, N, (size_t)i, seed, genv, 0u);   // in flight while `cur` is stepped
+                if (t0 != t_start) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start));
+            } else if (t0 + 3 * PF <= t_tail) {
+                load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c2, actions, noise, N, idx + 2 * chunk_stride, seed, genv, 0u);   // in flight for two chunks
             }
-            step_chunk<KIND, DISCRETE, SHAPED, PF>(e, acc, cur, t0, t_done, t_start, N, (size_t)i, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
-            if (!GEN) cur = nxt;
+            step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+            if (!GEN) { c0 = c1; c1 = c2; }
         }
     }
 #pragma unroll 1
-    for (; t0 < t_end; ++t0) {   // tail: fewer than PF steps left in the segment
-        ActionChunk<DISCRETE, 1> one;
-        load_chunk<KIND, DISCRETE, GEN, 1>(one, actions, noise, t0, N, (size_t)i, seed, genv, ts_start + (uint32_t)(t0 - t_start));
-        step_chunk<KIND, DISCRETE, SHAPED, 1>(e, acc, one, t0, t_done, t_start, N, (size_t)i, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+    for (; t0 < t_end; t0 += PF, idx += chunk_stride) {   // one iteration with auto-reset; more only when stepping on past `done`
+        tail_valid = t_end - t0 < PF ? t_end - t0 : PF;
+        if (GEN || t0 != t_tail) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(tl, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start), tail_valid);
+        step_chunk<KIND, DISCRETE, SHAPED, FAST, true, PF>(e, acc, tl, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len, tail_valid);
     }
     const int steps = t_end - t_start;
     e.counter = c_start + steps;                                   // :268
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     if (t_end == T) mobile_store(out, i, e, true, TWO);
 }
 
-template <int KIND, bool DISCRETE, bool GEN, bool SHAPED>
+template <int KIND, bool DISCRETE, bool GEN, bool SHAPED, bool FAST>
 int launch_rollout_variant(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
                            float* ep_ret, int32_t* ep_len, cudaStream_t st) {
     // segments per env: 1 + the episodes that can start inside T steps (worst case: the first step ends an episode)
@@ -395,31 +420,36 @@ int launch_rollout_variant(srl_sim* s, int T, const void* actions, const float* 
     const int nseg = s->auto_reset ? (int)(1 + ((long long)T - 1 + per - 1) / per) : 1;
     // one warp per CTA while the whole launch is a few warps per SM: spreads the (latency-bound) warps over all 148 SMs
     const long long warps = (long long)nseg * ((s->n + 31) / 32);
-    int block = warps <= 148 * 16 ? 32 : warps <= 148 * 32 ? 64 : 128;
+    int block = warps <= 148 * 4 ? 32 : 128;
     if (s->mobile_block > 0) block = s->mobile_block;
     const dim3 grid((unsigned)((s->n + block - 1) / block), (unsigned)nseg);
-    mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED><<<grid, block, 0, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
-                                                                                 s->cfg.random_target != 0, s->auto_reset != 0, s->max_steps, s->seed, s->cfg.global_env_offset);
+    mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED, FAST><<<grid, block, 0, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
+                                                                                       s->cfg.random_target != 0, s->auto_reset != 0,
+                                                                                       s->max_steps, s->seed, s->cfg.global_env_offset);
     SRL_CUDA_OK(cudaGetLastError());
     const MobileDev tmp = s->mob; s->mob = s->mob_alt; s->mob_alt = tmp;   // stream-ordered: later launches read what this one wrote
     return 0;
 }
 
-template <int KIND, bool DISCRETE>
-int launch_rollout_da(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
-                      float* ep_ret, int32_t* ep_len, cudaStream_t st) {
+template <int KIND, bool DISCRETE, bool GEN>
+int launch_rollout_gen(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
+                       float* ep_ret, int32_t* ep_len, cudaStream_t st) {
+    const bool fast = !noise && obs && rew && done;
     if (s->cfg.shape_reward)
-        return actions ? launch_rollout_variant<KIND, DISCRETE, false, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
-                       : launch_rollout_variant<KIND, DISCRETE, true, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
-    return actions ? launch_rollout_variant<KIND, DISCRETE, false, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
-                   : launch_rollout_variant<KIND, DISCRETE, true, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
+        return fast ? launch_rollout_variant<KIND, DISCRETE, GEN, true, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                    : launch_rollout_variant<KIND, DISCRETE, GEN, true, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
+    return fast ? launch_rollout_variant<KIND, DISCRETE, GEN, false, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                : launch_rollout_variant<KIND, DISCRETE, GEN, false, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
 }
 
 template <int KIND>
 int launch_rollout_kind(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew, uint8_t* done,
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
-    return s->cfg.is_discrete ? launch_rollout_da<KIND, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
-                              : launch_rollout_da<KIND, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
+    if (s->cfg.is_discrete)
+        return actions ? launch_rollout_gen<KIND, true, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                       : launch_rollout_gen<KIND, true, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
+    return actions ? launch_rollout_gen<KIND, false, false>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st)
+                   : launch_rollout_gen<KIND, false, true>(s, T, actions, noise, obs, rew, done, ep_ret, ep_len, st);
 }
 
 }  // namespace

@@ -7,7 +7,7 @@
 //   key     = (seed & 0xffffffff, seed >> 32)
 //   counter = (env_global_lo, env_global_hi, index, purpose)
 //   purpose 0..7 : reset block `purpose` of episode `index`
-//   purpose 8    : step-noise draw of env step `index`;  purpose 9 : random action of step `index`
+//   purpose 8    : step-noise draw of env step `index`;  purpose 9 (and 10: words 4-6 of a 7-joint action) : random action of step `index`
 #pragma once
 #include <stdint.h>
 

@@ -71,7 +71,10 @@ int srl_sim_create(srl_sim** out, int env_kind, int num_envs, int device, const 
     if (device < 0) { srl_set_error("create: this library has no CPU path (device=%d)", device); return 1; }
     if (num_envs <= 0) { srl_set_error("create: num_envs must be positive"); return 1; }
     if (!srl_is_mobile(env_kind) && !srl_is_kuka(env_kind)) { srl_set_error("create: unknown env kind %d", env_kind); return 1; }
-    if (cfg->action_joints) { srl_set_error("create: action_joints is not implemented"); return 1; }
+    if (cfg->action_joints && (!srl_is_kuka(env_kind) || cfg->is_discrete)) {
+        // kuka_button_gym_env.py:149-161: the (7,) joint action space only exists for continuous Kuka actions
+        srl_set_error("create: action_joints needs a Kuka env with is_discrete=0"); return 1;
+    }
     if (srl_is_mobile(env_kind) && !cfg->is_discrete && env_kind != SRL_ENV_MOBILE && env_kind != SRL_ENV_MOBILE_LINE_TARGET) {
         // mobile_robot_2target_env.py:128, mobile_robot_1D_env.py:43,118 raise ValueError
         srl_set_error("Only discrete actions is supported");
@@ -128,7 +131,7 @@ int srl_sim_obs_dim(const srl_sim* s) { return !s ? 0 : srl_is_kuka(s->kind) ? 3
 int srl_sim_action_dim(const srl_sim* s) {
     if (!s) return 0;
     if (s->cfg.is_discrete) return 1;
-    return srl_is_mobile(s->kind) ? 2 : 3;
+    return srl_is_mobile(s->kind) ? 2 : (s->cfg.action_joints ? 7 : 3);
 }
 uint64_t srl_sim_launch_count(const srl_sim* s) { return s ? s->launches : 0; }
 

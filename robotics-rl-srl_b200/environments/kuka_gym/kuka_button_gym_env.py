@@ -67,7 +67,8 @@ class KukaButtonGymEnv(SRLGymEnv):
     :param max_distance: (float) Max distance between end effector and the button (for negative reward)
     :param action_repeat: (int) Number of timesteps an action is repeated (here it is equivalent to frameskip)
     :param shape_reward: (bool) Set to true, reward = -distance_to_goal
-    :param action_joints: (bool) joint-space actions (not implemented by the simulator)
+    :param action_joints: (bool) Set actions to apply to the joint space (7 set-points relative to the initial joint
+        vector; needs is_discrete=False -- the reference's own reset() fails for the discrete combination)
     :param record_data: (bool) not supported (EpisodeSaver image recording)
     :param random_target: (bool) Set the button position to a random position on the table
     :param force_down: (bool) Set Down as the only vertical action allowed
@@ -88,8 +89,10 @@ class KukaButtonGymEnv(SRLGymEnv):
                                                srl_pipe=srl_pipe)
         if record_data:
             raise NotImplementedError("record_data (EpisodeSaver image recording) is out of scope of the simulator")
-        if action_joints:
-            raise NotImplementedError("action_joints is not implemented by the batched simulator")
+        if action_joints and is_discrete:
+            # the reference constructs this combination but its reset() dies with an IndexError (a 5-element discrete
+            # action reaches Kuka.applyAction's 9-element joint branch, kuka.py:158-161); fail early and clearly instead
+            raise ValueError("action_joints requires is_discrete=False")
         self._timestep = 1. / 240.
         self._urdf_root = urdf_root
         self._action_repeat = action_repeat
@@ -121,7 +124,10 @@ class KukaButtonGymEnv(SRLGymEnv):
         if self._is_discrete:
             self.action_space = spaces.Discrete(N_DISCRETE_ACTIONS)
         else:
-            action_dim = 3  # 3 directions for the arm movement, from -1 to 1
+            if self.action_joints:
+                action_dim = 7  # 7 angles for the arm rotation, from -1 to 1
+            else:
+                action_dim = 3  # 3 directions for the arm movement, from -1 to 1
             self._action_bound = 1
             action_high = np.array([self._action_bound] * action_dim)
             self.action_space = spaces.Box(-action_high, action_high, dtype=np.float32)
@@ -142,7 +148,7 @@ class KukaButtonGymEnv(SRLGymEnv):
         self._sim = self._backend.make_sim(self._ENV_ID, 1, seed=0, model_blob=load_kuka_scene().blob,
                                            is_discrete=is_discrete, random_target=random_target, force_down=force_down,
                                            shape_reward=shape_reward, action_repeat=action_repeat,
-                                           max_distance=max_distance, max_steps=self._MAX_STEPS, no_auto_reset=True)
+                                           action_joints=action_joints, max_distance=max_distance, max_steps=self._MAX_STEPS, no_auto_reset=True)
         be = self._backend
         self._obs_buf = be.zeros((1, 3), np.float32)
         self._rew_buf = be.zeros((1,), np.float32)
@@ -213,6 +219,10 @@ class KukaButtonGymEnv(SRLGymEnv):
                 sign = 1 if self.np_random.rand() > 0.5 else -1
                 action_idx = self.np_random.randint(3)  # dx, dy or dz
                 action[action_idx] += sign * DELTA_V
+            elif self.action_joints:
+                # joints += DELTA_THETA * np_random.normal(joints.shape): `(7,)` is the MEAN, i.e. one N(7, 1) draw that
+                # broadcasts to the seven joints (:257-260); the kernel takes the common set-point offset in the dx slot
+                action[0] = float((DELTA_THETA * self.np_random.normal((7,)))[0])
             else:
                 rand_direction = self.np_random.normal((3,))
                 # L2 normalize, so that the random direction is not too high or too low
@@ -239,12 +249,16 @@ class KukaButtonGymEnv(SRLGymEnv):
         noise = 0.0
         if action is None:
             # the reference steps with a zero action and draws no noise (:295-299)
-            act = np.asarray([-1], dtype=np.int32) if self._is_discrete else np.zeros((1, 3), dtype=np.float32)
+            # (joints mode: the initial joint vector, i.e. a zero action on the relative set-points)
+            act = np.asarray([-1], dtype=np.int32) if self._is_discrete else np.zeros((1, 7 if self.action_joints else 3), dtype=np.float32)
         else:
             self.action = action
             if self._is_discrete:
                 noise = self.np_random.normal(0.0, scale=NOISE_STD)
                 act = np.asarray([int(action)], dtype=np.int32)
+            elif self.action_joints:
+                noise = self.np_random.normal(0.0, scale=NOISE_STD_JOINTS)
+                act = np.asarray(action, dtype=np.float32).reshape(1, 7)
             else:
                 noise = self.np_random.normal(0.0, scale=NOISE_STD_CONTINUOUS)
                 act = np.asarray(action, dtype=np.float32).reshape(1, 3)

@@ -41,6 +41,8 @@ CASES = [
     ("rand_button_disc", "KukaRandButtonGymEnv", dict(is_discrete=True, random_target=True), 6, 500),
     ("moving_disc", "KukaMovingButtonGymEnv", dict(is_discrete=True), 7, 500),
     ("moving_cont_rand", "KukaMovingButtonGymEnv", dict(is_discrete=False, random_target=True), 8, 400),
+    ("joints", "KukaButtonGymEnv", dict(is_discrete=False, action_joints=True), 9, 400),
+    ("joints_shaped_none", "KukaButtonGymEnv", dict(is_discrete=False, action_joints=True, shape_reward=True), 10, 300),
 ]
 CLASSES = {"KukaButtonGymEnv": KukaButtonGymEnv, "KukaRandButtonGymEnv": KukaRandButtonGymEnv,
            "KukaMovingButtonGymEnv": KukaMovingButtonGymEnv}
@@ -55,6 +57,13 @@ def make_actions(tag, kwargs, n, seed):
         if "none" in tag:
             a[rs.rand(n) < 0.1] = -1           # -1 encodes step(None)
         return np.stack([a, np.zeros(n), np.zeros(n)], axis=1)
+    if kwargs.get("action_joints", False):
+        # joint-space set-points: a slowly varying random walk bends the arm towards the table for part of the episode
+        a = np.clip(np.cumsum(rs.normal(0, 0.15, size=(n, 7)), axis=0), -1, 1)
+        a[:, 1] = np.clip(a[:, 1] + np.linspace(0, 4, n) % 2.0, -1, 1)
+        if "none" in tag:
+            a[rs.rand(n) < 0.1, 0] = np.nan      # NaN in column 0 encodes step(None)
+        return a.astype(np.float32).astype(np.float64)
     a = rs.uniform(-1, 1, size=(n, 3))
     a[:, 2] = -np.abs(a[:, 2]) if "up" not in tag else a[:, 2]
     return a.astype(np.float32).astype(np.float64)
@@ -76,7 +85,7 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
             if kwargs.get("is_discrete", True):
                 a = None if actions[t, 0] < 0 else int(actions[t, 0])
             else:
-                a = actions[t].astype(np.float32)
+                a = None if np.isnan(actions[t, 0]) else actions[t].astype(np.float32)
             o, r, done, _ = env.step(a)
             rec["obs"].append(np.asarray(o, np.float64)); rec["reward"].append(float(r)); rec["done"].append(bool(done))
             rec["arm"].append(np.array(env.getArmPos(), dtype=np.float64, copy=True)); rec["target"].append(np.array(env.getTargetPos(), dtype=np.float64, copy=True))

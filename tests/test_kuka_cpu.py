@@ -262,8 +262,13 @@ def test_single_env_classes_on_oracle(use_oracle_backend):
     assert c.action_space.shape == (3,) and abs(c.getTargetPos()[0] - 0.5) <= 0.15 and abs(c.getTargetPos()[1]) <= 0.3
     _, r, _, _ = c.step(c.action_space.sample())
     assert isinstance(r, float) and r < 0
-    with pytest.raises(NotImplementedError):
-        registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth", action_joints=True)
+    with pytest.raises(ValueError):
+        registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth", action_joints=True)   # joint actions are continuous only
+    jt = registered_env["KukaButtonGymEnv-v0"][0](srl_model="ground_truth", action_joints=True, is_discrete=False)
+    jt.seed(2); jt.reset()
+    assert jt.action_space.shape == (7,)
+    o, r, d, _ = jt.step(jt.action_space.sample())
+    assert o.shape == (3,) and r in (-1, 0, 1) and not d
     with pytest.raises(NotImplementedError):
         registered_env["KukaButtonGymEnv-v0"][0]().reset()             # default raw_pixels: no rasteriser
 
@@ -280,6 +285,8 @@ REF_LOGIC_CASES = {
     "rand_button_disc": ("KukaRandButtonGymEnv-v0", dict(is_discrete=True, random_target=True), 6),
     "moving_disc": ("KukaMovingButtonGymEnv-v0", dict(is_discrete=True), 7),
     "moving_cont_rand": ("KukaMovingButtonGymEnv-v0", dict(is_discrete=False, random_target=True), 8),
+    "joints": ("KukaButtonGymEnv-v0", dict(is_discrete=False, action_joints=True), 9),
+    "joints_shaped_none": ("KukaButtonGymEnv-v0", dict(is_discrete=False, action_joints=True, shape_reward=True), 10),
 }
 
 
@@ -305,7 +312,7 @@ def replay_ref_logic_case(tag, pos_tol):
             if kwargs.get("is_discrete", True):
                 a = None if actions[t, 0] < 0 else int(actions[t, 0])
             else:
-                a = actions[t].astype(np.float32)
+                a = None if np.isnan(actions[t, 0]) else actions[t].astype(np.float32)
             o, r, d, _ = env.step(a)
             assert np.abs(np.asarray(o) - obs[t]).max() < pos_tol, (tag, "obs", t)
             assert np.abs(np.asarray(env.getArmPos()) - arm[t]).max() < pos_tol and np.abs(env.getTargetPos() - target[t]).max() < max(1e-6, pos_tol * 1e-2)

@@ -118,6 +118,22 @@ def test_variants_vs_oracle(cfg, cuda_backend, oracle_backend):
         assert np.abs(c["rew"] - o["rew"]).max() < POS_TOL                # reward = -distance
 
 
+@pytest.mark.parametrize("in_kernel_actions", [False, True])
+def test_action_joints_vs_oracle(in_kernel_actions, cuda_backend, oracle_backend):
+    """action_joints=True (kuka_button_gym_env.py:317-323, kuka.py:158-161): 7 joint set-points relative to the initial
+    joint vector, no IK; its own 500-step settle snapshot and N(7, 1) random-init offsets.  max_steps=150 forces resets."""
+    n, T = 24, 400
+    rs = np.random.RandomState(12)
+    acts = None if in_kernel_actions else np.clip(np.cumsum(rs.normal(0, 0.2, size=(T, n, 7)), axis=0), -1, 1).astype(np.float32)
+    noise = None if in_kernel_actions else rs.normal(0, 0.002, size=(T, n)).astype(np.float32)
+    cfg = dict(seed=31, is_discrete=False, action_joints=True, max_steps=150)
+    c = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, **cfg)
+    o = _run(oracle_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, **cfg)
+    _assert_parity(c, o)
+    assert o["done"].sum() >= 2 * n
+    assert np.abs(o["q"][:, :7] - np.asarray(load_kuka_scene().q_init)[:7]).max() < 0.2   # +-DELTA_THETA around the initial posture
+
+
 def test_cuda_matches_committed_golden(cuda_backend):
     gen = _gen()
     g = np.load(os.path.join(GOLDEN, "kuka_oracle_golden.npz"))
@@ -220,7 +236,8 @@ def test_single_env_classes_on_cuda(cuda_lib):
     env.close()
 
 
-@pytest.mark.parametrize("tag", ["disc", "cont", "disc_rep3_none", "rand_button_disc", "disc_rand_shaped", "moving_disc", "moving_cont_rand"])
+@pytest.mark.parametrize("tag", ["disc", "cont", "disc_rep3_none", "rand_button_disc", "disc_rand_shaped", "moving_disc", "moving_cont_rand",
+                                 "joints", "joints_shaped_none"])
 def test_reference_class_logic_golden_through_cuda(tag, cuda_lib):
     """Trajectories recorded from the REFERENCE Kuka classes (on the oracle's physics, tests/golden/fake_pybullet.py)
     replayed through our env classes -> C-ABI -> the fp32 kernel: flags exact, positions within 1e-3 m."""
