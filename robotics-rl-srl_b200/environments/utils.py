@@ -1,10 +1,11 @@
 """
 Mirror of environments/utils.py:36-95 (``makeEnv`` / ``_make`` / ``dynamicEnvLoad``): the single-env construction
 path used by ``rl_baselines``, ``environments.dataset_generator`` and ``replay.enjoy_baselines``.  gym's registry is
-replaced by ``environments.registry.registry``; ``bench.Monitor`` file logging is not reproduced (the batched VecEnv
-reports Monitor-style ``info['episode']`` itself).
+replaced by ``environments.registry.registry``; ``bench.Monitor`` is ``srl_sim.monitor.Monitor`` (same ``*.monitor.csv`` format,
+readable by the reference's ``rl_baselines/visualize.py:loadCsv``).
 """
 import importlib
+import os
 
 from environments.registry import registry
 
@@ -49,5 +50,8 @@ def makeEnv(env_id, seed, rank, log_dir, allow_early_resets=False, env_kwargs=No
         local_env_kwargs["env_rank"] = rank
         env = _make(env_id, env_kwargs=local_env_kwargs)
         env.seed(seed + rank)
+        if log_dir is not None:
+            from srl_sim.monitor import Monitor
+            env = Monitor(env, os.path.join(log_dir, str(rank)), allow_early_resets=allow_early_resets)
         return env
     return _thunk

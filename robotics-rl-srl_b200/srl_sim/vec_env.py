@@ -34,22 +34,28 @@ class BatchedSRLVecEnv(object):
     :param seed: (int) base seed; env ``i`` uses the stream of global index ``global_env_offset + i``
     :param device: (int) CUDA ordinal (default 0)
     :param global_env_offset: (int) index of local env 0 in the global batch (rank * num_envs under torchrun)
+    :param log_dir: (str) if given, every finished episode is appended to ``<log_dir>/<global_env_offset>.monitor.csv``
+        (``bench.Monitor`` format; the reference writes one such file per env process, environments/utils.py:53-54)
     :param env_kwargs: the reference's env keyword arguments (is_discrete, random_target, shape_reward, force_down,
         action_repeat, max_distance, srl_model, ...); unknown ones are ignored like the reference's ``**_``
     """
 
-    def __init__(self, env_id, num_envs, seed=0, device=None, global_env_offset=0, **env_kwargs):
+    def __init__(self, env_id, num_envs, seed=0, device=None, global_env_offset=0, log_dir=None, **env_kwargs):
         if env_id not in _abi.ENV_KINDS:
             raise KeyError("unknown env id %r" % env_id)
         srl_model = env_kwargs.pop("srl_model", "ground_truth")
-        if srl_model != "ground_truth":
-            raise NotImplementedError("BatchedSRLVecEnv provides the ground_truth observation (got srl_model=%r)" % srl_model)
+        kuka_state_models = ("joints", "joints_position") if env_id.startswith("Kuka") else ()
+        if srl_model != "ground_truth" and srl_model not in kuka_state_models:
+            raise NotImplementedError("BatchedSRLVecEnv provides the state observations ground_truth%s (got srl_model=%r)"
+                                      % ("".join(" / " + m for m in kuka_state_models), srl_model))
+        self.srl_model = srl_model
         self.env_id = env_id
         self.num_envs = int(num_envs)
         self.backend = default_backend(device)
         cfg = dict(is_discrete=env_kwargs.get("is_discrete", True), random_target=env_kwargs.get("random_target", False),
                    shape_reward=env_kwargs.get("shape_reward", False), force_down=env_kwargs.get("force_down", True),
-                   action_repeat=env_kwargs.get("action_repeat", 1), global_env_offset=global_env_offset)
+                   action_repeat=env_kwargs.get("action_repeat", 1), action_joints=env_kwargs.get("action_joints", False),
+                   global_env_offset=global_env_offset)
         blob = None
         if env_id in _KUKA_IDS:
             from .model import load_kuka_scene
@@ -61,7 +67,19 @@ class BatchedSRLVecEnv(object):
         self.sim = self.backend.make_sim(env_id, self.num_envs, seed=seed, model_blob=blob, **cfg)
         self.is_discrete = bool(cfg["is_discrete"])
         D = self.sim.obs_dim
-        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(D,), dtype=np.float32)
+        # Kuka `joints` / `joints_position` states (kuka_button_gym_env.py:175-189): the 14 stored joint positions are the
+        # INITIAL vector -- the reference never updates `_kuka.joint_positions` (kuka.py:65-66) -- so they are a constant
+        self._joints = None
+        if srl_model in ("joints", "joints_position"):
+            from .model import KUKA_INIT_JOINT_POSITIONS
+            self._joints = np.tile(np.asarray(KUKA_INIT_JOINT_POSITIONS, np.float32), (self.num_envs, 1))
+        out_dim = {"ground_truth": D, "joints": 14, "joints_position": D + 14}[srl_model]
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(out_dim,), dtype=np.float32)
+        self._monitor = None
+        if log_dir is not None:
+            from .monitor import MonitorWriter
+            import os
+            self._monitor = MonitorWriter(os.path.join(log_dir, str(global_env_offset)), env_id=env_id)
         if self.is_discrete:
             self.action_space = spaces.Discrete(_N_ACTIONS[env_id])
         else:
@@ -78,9 +96,15 @@ class BatchedSRLVecEnv(object):
         self.closed = False
 
     # ---- VecEnv API (numpy) --------------------------------------------------------------------------
+    def _state(self, obs):
+        """ground-truth observation [N, D] -> the configured state (getSRLState)."""
+        if self._joints is None:
+            return obs
+        return self._joints.copy() if self.srl_model == "joints" else np.concatenate([obs, self._joints], axis=1)
+
     def reset(self):
         self.sim.reset(obs_out=self._obs, stream=self.backend.stream())
-        return self.backend.to_host(self._obs).copy()
+        return self._state(self.backend.to_host(self._obs).copy())
 
     def step_async(self, actions):
         if self.is_discrete:
@@ -101,8 +125,11 @@ class BatchedSRLVecEnv(object):
             ep_ret, ep_len = be.to_host(self._ep_ret), be.to_host(self._ep_len)
             t = round(time.time() - self._t0, 6)
             for i in np.nonzero(done)[0]:
-                infos[i]["episode"] = {"r": round(float(ep_ret[i]), 6), "l": int(ep_len[i]), "t": t}
-        return obs, rew, done, infos
+                if self._monitor is not None:
+                    infos[i]["episode"] = self._monitor.write_episode(ep_ret[i], ep_len[i])
+                else:
+                    infos[i]["episode"] = {"r": round(float(ep_ret[i]), 6), "l": int(ep_len[i]), "t": t}
+        return self._state(obs), rew, done, infos
 
     def step(self, actions):
         self.step_async(actions)
@@ -111,6 +138,8 @@ class BatchedSRLVecEnv(object):
     def close(self):
         if not self.closed:
             self.sim.close()
+            if self._monitor is not None:
+                self._monitor.close()
             self.closed = True
 
     def seed(self, seed=None):

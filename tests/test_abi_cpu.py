@@ -58,7 +58,10 @@ def test_bad_arguments_are_reported_not_thrown(oracle_lib):
     with pytest.raises(_abi.SimError, match="model blob"):
         _abi.Sim(oracle_lib, "KukaButtonGymEnv-v0", 2, -1, model_blob=np.zeros(8))
     with pytest.raises(_abi.SimError, match="action_joints"):
-        _abi.Sim(oracle_lib, "KukaButtonGymEnv-v0", 2, -1, action_joints=True)
+        _abi.Sim(oracle_lib, "MobileRobotGymEnv-v0", 2, -1, action_joints=True, is_discrete=False)   # joint actions are Kuka-only ...
+    with pytest.raises(_abi.SimError, match="action_joints"):
+        from srl_sim.model import load_kuka_scene
+        _abi.Sim(oracle_lib, "KukaButtonGymEnv-v0", 2, -1, model_blob=load_kuka_scene().blob, action_joints=True)   # ... and continuous-only
     sim = _abi.Sim(oracle_lib, "MobileRobotGymEnv-v0", 3, -1)
     with pytest.raises(_abi.SimError, match="not available"):
         sim.get_state(_abi.F_JOINT_POS)
@@ -90,3 +93,53 @@ def test_vec_env_semantics_on_oracle(use_oracle_backend):
         o, r, d, infos = venv.step(np.zeros((3, 3), np.float32))
     assert venv.get_original_obs().shape == (3, 6)
     venv.close()
+
+
+def test_monitor_files_and_joint_states_on_oracle(use_oracle_backend, tmp_path):
+    """bench.Monitor file format (environments/utils.py:53-54, read back like rl_baselines/visualize.py:59-76) from both the
+    single-env makeEnv path and the batched VecEnv; Kuka `joints` / `joints_position` states in the batch."""
+    import json
+    from environments.utils import makeEnv
+    from srl_sim.vec_env import BatchedSRLVecEnv
+
+    def load_csv(path):
+        with open(path) as f:
+            header = json.loads(f.readline()[1:])
+            assert f.readline().strip() == "r,l,t"
+            rows = [line.strip().split(",") for line in f]
+        return header, [(float(r), int(l), float(t)) for r, l, t in rows]
+
+    env = makeEnv("MobileRobotGymEnv-v0", seed=0, rank=3, log_dir=str(tmp_path), env_kwargs=dict(srl_model="ground_truth"))()
+    with pytest.raises(RuntimeError):
+        env.step(0)                                   # bench.Monitor: step before reset
+    env.reset()
+    ret, done, n = 0, False, 0
+    while not done:
+        _, r, done, info = env.step(n % 4)
+        ret += r; n += 1
+    assert n == 251 and info["episode"]["l"] == 251 and info["episode"]["r"] == ret
+    with pytest.raises(RuntimeError):
+        env.step(0)                                   # needs reset after done
+    env.close()
+    header, rows = load_csv(str(tmp_path / "3.monitor.csv"))
+    assert header["env_id"] == "MobileRobotGymEnv-v0" and rows == [(float(ret), 251, rows[0][2])]
+
+    venv = BatchedSRLVecEnv("MobileRobotGymEnv-v0", 5, seed=1, log_dir=str(tmp_path / "batch"), global_env_offset=10)
+    venv.reset()
+    for t in range(260):
+        _, _, d, infos = venv.step(np.full(5, t % 4))
+    venv.close()
+    header, rows = load_csv(str(tmp_path / "batch" / "10.monitor.csv"))
+    assert len(rows) == 5 and all(l == 251 for _, l, _ in rows)
+
+    from srl_sim.model import KUKA_INIT_JOINT_POSITIONS
+    for model, dim in (("joints", 14), ("joints_position", 17)):
+        kenv = BatchedSRLVecEnv("KukaButtonGymEnv-v0", 2, seed=0, srl_model=model, max_steps=5)
+        o = kenv.reset()
+        assert o.shape == (2, dim) and kenv.observation_space.shape == (dim,)
+        assert np.allclose(o[:, -14:], KUKA_INIT_JOINT_POSITIONS, atol=1e-6)
+        o, _, _, _ = kenv.step([0, 1])
+        assert o.shape == (2, dim)
+        kenv.close()
+    with pytest.raises(NotImplementedError):
+        BatchedSRLVecEnv("MobileRobotGymEnv-v0", 2, srl_model="joints")
