@@ -104,7 +104,9 @@ enum srl_state_field {
     SRL_F_BUTTON_GLIDER = 7,  /* f64[N,2] button prismatic joint (q, qd)                       */
     SRL_F_COUNTERS      = 8,  /* i32[N,4] Kuka: n_contacts, n_steps_outside, terminated, episode index */
     SRL_F_EPISODE_STATS = 9,  /* f64[N,2] running episode return, length                       */
-    SRL_F_BUTTON_BASE   = 10  /* f64[N,3] Kuka: button base link origin (x, y, z)              */
+    SRL_F_BUTTON_BASE   = 10, /* f64[N,3] Kuka: button base link origin (x, y, z)              */
+    SRL_F_TWO_BUTTON    = 11  /* f64[N,8] Kuka2Button (read-only): n_contacts[0], n_contacts[1], goal_id, second button base x y z,
+                                 second glider q, qd (kuka_2button_gym_env.py:34,40-43)          */
 };
 
 int srl_sim_abi_version(void);

@@ -34,7 +34,7 @@
 namespace {
 
 const int NB = KM_NBODY;     /* 12 movable bodies */
-const int ND = KM_NBODY + 1; /* + button glider   */
+const int ND = KM_NBODY + 2; /* + button glider(s): DoF NB = button 1, NB + 1 = button 2 (Kuka2ButtonGymEnv only; inert otherwise) */
 
 /* ---------------------------------------------------------------- small linear algebra ---- */
 struct V3 { double x, y, z; };
@@ -187,6 +187,12 @@ struct KEnv {
     double btn_speed;        /* kuka_moving_button_gym_env.py:33 */
     int counter, n_contacts, n_outside, terminated;
     int contact_button, contact_table; /* manifold flags of the last stepSimulation */
+    /* ---- Kuka2ButtonGymEnv (kuka_2button_gym_env.py): the second button body and the goal bookkeeping ---- */
+    int nbuttons;            /* 1, or 2 for the two-button kind */
+    double qb2, qdb2;        /* second button glider */
+    double button2_base[3];
+    int contact_button_any[2]; /* contact with ANY link of button b (getContactPoints without a link index, :165) */
+    int n_contacts2[2], goal_id, pressed[2];
     double gripper_pos[3], ee_pos[3];  /* link states after the last stepSimulation */
     uint32_t episode, total_steps;
     double ep_ret; int ep_len;
@@ -386,7 +392,7 @@ static void inverse_kinematics(const KModel& m, const Kin& k, const double* q, c
 
 /* ----------------------------------------------------------------------- collision detection */
 struct Contact {
-    int sphere, body, shape; /* shape: 0 table, 1 button disc (button_uid link 1), 2 button base stack */
+    int sphere, body, shape; /* shape: 0 table, 1 button disc (button_uid link 1), 2 button base stack, 3 / 4 the same of button 2 */
     double dist; V3 n, p;    /* signed distance, normal from the shape towards the arm, point on the sphere surface */
 };
 
@@ -420,23 +426,34 @@ static int detect_contacts(const KModel& m, const Kin& k, const KEnv& e, Contact
     const double disc1 = bz + m.sc[KM_SC_GLIDER_Z] + e.qb + m.sc[KM_SC_DISC_Z1];
     int n = 0;
     button_flag = 0; table_flag = 0;
+    const int nshapes = e.nbuttons == 2 ? 5 : 3;
+    const double b2z = e.button2_base[2];
+    const double disc20 = b2z + m.sc[KM_SC_GLIDER_Z] + e.qb2 + m.sc[KM_SC_DISC_Z0];
+    const double disc21 = b2z + m.sc[KM_SC_GLIDER_Z] + e.qb2 + m.sc[KM_SC_DISC_Z1];
+    int any[2] = {0, 0};
     for (int s = 0; s < m.nsphere; ++s) {
         const int b = m.sph[s].body;
         const V3 c = k.p[b] + k.R[b] * m.sph[s].c;
         const double r = m.sph[s].r;
-        for (int shape = 0; shape < 3; ++shape) {
+        for (int shape = 0; shape < nshapes; ++shape) {
             double dist; V3 nn;
             if (shape == 0) {
                 if (c.x < m.sc[KM_SC_TABLE_XMIN] || c.x > m.sc[KM_SC_TABLE_XMAX] || c.y < m.sc[KM_SC_TABLE_YMIN] || c.y > m.sc[KM_SC_TABLE_YMAX]) continue;
                 dist = c.z - zt - r; nn = v3(0, 0, 1);
             } else if (shape == 1) {
                 sphere_cylinder(c, r, e.button_base[0], e.button_base[1], disc0, disc1, m.sc[KM_SC_DISC_RADIUS], dist, nn);
-            } else {
+            } else if (shape == 2) {
                 sphere_cylinder(c, r, e.button_base[0], e.button_base[1], bz, bz + m.sc[KM_SC_STACK_TOP], m.sc[KM_SC_STACK_RADIUS], dist, nn);
+            } else if (shape == 3) {
+                sphere_cylinder(c, r, e.button2_base[0], e.button2_base[1], disc20, disc21, m.sc[KM_SC_DISC_RADIUS], dist, nn);
+            } else {
+                sphere_cylinder(c, r, e.button2_base[0], e.button2_base[1], b2z, b2z + m.sc[KM_SC_STACK_TOP], m.sc[KM_SC_STACK_RADIUS], dist, nn);
             }
             if (dist > thr) continue;
             if (shape == 0) table_flag = 1;
             if (shape == 1) button_flag = 1;
+            if (shape == 1 || shape == 2) any[0] = 1;
+            if (shape == 3 || shape == 4) any[1] = 1;
             if (n < max_out) {
                 out[n].sphere = s; out[n].body = b; out[n].shape = shape; out[n].dist = dist; out[n].n = nn;
                 out[n].p = c - r * nn;
@@ -444,6 +461,8 @@ static int detect_contacts(const KModel& m, const Kin& k, const KEnv& e, Contact
             }
         }
     }
+    const_cast<KEnv&>(e).contact_button_any[0] = any[0];
+    const_cast<KEnv&>(e).contact_button_any[1] = any[1];
     return n;
 }
 
@@ -465,6 +484,7 @@ static void fill_point_row(const KModel& m, const Kin& k, const Contact& c, V3 d
     for (int j = 0; j < NB; ++j)
         if (is_ancestor_or_self(m, j, c.body)) r.J[j] = dot(dir, cross(k.a[j], c.p - k.p[j]));
     if (c.shape == 1) r.J[NB] = -dir.z; /* the button link moves along +z with the glider */
+    if (c.shape == 3) r.J[NB + 1] = -dir.z;
 }
 
 static void plane_space(V3 n, V3& p, V3& q) { /* btPlaneSpace1 */
@@ -508,6 +528,11 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
         const double vb = e.qdb;
         const double acc = m.sc[KM_SC_GRAVITY_Z] - m.sc[KM_SC_LIN_DAMPING] * vb * (1.0 + fabs(vb));
         v0[NB] = vb + dt * acc;
+        v0[NB + 1] = 0.0;
+        if (e.nbuttons == 2) {
+            const double vb2 = e.qdb2;
+            v0[NB + 1] = vb2 + dt * (m.sc[KM_SC_GRAVITY_Z] - m.sc[KM_SC_LIN_DAMPING] * vb2 * (1.0 + fabs(vb2)));
+        }
     }
     const double minv_button = 1.0 / m.sc[KM_SC_BUTTON_MASS];
 
@@ -529,6 +554,7 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
         else if (unit) { for (int j = 0; j < NB; ++j) r.W[j] = us * Minv[ui][j]; }
         else { for (int j = 0; j < NB; ++j) tau[j] = r.J[j]; aba_minv(m, A, tau, w); for (int j = 0; j < NB; ++j) r.W[j] = w[j]; }
         r.W[NB] = r.J[NB] * minv_button;
+        r.W[NB + 1] = r.J[NB + 1] * minv_button;
         double D = 0; for (int j = 0; j < ND; ++j) D += r.J[j] * r.W[j];
         r.invD = 1.0 / D;
         double rel = 0; for (int j = 0; j < ND; ++j) rel += r.J[j] * v0[j];
@@ -555,6 +581,15 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
         r.lo = -r.hi;
         finish_row(r); rows.push_back(r);
     }
+    if (e.nbuttons == 2) {   /* the second button is loaded right after the first (kuka_2button_gym_env.py:58-69): same motor, next in line */
+        Row r = joint_row(NB + 1, 1.0);
+        if (btn.position_control) {
+            r.target = btn.kp * (btn.target - e.qb2) / dt + v0[NB + 1] + btn.kd * (0.0 - v0[NB + 1]);
+            r.hi = btn.maxforce * dt;
+        } else { r.target = 0.0; r.hi = m.sc[KM_SC_BTN_IDLE_IMPULSE]; }
+        r.lo = -r.hi;
+        finish_row(r); rows.push_back(r);
+    }
     for (int i = 0; i < NB; ++i) {
         const MotorCmd& b = cmd[i];
         Row r = joint_row(i, 1.0);
@@ -573,6 +608,7 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
         if (pen_hi <= lim_eps) { Row r = joint_row(dof, -1.0); r.target = -erp * pen_hi / dt; r.lo = 0; r.hi = m.sc[KM_SC_LIMIT_MAX_IMPULSE]; finish_row(r); rows.push_back(r); }
     };
     limit_rows(NB, e.qb, m.sc[KM_SC_GLIDER_LOWER], m.sc[KM_SC_GLIDER_UPPER]);
+    if (e.nbuttons == 2) limit_rows(NB + 1, e.qb2, m.sc[KM_SC_GLIDER_LOWER], m.sc[KM_SC_GLIDER_UPPER]);
     for (int i = 0; i < NB; ++i) limit_rows(i, e.q[i], m.b[i].lower, m.b[i].upper);
     /* (3) contact normals, then (4) two friction rows per contact */
     const int first_contact = (int)rows.size();
@@ -615,6 +651,7 @@ static void physics_step_cmd(const KModel& m, KEnv& e, const MotorCmd* cmd, cons
     /* write back and integrate (semi-implicit Euler): qd <- v, q <- q + dt qd */
     for (int i = 0; i < NB; ++i) { e.qd[i] = v0[i] + dv[i]; e.q[i] += dt * e.qd[i]; }
     e.qdb = v0[NB] + dv[NB]; e.qb += dt * e.qdb;
+    if (e.nbuttons == 2) { e.qdb2 = v0[NB + 1] + dv[NB + 1]; e.qb2 += dt * e.qdb2; }
 
     /* link states after the step (getLinkState: COM of link 8; link-6 frame origin) */
     forward_kinematics(m, e.q, k);
@@ -663,9 +700,18 @@ struct KukaWorld {
 
 namespace {
 
+/* Kuka2ButtonGymEnv scene: button 1 at (0.5, 0.125), button 2 at (0.5, -0.125) (kuka_2button_gym_env.py:49-69), both resting on the table */
+static const double TWO_BUTTON_Y = 0.125, TWO_BUTTON_RAND_Y = 0.175;
+static void two_button_defaults(const KModel& m, KEnv& e) {
+    e.nbuttons = 2;
+    e.button_base[0] = m.sc[KM_SC_BUTTON_BASE]; e.button_base[1] = TWO_BUTTON_Y; e.button_base[2] = m.sc[KM_SC_BUTTON_BASE + 2];
+    e.button2_base[0] = m.sc[KM_SC_BUTTON_BASE]; e.button2_base[1] = -TWO_BUTTON_Y; e.button2_base[2] = m.sc[KM_SC_BUTTON_BASE + 2];
+}
+
 /* Kuka.applyAction's accumulate + clip (kuka.py:134-139) */
 static void apply_ee_delta(const KukaWorld& w, const srl_sim* s, KEnv& e, const double d[3]) {
-    const double* box = w.m.sc + (s->cfg.random_target ? KM_SC_BOX_LARGE : KM_SC_BOX_SMALL); /* small_constraints = not random_target (:239) */
+    /* small_constraints = not random_target (:239); Kuka2Button always uses the large box (kuka_2button_gym_env.py:78) */
+    const double* box = w.m.sc + ((s->cfg.random_target || s->kind == SRL_ENV_KUKA_2BUTTON) ? KM_SC_BOX_LARGE : KM_SC_BOX_SMALL);
     for (int a = 0; a < 3; ++a) {
         e.ee[a] += d[a];
         if (e.ee[a] < box[2 * a]) e.ee[a] = box[2 * a];
@@ -685,6 +731,8 @@ static void make_snapshot(KukaWorld& w, const srl_sim* s) {
     for (int i = 0; i < NB; ++i) { e.q[i] = w.m.b[i].qinit; e.qd[i] = 0.0; }  /* resetJointState, kuka.py:68-69 */
     for (int a = 0; a < 3; ++a) { e.ee[a] = w.m.sc[KM_SC_EE_INIT + a]; e.button_base[a] = w.m.sc[KM_SC_BUTTON_BASE + a]; }
     e.ee_angle = 0.0;
+    e.nbuttons = 1;
+    if (s->kind == SRL_ENV_KUKA_2BUTTON) two_button_defaults(w.m, e);
     const double zero[3] = {0, 0, 0};
     double qj[7];
     for (int j = 0; j < 7; ++j) qj[j] = w.m.b[j].qinit; /* self._kuka.joint_positions[:7] (:244) */
@@ -705,7 +753,12 @@ KukaWorld* oracle_kuka_create(srl_sim* s, const void* blob, size_t bytes) {
     if (s->cfg.timestep > 0) w->m.sc[KM_SC_TIMESTEP] = (double)s->cfg.timestep;
     if (s->kind == SRL_ENV_KUKA_MOVING_BUTTON && s->cfg.max_steps <= 0) w->max_steps = 1500; /* kuka_moving_button_gym_env.py:3,28 */
     if (s->kind == SRL_ENV_KUKA_2BUTTON) {
-        oracle_set_error("Kuka2ButtonGymEnv-v0 (two buttons, null-space IK) is not implemented"); delete w; return NULL;
+        if (s->cfg.max_steps <= 0) w->max_steps = 1500; /* kuka_2button_gym_env.py:3,33 */
+        /* `use_null_space = True` (:80): calculateInverseKinematics(uid, link, pos, orn, ll, ul, jr, rp) (kuka.py:147-149).  RECALLED
+           pybullet 1.8.6 behaviour: the null-space task is only enabled when all four lists have one entry per JOINT (14 for
+           kuka_with_gripper2; kuka.py:34-40 gives 7), so it is silently dropped -- and since this call passes no jointDamping, the
+           server's default damping 0.5 per DoF replaces the 1e-5 of the single-button envs. */
+        w->m.sc[KM_SC_IK_DAMPING] = 0.5;
     }
     w->envs.resize(s->n);
     memset(w->envs.data(), 0, sizeof(KEnv) * (size_t)s->n);
@@ -755,10 +808,23 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
             d[17] = (r[0] & 1u) ? 0.001 : -0.001;
         }
     }
+    const bool two = s->kind == SRL_ENV_KUKA_2BUTTON;
+    if (two && !draws) {
+        /* button 1 is always at (0.5, 0.125): its random placement is overwritten (kuka_2button_gym_env.py:56-57);
+           button 2: x = 0.5 + 0.15 U(-1, 1), y = -0.125 + 0.175 U(-1, 0) (:63-66) */
+        const uint64_t genv = s->cfg.global_env_offset + (uint64_t)i;
+        uint32_t r[4];
+        philox4x32_10(s->seed, genv, episode, PHILOX_PURPOSE_RESET0 + 0, r);
+        d[0] = w.m.sc[KM_SC_BUTTON_BASE] + w.m.sc[KM_SC_RAND_X] * (-1.0 + 2.0 * philox_u01(r[0], r[1]));
+        d[1] = -TWO_BUTTON_Y + TWO_BUTTON_RAND_Y * (-1.0 + philox_u01(r[2], r[3]));
+    }
     e = w.snapshot;
     e.episode = episode + 1; e.total_steps = total;
     e.btn_speed = (s->kind == SRL_ENV_KUKA_MOVING_BUTTON) ? d[17] : 0.0;
-    if (s->cfg.random_target) { e.button_base[0] = d[0]; e.button_base[1] = d[1]; }
+    if (s->cfg.random_target) {
+        if (two) { e.button2_base[0] = d[0]; e.button2_base[1] = d[1]; }
+        else { e.button_base[0] = d[0]; e.button_base[1] = d[1]; }
+    }
     for (int k = 0; k < 5; ++k) { /* N_RANDOM_ACTIONS_AT_INIT, :250-269 */
         if (s->cfg.action_joints) {
             double qj[7];
@@ -773,6 +839,8 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
     e.button_pos[0] = e.button_base[0];
     e.button_pos[1] = e.button_base[1];
     e.button_pos[2] = e.button_base[2] + w.m.sc[KM_SC_GLIDER_Z] + e.qb + w.m.sc[KM_SC_TARGET_HEIGHT];
+    if (two) e.button_pos[2] = -0.2 + w.m.sc[KM_SC_TARGET_HEIGHT]; /* button_all_pos = [x, y, Z_TABLE + BUTTON_DISTANCE_HEIGHT] (:59,69,72), not a link state */
+    e.goal_id = 0; e.n_contacts2[0] = e.n_contacts2[1] = 0; e.pressed[0] = e.pressed[1] = 0;
     e.counter = 0; e.n_contacts = 0; e.n_outside = 0; e.terminated = 0;
     e.ep_ret = 0.0; e.ep_len = 0;
 }
@@ -780,6 +848,43 @@ void oracle_kuka_reset_env(srl_sim* s, int i, const double* draws) {
 void oracle_kuka_obs(const srl_sim* s, int i, float* obs) {
     const KEnv& e = s->kuka->envs[i];
     for (int a = 0; a < 3; ++a) obs[a] = (float)(e.gripper_pos[a] - e.button_pos[a]); /* :175-186, RELATIVE_POS */
+}
+
+/* Kuka2ButtonGymEnv._reward (kuka_2button_gym_env.py:157-214) + _termination + the VecEnv epilogue */
+static void two_button_reward(srl_sim* s, KukaWorld& w, KEnv& e, int i, double distance, float* obs, float* rew, uint8_t* done,
+                              float* ep_ret, int32_t* ep_len) {
+    double reward = 0.0;
+    const int contact = e.contact_button_any[e.goal_id];      /* getContactPoints(button_uid[goal_id], kuka_uid): ANY link of that button (:165) */
+    e.n_contacts2[e.goal_id] += contact;
+    if (e.goal_id == 1) reward = contact;                     /* sparse reward only on the last button (:169-170) */
+    if (e.n_contacts2[e.goal_id] >= 5 && !e.pressed[e.goal_id]) {   /* next button (:173-178) */
+        e.pressed[e.goal_id] = 1;
+        if (e.goal_id == 0) {
+            e.goal_id = 1;
+            e.button_pos[0] = e.button2_base[0]; e.button_pos[1] = e.button2_base[1];   /* button_all_pos[1]; z is the same constant */
+        }
+    }
+    const int table = e.contact_table;
+    if (distance > (double)s->cfg.max_distance || table) { reward = -1.0; e.n_outside += 1; } else e.n_outside = 0;
+    if (table || e.n_contacts2[1] >= 5 || e.n_outside >= 5000 - 1) e.terminated = 1;   /* :188-190 */
+    if (s->cfg.shape_reward) {   /* :192-212 */
+        if (e.terminated && reward > 0) reward = 50;
+        else if (e.n_contacts2[e.goal_id] < 5 && contact) reward = 25;
+        else if (table) reward = -250;
+        else if (distance > (double)s->cfg.max_distance) reward = -20;
+        else reward = -distance;
+    }
+    const int is_done = e.terminated || e.counter > w.max_steps;
+    e.ep_ret += reward; e.ep_len += 1;
+    e.n_contacts = e.n_contacts2[0];   /* reported through SRL_F_COUNTERS */
+    if (rew) rew[i] = (float)reward;
+    if (done) done[i] = (uint8_t)is_done;
+    if (is_done) {
+        if (ep_ret) ep_ret[i] = (float)e.ep_ret;
+        if (ep_len) ep_len[i] = e.ep_len;
+        if (s->auto_reset) oracle_kuka_reset_env(s, i, NULL);
+    }
+    if (obs) oracle_kuka_obs(s, i, obs + 3 * (size_t)i);
 }
 
 void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* noise, float* obs, float* rew,
@@ -850,6 +955,10 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
     /* ---- _reward() (:428-463) ---- */
     const double dx = e.button_pos[0] - e.gripper_pos[0], dy = e.button_pos[1] - e.gripper_pos[1], dz = e.button_pos[2] - e.gripper_pos[2];
     const double distance = sqrt(dx * dx + dy * dy + dz * dz);
+    if (s->kind == SRL_ENV_KUKA_2BUTTON) {
+        two_button_reward(s, w, e, i, distance, obs, rew, done, ep_ret, ep_len);
+        return;
+    }
     double reward = e.contact_button ? 1.0 : 0.0;
     e.n_contacts += e.contact_button ? 1 : 0;
     const int table = e.contact_table;
@@ -892,6 +1001,10 @@ int oracle_kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
         case SRL_F_COUNTERS: if (!need(4, 4)) return 1; I[4 * i] = e.n_contacts; I[4 * i + 1] = e.n_outside; I[4 * i + 2] = e.terminated; I[4 * i + 3] = (int32_t)e.episode; break;
         case SRL_F_EPISODE_STATS: if (!need(2, 8)) return 1; D[2 * i] = e.ep_ret; D[2 * i + 1] = (double)e.ep_len; break;
         case SRL_F_BUTTON_BASE: if (!need(3, 8)) return 1; for (int a = 0; a < 3; ++a) D[3 * i + a] = e.button_base[a]; break;
+        case SRL_F_TWO_BUTTON: if (!need(8, 8)) return 1;
+            D[8 * i] = e.n_contacts2[0]; D[8 * i + 1] = e.n_contacts2[1]; D[8 * i + 2] = e.goal_id;
+            for (int a = 0; a < 3; ++a) D[8 * i + 3 + a] = e.button2_base[a];
+            D[8 * i + 6] = e.qb2; D[8 * i + 7] = e.qdb2; break;
         default: oracle_set_error("get_state: unknown field %d", field); return 1;
         }
     }
@@ -979,6 +1092,7 @@ void* okb_create(const void* blob, size_t bytes) {
     OkbWorld* w = new OkbWorld();
     if (!parse_model(blob, bytes, w->m)) { delete w; return NULL; }
     memset(&w->e, 0, sizeof(KEnv));
+    w->e.nbuttons = 1;
     w->iterations = (int)w->m.sc[KM_SC_SOLVER_ITERS];
     for (int a = 0; a < 3; ++a) w->e.button_base[a] = w->m.sc[KM_SC_BUTTON_BASE + a];
     return w;
@@ -987,10 +1101,18 @@ void okb_destroy(void* h) { delete (OkbWorld*)h; }
 void okb_reset_world(void* h) {           /* p.resetSimulation(): everything back to the load-time state */
     OkbWorld* w = (OkbWorld*)h;
     memset(&w->e, 0, sizeof(KEnv));
+    w->e.nbuttons = 1;
     for (int a = 0; a < 3; ++a) w->e.button_base[a] = w->m.sc[KM_SC_BUTTON_BASE + a];
     refresh_link_states(w->m, w->e);
 }
 void okb_set_iterations(void* h, int n) { ((OkbWorld*)h)->iterations = n; }
+void okb_set_ik_damping(void* h, double d) { ((OkbWorld*)h)->m.sc[KM_SC_IK_DAMPING] = d; }   /* jointDamping given / server default */
+void okb_set_button2_base(void* h, double x, double y) {   /* a second simple_button body is loaded (kuka_2button_gym_env.py:68) */
+    OkbWorld* w = (OkbWorld*)h; w->e.nbuttons = 2; w->e.button2_base[0] = x; w->e.button2_base[1] = y; w->e.button2_base[2] = w->m.sc[KM_SC_BUTTON_BASE + 2];
+}
+void okb_get2(void* h, double* out) {   /* contact with any link of button 1 / button 2 in the last manifold; second glider */
+    OkbWorld* w = (OkbWorld*)h; out[0] = w->e.contact_button_any[0]; out[1] = w->e.contact_button_any[1]; out[2] = w->e.qb2; out[3] = w->e.qdb2;
+}
 void okb_set_button_base(void* h, double x, double y) { OkbWorld* w = (OkbWorld*)h; w->e.button_base[0] = x; w->e.button_base[1] = y; }
 void okb_set_button_base3(void* h, double x, double y, double z) { OkbWorld* w = (OkbWorld*)h; w->e.button_base[0] = x; w->e.button_base[1] = y; w->e.button_base[2] = z; }
 void okb_reset_joint(void* h, int body, double q) {  /* p.resetJointState */

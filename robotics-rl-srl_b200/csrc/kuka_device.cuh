@@ -69,6 +69,12 @@ struct KukaEnv {
     int cbutton, ctable;     // manifold flags of the last stepSimulation
     uint32_t episode, total_steps;
     float ep_ret; int ep_len;
+    // ---- Kuka2ButtonGymEnv only (kuka_2button_gym_env.py): second button body + goal bookkeeping ----
+    float qb2, qdb2;         // second button glider
+    float bb2x, bb2y;        // second button base origin (z = P.btn_base[2]: both rest on the table)
+    int n_contacts2;         // n_contacts[1]; n_contacts above is n_contacts[0]
+    int goal_id;             // which button is the next one to press (:43)
+    int cany0, cany1;        // manifold flags: contact with ANY link of button 1 / 2 (getContactPoints without a link index, :165)
 };
 
 struct KukaKin {             // kinematics of the current configuration
@@ -113,7 +119,7 @@ KK_DEV void sphere_cylinder(f3 s, float r, float cx, float cy, float z0, float z
 // streamed from L2 every step -- 58% of all stall samples were `no_inst` (instruction fetch).  The per-body passes are
 // therefore ROLLED loops over the 12 bodies with their arrays in thread-local memory: a few hundred instructions that
 // stay resident in the instruction caches.
-template <bool WITH_CONTACTS>
+template <bool WITH_CONTACTS, bool TWOB>
 KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& ct) {
     float R[9], R7[9];
     float Rall[WITH_CONTACTS ? KK_NB : 1][9];  // per-body rotations for the sphere loop (local memory)
@@ -124,12 +130,15 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
     R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) R7[t] = R[t];
-    int cbutton = 0, ctable = 0;
+    int cbutton = 0, ctable = 0, cany0 = 0, cany1 = 0;
     float zmin_body = 1e30f;
     if (WITH_CONTACTS) ct.n = 0;
     const float bz = e.bbz;
     const float disc0 = bz + P.glider_z + e.qb + P.disc_z0, disc1 = bz + P.glider_z + e.qb + P.disc_z1;
-    const float zmax_shapes = fmaxf(disc1, fmaxf(bz + P.stack_top, P.table_z));
+    const float b2z = P.btn_base[2];
+    const float disc20 = b2z + P.glider_z + e.qb2 + P.disc_z0, disc21 = b2z + P.glider_z + e.qb2 + P.disc_z1;
+    float zmax_shapes = fmaxf(disc1, fmaxf(bz + P.stack_top, P.table_z));
+    if (TWOB) zmax_shapes = fmaxf(zmax_shapes, fmaxf(disc21, b2z + P.stack_top));
 #pragma unroll 1
     for (int i = 0; i < KK_NB; ++i) {
         if (i == 10) {  // second finger restarts from the gripper base
@@ -211,18 +220,22 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
             const f3 sc = mk3(pb.x + Rb[0] * P.sph_c[sidx][0] + Rb[1] * P.sph_c[sidx][1] + Rb[2] * P.sph_c[sidx][2],
                               pb.y + Rb[3] * P.sph_c[sidx][0] + Rb[4] * P.sph_c[sidx][1] + Rb[5] * P.sph_c[sidx][2], scz);
 #pragma unroll 1
-            for (int shape = 0; shape < 3; ++shape) {
+            for (int shape = 0; shape < (TWOB ? 5 : 3); ++shape) {   // 0 table, 1 / 2 disc / stack of button 1, 3 / 4 of button 2
                 float dist; f3 nn;
                 if (shape == 0) {
                     if (sc.x < P.txmin || sc.x > P.txmax || sc.y < P.tymin || sc.y > P.tymax) continue;
                     dist = sc.z - P.table_z - r; nn = mk3(0.f, 0.f, 1.f);
-                } else {
+                } else if (!TWOB || shape < 3) {
                     const float z0 = shape == 1 ? disc0 : bz, z1 = shape == 1 ? disc1 : bz + P.stack_top;
                     sphere_cylinder(sc, r, e.bbx, e.bby, z0, z1, shape == 1 ? P.disc_r : P.stack_r, dist, nn);
+                } else {
+                    const float z0 = shape == 3 ? disc20 : b2z, z1 = shape == 3 ? disc21 : b2z + P.stack_top;
+                    sphere_cylinder(sc, r, e.bb2x, e.bb2y, z0, z1, shape == 3 ? P.disc_r : P.stack_r, dist, nn);
                 }
                 if (dist > P.cdist) continue;
                 if (shape == 0) ctable = 1;
                 if (shape == 1) cbutton = 1;
+                if (TWOB) { if (shape == 1 || shape == 2) cany0 = 1; if (shape >= 3) cany1 = 1; }
                 if (ct.n < P.max_contacts && ct.n < KK_MAXC) {
                     const int n = ct.n;
                     ct.body[n] = b; ct.shape[n] = shape; ct.dist[n] = dist; ct.nrm[n] = nn;
@@ -232,7 +245,7 @@ KK_DEV void kuka_fk(const KukaParams& P, KukaEnv& e, KukaKin& k, KukaContacts& c
             }
         }
     }
-    if (WITH_CONTACTS) { e.cbutton = cbutton; e.ctable = ctable; }
+    if (WITH_CONTACTS) { e.cbutton = cbutton; e.ctable = ctable; if (TWOB) { e.cany0 = cany0; e.cany1 = cany1; } }
     e.grip[0] = k.c[8].x; e.grip[1] = k.c[8].y; e.grip[2] = k.c[8].z;   // getLinkState(kuka, 8)[0]: COM of link 8
     e.eepos[0] = k.p[6].x; e.eepos[1] = k.p[6].y; e.eepos[2] = k.p[6].z;
 }
@@ -638,8 +651,10 @@ KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
 // One applyAction + stepSimulation.  `k`/`ct` hold the kinematics / contacts of the CURRENT configuration
 // (computed by the caller with kuka_fk<true>); on return q, qd, qb, qdb are advanced by one time step.
 // JOINTS: use_inverse_kinematics = False (action_joints): the 7 arm set-points are given (`q_joints`), no IK (kuka.py:158-161).
-template <bool JOINTS>
+// TWOB: Kuka2ButtonGymEnv -- a second button glider (DoF KK_NB + 1) with the same motor / limit rows, right after the first.
+template <bool JOINTS, bool TWOB>
 KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed, const float* q_joints) {
+    constexpr int ND = TWOB ? KK_NB + 2 : KK_NB + 1;
     // ---- applyAction: IK + motor set-points (kuka.py:142-187) ----
     float q_ik[7];
     if (JOINTS) {
@@ -663,7 +678,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     kuka_dynamics(P, e, k, A, bias);
 #endif
     kuka_spd_inverse(A);
-    float v[KK_ND];
+    float v[ND];
     {
         float rhs[KK_NB];
 #pragma unroll
@@ -677,6 +692,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         }
         const float vb = e.qdb;
         v[KK_NB] = fmaf(P.dt, P.gz - P.kl * vb * (1.0f + fabsf(vb)), vb);
+        if (TWOB) { const float vb2 = e.qdb2; v[ND - 1] = fmaf(P.dt, P.gz - P.kl * vb2 * (1.0f + fabsf(vb2)), vb2); }
     }
     // ---- motor rows: target velocity, impulse bound (btMultiBodyJointMotor) ----
     float tgt[KK_NB], lam[KK_NB], invd[KK_NB];
@@ -691,10 +707,15 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     if (button_armed) { b_tgt = fmaf(P.btn_kp_dt, P.btn_target - e.qb, v[KK_NB]) - P.btn_kd * v[KK_NB]; b_hi = P.btn_maximp; }
     else { b_tgt = 0.f; b_hi = P.btn_idle_imp; }
     const float b_invd = 1.0f / P.btn_minv;
+    float b2_tgt = 0.f, b2_lam = 0.f;   // second button motor: same command as the first (kuka_2button_gym_env.py:137-138)
+    if (TWOB && button_armed) b2_tgt = fmaf(P.btn_kp_dt, P.btn_target - e.qb2, v[ND - 1]) - P.btn_kd * v[ND - 1];
     // ---- limit rows (active while the joint is on / beyond the limit) ----
     const bool bl_lo = (e.qb - P.gl_lo) <= P.lim_eps, bl_hi = (P.gl_hi - e.qb) <= P.lim_eps;
     const float bl_lo_t = -P.erp * (e.qb - P.gl_lo) * P.inv_dt, bl_hi_t = -P.erp * (P.gl_hi - e.qb) * P.inv_dt;
     float bl_lo_lam = 0.f, bl_hi_lam = 0.f;
+    const bool b2l_lo = TWOB && (e.qb2 - P.gl_lo) <= P.lim_eps, b2l_hi = TWOB && (P.gl_hi - e.qb2) <= P.lim_eps;
+    const float b2l_lo_t = TWOB ? -P.erp * (e.qb2 - P.gl_lo) * P.inv_dt : 0.f, b2l_hi_t = TWOB ? -P.erp * (P.gl_hi - e.qb2) * P.inv_dt : 0.f;
+    float b2l_lo_lam = 0.f, b2l_hi_lam = 0.f;
     unsigned lim_lo_mask = 0u, lim_hi_mask = 0u;
     float lim_lam_lo[KK_NB], lim_lam_hi[KK_NB];
 #pragma unroll
@@ -705,7 +726,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     }
     // ---- contact rows: J, W = M^-1 J^T, 1/D, target; two friction rows each (rare path, local memory) ----
     const int nc = ct.n;
-    float cJ[3 * KK_MAXC][KK_ND], cW[3 * KK_MAXC][KK_ND], c_invd[3 * KK_MAXC], c_tgt[3 * KK_MAXC], c_lam[3 * KK_MAXC];
+    float cJ[3 * KK_MAXC][ND], cW[3 * KK_MAXC][ND], c_invd[3 * KK_MAXC], c_tgt[3 * KK_MAXC], c_lam[3 * KK_MAXC];
     if (nc > 0) {
         for (int r = 0; r < 3 * nc; ++r) {
             const int c = r < nc ? r : (r - nc) >> 1;
@@ -739,6 +760,11 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             }
             cW[r][KK_NB] = cJ[r][KK_NB] * P.btn_minv;
             D = fmaf(cJ[r][KK_NB], cW[r][KK_NB], D);
+            if (TWOB) {
+                cJ[r][ND - 1] = ct.shape[c] == 3 ? -dir.z : 0.f;
+                cW[r][ND - 1] = cJ[r][ND - 1] * P.btn_minv;
+                D = fmaf(cJ[r][ND - 1], cW[r][ND - 1], D);
+            }
             c_invd[r] = 1.0f / D;
             c_lam[r] = 0.f;
             if (r < nc) { const float pen = ct.dist[c]; c_tgt[r] = pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt; }
@@ -748,6 +774,20 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     // ---- projected Gauss-Seidel: row order = motors (button first), limits (button first), contact normals, friction ----
     // Button rows are made branch-free: an inactive limit row gets the bound [0, 0] (an exact no-op).
     const float bl_lo_hi = bl_lo ? P.lim_maximp : 0.f, bl_hi_hi = bl_hi ? P.lim_maximp : 0.f;
+    const float b2l_lo_hi = b2l_lo ? P.lim_maximp : 0.f, b2l_hi_hi = b2l_hi ? P.lim_maximp : 0.f;
+    // the second button's rows (motor; lower / upper limit): an independent 1-DoF chain like the first one's
+#define KK_BUTTON2_MOTOR()                                                                                             \
+    if (TWOB) {                                                                                                        \
+        const float s2 = fminf(fmaxf(fmaf(b2_tgt - v[ND - 1], b_invd, b2_lam), -b_hi), b_hi);                          \
+        v[ND - 1] = fmaf(P.btn_minv, s2 - b2_lam, v[ND - 1]); b2_lam = s2;                                             \
+    }
+#define KK_BUTTON2_LIMITS()                                                                                            \
+    if (TWOB) {                                                                                                        \
+        float s2 = fminf(fmaxf(fmaf(b2l_lo_t - v[ND - 1], b_invd, b2l_lo_lam), 0.f), b2l_lo_hi);                       \
+        v[ND - 1] = fmaf(P.btn_minv, s2 - b2l_lo_lam, v[ND - 1]); b2l_lo_lam = s2;                                     \
+        s2 = fminf(fmaxf(fmaf(b2l_hi_t + v[ND - 1], b_invd, b2l_hi_lam), 0.f), b2l_hi_hi);                             \
+        v[ND - 1] = fmaf(-P.btn_minv, s2 - b2l_hi_lam, v[ND - 1]); b2l_hi_lam = s2;                                    \
+    }
     float mi[KK_NB];  // impulse bounds in vector registers: no uniform-register reloads inside the sweep
 #pragma unroll
     for (int i = 0; i < KK_NB; ++i) asm volatile("mov.f32 %0, %1;" : "=f"(mi[i]) : "f"(P.maximp[i]));  // opaque copy: keeps ptxas from re-reading the constant bank
@@ -787,6 +827,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
                 v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
             }
+            KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
             float dprev = 0.f;
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {
@@ -821,6 +862,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
                 v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
             }
+            KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
             float dprev = 0.f;
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {
@@ -842,7 +884,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 for (int c = 0; c < nc; ++c) {
                     float jv = 0.f;
 #pragma unroll
-                    for (int j = 0; j < KK_ND; ++j) jv = fmaf(cJ[c][j], v[j], jv);
+                    for (int j = 0; j < ND; ++j) jv = fmaf(cJ[c][j], v[j], jv);
                     act = act | (c_tgt[c] - jv > 0.f);
                 }
                 if (act) { it0 = it; resume_mid_sweep = true; break; }
@@ -862,6 +904,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 const float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
                 v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
             }
+            KK_BUTTON2_MOTOR()
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {  // arm motors: unit Jacobian, W = A[:, i]
                 const float s = fminf(fmaxf(fmaf(tgt[i] - v[i], invd[i], lam[i]), -mi[i]), mi[i]);
@@ -876,6 +919,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
                 v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
             }
+            KK_BUTTON2_LIMITS()
             }
             resume_mid_sweep = false;
             if (lim_lo_mask | lim_hi_mask) {
@@ -905,13 +949,13 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 }
                 float jv = 0.f;
 #pragma unroll
-                for (int j = 0; j < KK_ND; ++j) jv = fmaf(cJ[r][j], v[j], jv);
+                for (int j = 0; j < ND; ++j) jv = fmaf(cJ[r][j], v[j], jv);
                 const float s = fminf(fmaxf(fmaf(c_tgt[r] - jv, c_invd[r], c_lam[r]), lo), hi);
                 const float d = s - c_lam[r];
                 if (d == 0.f) continue;       // inactive (separating) contact: nothing to apply
                 c_lam[r] = s;
 #pragma unroll
-                for (int j = 0; j < KK_ND; ++j) v[j] = fmaf(cW[r][j], d, v[j]);
+                for (int j = 0; j < ND; ++j) v[j] = fmaf(cW[r][j], d, v[j]);
             }
         }
     }
@@ -919,4 +963,5 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
 #pragma unroll
     for (int i = 0; i < KK_NB; ++i) { e.qd[i] = v[i]; e.q[i] = fmaf(P.dt, v[i], e.q[i]); }
     e.qdb = v[KK_NB]; e.qb = fmaf(P.dt, v[KK_NB], e.qb);
+    if (TWOB) { e.qdb2 = v[ND - 1]; e.qb2 = fmaf(P.dt, v[ND - 1], e.qb2); }
 }

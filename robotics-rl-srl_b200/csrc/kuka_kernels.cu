@@ -26,7 +26,8 @@ struct KukaDev {
     float4* grip;    // gripper_pos.xyz, signed button speed
     float4* eepos;   // link-6 origin xyz, moving button: low word of the float64 target y
     int4*   cnt;     // counter, n_contacts, n_outside, terminated | cbutton << 1 | ctable << 2
-    int4*   cnt2;    // episode, total_steps, ep_len, moving button: high word of the float64 target y
+    int4*   cnt2;    // episode, total_steps, ep_len, moving button: high word of the float64 target y / two buttons: n_contacts[1]
+    float4* btn2;    // two buttons only: second glider q, qd, second button base x, y
     KukaParams P;
     int epw;         // live lanes per warp
 };
@@ -37,6 +38,7 @@ constexpr float DELTA_V = 0.03f, DELTA_V_CONTINUOUS = 0.0035f, DELTA_THETA = 0.1
 constexpr double NOISE_STD = 0.01, NOISE_STD_CONTINUOUS = 0.0001, NOISE_STD_JOINTS = 0.002;   // :31-33
 constexpr int N_CONTACTS_BEFORE_TERMINATION = 5, N_STEPS_OUTSIDE_SAFETY_SPHERE = 5000, N_RANDOM_ACTIONS_AT_INIT = 5;
 
+template <bool TWOB>
 KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -55,8 +57,16 @@ KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
     e.terminated = c.w & 1; e.cbutton = (c.w >> 1) & 1; e.ctable = (c.w >> 2) & 1;
     e.episode = (uint32_t)c2.x; e.total_steps = (uint32_t)c2.y; e.ep_len = c2.z;
     e.by64 = __hiloint2double(c2.w, __float_as_int(ep.w));
+    e.qb2 = 0.f; e.qdb2 = 0.f; e.bb2x = 0.f; e.bb2y = 0.f; e.n_contacts2 = 0; e.goal_id = 0; e.cany0 = 0; e.cany1 = 0;
+    if (TWOB) {
+        const float4 b2 = d.btn2[i];
+        e.qb2 = b2.x; e.qdb2 = b2.y; e.bb2x = b2.z; e.bb2y = b2.w;
+        e.n_contacts2 = c2.w; e.by64 = 0.0;
+        e.cany0 = (c.w >> 3) & 1; e.cany1 = (c.w >> 4) & 1; e.goal_id = (c.w >> 5) & 1;
+    }
 }
 
+template <bool TWOB>
 KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -68,8 +78,11 @@ KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
     d.tgt[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.bbz);
     d.grip[i] = make_float4(e.grip[0], e.grip[1], e.grip[2], e.bspeed);
     d.eepos[i] = make_float4(e.eepos[0], e.eepos[1], e.eepos[2], __int_as_float(__double2loint(e.by64)));
-    d.cnt[i] = make_int4(e.counter, e.n_contacts, e.n_outside, e.terminated | (e.cbutton << 1) | (e.ctable << 2));
-    d.cnt2[i] = make_int4((int)e.episode, (int)e.total_steps, e.ep_len, __double2hiint(e.by64));
+    int flags = e.terminated | (e.cbutton << 1) | (e.ctable << 2);
+    if (TWOB) flags |= (e.cany0 << 3) | (e.cany1 << 4) | (e.goal_id << 5);
+    d.cnt[i] = make_int4(e.counter, e.n_contacts, e.n_outside, flags);
+    d.cnt2[i] = make_int4((int)e.episode, (int)e.total_steps, e.ep_len, TWOB ? e.n_contacts2 : __double2hiint(e.by64));
+    if (TWOB) d.btn2[i] = make_float4(e.qb2, e.qdb2, e.bb2x, e.bb2y);
 }
 
 // Kuka.applyAction's accumulate + clip of the commanded end-effector position (kuka.py:134-139)
@@ -104,6 +117,7 @@ KK_DEV void reset_action(const KukaParams& P, const double* __restrict__ d17, ui
 }
 
 // reset(), first half: restore the post-settle snapshot and place the button (:214-247)
+template <bool TWOB>
 KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restrict__ d17, uint64_t genv) {
 #pragma unroll
     for (int i = 0; i < KK_NB; ++i) { e.q[i] = P.snap_q[i]; e.qd[i] = P.snap_qd[i]; }
@@ -116,6 +130,21 @@ KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restric
         else e.bspeed = (philox4x32_10(P.seed, genv, e.episode, PHILOX_PURPOSE_RESET0 + 6).x & 1u) ? 0.001f : -0.001f;
     }
     e.by64 = (double)P.btn_base[1];
+    if (TWOB) {
+        // kuka_2button_gym_env.py:49-69: button 1 always sits at (0.5, 0.125) (its random placement is overwritten, :56-57);
+        // button 2 at (0.5, -0.125), or x = 0.5 + 0.15 U(-1, 1), y = -0.125 + 0.175 U(-1, 0) with random_target
+        e.qb2 = P.snap_qb; e.qdb2 = P.snap_qdb;       // both buttons settle identically (nothing touches them in the 500 steps)
+        e.bb2x = P.btn_base[0]; e.bb2y = -P.btn_base[1];
+        if (P.random_target) {
+            if (d17) { e.bb2x = (float)d17[0]; e.bb2y = (float)d17[1]; }
+            else {
+                const uint4 r = philox4x32_10(P.seed, genv, e.episode, PHILOX_PURPOSE_RESET0);
+                e.bb2x = (float)((double)P.btn_base[0] + (double)P.rand_x * (-1.0 + 2.0 * philox_u01(r.x, r.y)));
+                e.bb2y = (float)(-(double)P.btn_base[1] + 0.175 * (-1.0 + philox_u01(r.z, r.w)));
+            }
+        }
+        return;
+    }
     if (P.random_target) {
         if (d17) { e.bbx = (float)d17[0]; e.bby = (float)d17[1]; e.by64 = d17[1]; }
         else {
@@ -128,9 +157,12 @@ KK_DEV void reset_begin(const KukaParams& P, KukaEnv& e, const double* __restric
 }
 
 // reset(), second half: after the random steps, freeze the target and clear the episode counters (:273-274,215-217)
+template <bool TWOB>
 KK_DEV void reset_end(const KukaParams& P, KukaEnv& e) {
     e.tgt[0] = e.bbx; e.tgt[1] = e.bby;
     e.tgt[2] = e.bbz + P.glider_z + e.qb + P.target_h;  // button link state + BUTTON_DISTANCE_HEIGHT
+    if (TWOB) e.tgt[2] = P.two_tgt_z;          // button_all_pos = [x, y, Z_TABLE + BUTTON_DISTANCE_HEIGHT] (kuka_2button_gym_env.py:59,69,72)
+    if (TWOB) { e.n_contacts2 = 0; e.goal_id = 0; }
     e.counter = 0; e.n_contacts = 0; e.n_outside = 0; e.terminated = 0;
     e.ep_ret = 0.f; e.ep_len = 0;
     e.episode += 1;
@@ -154,7 +186,7 @@ enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2 };
 //   op = ROLLOUT: T env steps (step() + step2() + _reward() + _termination() + VecEnv auto-reset)
 //   op = RESET  : reset() of the masked envs with optional host-supplied draws
 //   op = SETTLE : the 500 zero-action steps of reset() (:242-247), identical for every episode -> snapshot
-template <bool JOINTS>
+template <bool JOINTS, bool TWOB>
 __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
                                                        const void* __restrict__ actions, const float* __restrict__ noise,
                                                        const uint8_t* __restrict__ mask, const double* __restrict__ draws,
@@ -168,13 +200,13 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     const uint64_t genv = P.env_offset + (uint64_t)i;
     const size_t N = (size_t)n;
     KukaEnv e; KukaKin k; KukaContacts ct;
-    env_load(d, i, e);
+    env_load<TWOB>(d, i, e);
 
     int reset_left = 0;          // > 0: inside reset(), this many random micro-steps to go
     bool in_reset = false;       // reset() in progress (finalised when reset_left reaches 0)
     bool pending = false;        // an env step's physics has run; reward / done / obs still to be produced
     int rep = 0, t = 0;
-    int saved_cb = 0, saved_ct = 0;
+    int saved_cb = 0, saved_ct = 0, saved_a0 = 0, saved_a1 = 0;
     float dx = 0.f, dy = 0.f, dz = 0.f;
     float qj[JOINTS ? 7 : 1];   // joint-space micro action: the 7 arm set-points (action_joints)
 #pragma unroll
@@ -182,25 +214,48 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     const double* d17 = nullptr;
     if (op == KUKA_OP_RESET) {
         d17 = draws ? draws + (size_t)i * 18 : nullptr;
-        reset_begin(P, e, d17, genv);
+        reset_begin<TWOB>(P, e, d17, genv);
         in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
     } else if (op == KUKA_OP_SETTLE) {
 #pragma unroll
         for (int j = 0; j < KK_NB; ++j) { e.q[j] = P.snap_q[j]; e.qd[j] = 0.f; }  // resetJointState (kuka.py:68-69)
         e.ee[0] = P.ee_init[0]; e.ee[1] = P.ee_init[1]; e.ee[2] = P.ee_init[2];
         e.qb = 0.f; e.qdb = 0.f; e.bbx = P.btn_base[0]; e.bby = P.btn_base[1]; e.bbz = P.btn_base[2]; e.bspeed = 0.f; e.by64 = 0.0;
+        if (TWOB) { e.qb2 = 0.f; e.qdb2 = 0.f; e.bb2x = P.btn_base[0]; e.bb2y = -P.btn_base[1]; }
         in_reset = true; reset_left = 500;
     }
     for (;;) {
-        kuka_fk<true>(P, e, k, ct);  // link states of the configuration just reached + collision detection for the next step
-        const int new_cb = e.cbutton, new_ct = e.ctable;
+        kuka_fk<true, TWOB>(P, e, k, ct);  // link states of the configuration just reached + collision detection for the next step
+        const int new_cb = e.cbutton, new_ct = e.ctable, new_a0 = TWOB ? e.cany0 : 0, new_a1 = TWOB ? e.cany1 : 0;
         if (pending) {
             // ---- _reward() (:428-463): manifold of the step that just ran, link states after it ----
             pending = false;
             const size_t off = (size_t)t * N + (size_t)i;
             const float ddx = e.tgt[0] - e.grip[0], ddy = e.tgt[1] - e.grip[1], ddz = e.tgt[2] - e.grip[2];
             const float distance = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-            float reward = saved_cb ? 1.f : 0.f;
+            float reward;
+            if (TWOB) {
+                // Kuka2ButtonGymEnv._reward (kuka_2button_gym_env.py:157-214): contact with ANY link of the goal button; the sparse
+                // reward only counts on the last button; 5 contacts on button 1 switch the goal (and the target) to button 2
+                const int contact = e.goal_id ? saved_a1 : saved_a0;
+                reward = 0.f;
+                if (e.goal_id) { e.n_contacts2 += contact; reward = contact ? 1.f : 0.f; }
+                else {
+                    e.n_contacts += contact;
+                    if (e.n_contacts >= N_CONTACTS_BEFORE_TERMINATION) { e.goal_id = 1; e.tgt[0] = e.bb2x; e.tgt[1] = e.bb2y; }
+                }
+                if (distance > P.max_distance || saved_ct) { reward = -1.f; e.n_outside += 1; } else e.n_outside = 0;
+                if (saved_ct || e.n_contacts2 >= N_CONTACTS_BEFORE_TERMINATION || e.n_outside >= N_STEPS_OUTSIDE_SAFETY_SPHERE - 1) e.terminated = 1;
+                if (P.shape_reward) {
+                    const int n_goal = e.goal_id ? e.n_contacts2 : e.n_contacts;   // of the goal AFTER a possible switch (:198)
+                    if (e.terminated && reward > 0.f) reward = 50.f;
+                    else if (n_goal < N_CONTACTS_BEFORE_TERMINATION && contact) reward = 25.f;
+                    else if (saved_ct) reward = -250.f;
+                    else if (distance > P.max_distance) reward = -20.f;
+                    else reward = -distance;
+                }
+            } else {
+            reward = saved_cb ? 1.f : 0.f;
             e.n_contacts += saved_cb;
             if (distance > P.max_distance || saved_ct) { reward = -1.f; e.n_outside += 1; } else e.n_outside = 0;
             if (saved_ct || e.n_contacts >= N_CONTACTS_BEFORE_TERMINATION || e.n_outside >= N_STEPS_OUTSIDE_SAFETY_SPHERE) e.terminated = 1;
@@ -209,6 +264,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 else if (e.terminated && reward > 0.f) reward = 50.f;
                 else if (e.terminated && reward < 0.f) reward = -250.f;
                 else reward = -distance;
+            }
             }
             const bool is_done = e.terminated || e.counter > P.max_steps;  // _termination() (:422-426)
             e.ep_ret += reward; e.ep_len += 1;
@@ -220,7 +276,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             }
             if (is_done && P.auto_reset) {   // SubprocVecEnv worker: reset and return the post-reset observation
                 d17 = nullptr;
-                reset_begin(P, e, nullptr, genv);
+                reset_begin<TWOB>(P, e, nullptr, genv);
                 in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
                 continue;                      // the snapshot configuration needs its own kinematics
             }
@@ -234,7 +290,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 snap[24] = e.ee[0]; snap[25] = e.ee[1]; snap[26] = e.ee[2]; snap[27] = e.qb; snap[28] = e.qdb;
                 return;
             }
-            reset_end(P, e);
+            reset_end<TWOB>(P, e);
             if (obs) {  // getSRLState after reset (:278-279)
                 float* o = obs + 3 * (op == KUKA_OP_RESET ? (size_t)i : (size_t)t * N + (size_t)i);
                 o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2];
@@ -321,8 +377,8 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         }
         // ---- applyAction + stepSimulation ----
         if (!JOINTS) apply_ee_delta(P, e, dx, dy, dz);
-        saved_cb = new_cb; saved_ct = new_ct;
-        kuka_physics_step<JOINTS>(P, e, k, ct, armed, qj);
+        saved_cb = new_cb; saved_ct = new_ct; saved_a0 = new_a0; saved_a1 = new_a1;
+        kuka_physics_step<JOINTS, TWOB>(P, e, k, ct, armed, qj);
         if (!in_reset) {
             // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
             if (e.terminated || e.counter > P.max_steps) { pending = true; rep = 0; }
@@ -330,7 +386,8 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         }
     }
     e.cbutton = saved_cb; e.ctable = saved_ct;
-    env_store(d, i, e);
+    if (TWOB) { e.cany0 = saved_a0; e.cany1 = saved_a1; }
+    env_store<TWOB>(d, i, e);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -383,7 +440,9 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
     P.stack_r = (float)sc[KM_SC_STACK_RADIUS]; P.stack_top = (float)sc[KM_SC_STACK_TOP];
     P.cdist = (float)sc[KM_SC_CONTACT_DIST]; P.mu = (float)sc[KM_SC_FRICTION]; P.erp = (float)sc[KM_SC_ERP];
     P.kl = (float)sc[KM_SC_LIN_DAMPING]; P.ka = (float)sc[KM_SC_ANG_DAMPING];
-    const double* box = sc + (s->cfg.random_target ? KM_SC_BOX_LARGE : KM_SC_BOX_SMALL);  // small_constraints = not random_target (:239)
+    const bool two = s->kind == SRL_ENV_KUKA_2BUTTON;
+    // small_constraints = not random_target (:239); Kuka2Button always uses the large box (kuka_2button_gym_env.py:78)
+    const double* box = sc + ((s->cfg.random_target || two) ? KM_SC_BOX_LARGE : KM_SC_BOX_SMALL);
     for (int a = 0; a < 6; ++a) P.box[a] = (float)box[a];
     for (int a = 0; a < 4; ++a) P.ikq[a] = (float)sc[KM_SC_IK_QUAT + a];
     P.ik_damp = sc[KM_SC_IK_DAMPING];
@@ -400,10 +459,29 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
     P.auto_reset = s->auto_reset; P.max_distance = s->cfg.max_distance;
     P.moving_button = s->kind == SRL_ENV_KUKA_MOVING_BUTTON;
     P.action_joints = s->cfg.action_joints != 0;
+    P.two_buttons = two;
+    P.two_tgt_z = (float)(-0.2 + sc[KM_SC_TARGET_HEIGHT]);   // Z_TABLE + BUTTON_DISTANCE_HEIGHT (kuka_button_gym_env.py:26,35)
+    if (two) {
+        P.btn_base[1] = 0.125f;                               // kuka_2button_gym_env.py:49-57 (button 2 mirrors it at -0.125)
+        // `use_null_space = True` (:80) -> calculateInverseKinematics(uid, link, pos, orn, ll, ul, jr, rp) (kuka.py:147-149).  RECALLED
+        // pybullet 1.8.6 behaviour: the null-space task needs one list entry per JOINT (14; kuka.py:34-40 gives 7) and is dropped,
+        // and without a jointDamping argument the server's default damping 0.5 per DoF applies
+        P.ik_damp = 0.5;
+    }
     for (int j = 0; j < 7; ++j) P.qinit[j] = P.snap_q[j];   // snap_q still holds the initial joint vector here
     P.seed = s->seed; P.env_offset = s->cfg.global_env_offset;
     return true;
 }
+
+// one instantiation per (action_joints, two_buttons): the default kernel pays nothing for the variants
+#define KUKA_LAUNCH(d, grid, block, st, ...)                                                                            \
+    do {                                                                                                                \
+        if ((d)->P.two_buttons) {                                                                                       \
+            if ((d)->P.action_joints) kuka_kernel<true, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                \
+            else kuka_kernel<false, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                                    \
+        } else if ((d)->P.action_joints) kuka_kernel<true, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);            \
+        else kuka_kernel<false, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                                       \
+    } while (0)
 
 void grid_for(const srl_sim* s, const KukaDev* d, int& grid, int& block) {
     const int warps = (s->n + d->epw - 1) / d->epw;
@@ -414,9 +492,6 @@ void grid_for(const srl_sim* s, const KukaDev* d, int& grid, int& block) {
 }  // namespace
 
 int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
-    if (s->kind == SRL_ENV_KUKA_2BUTTON) {
-        srl_set_error("Kuka2ButtonGymEnv-v0 (two buttons, null-space IK) is not implemented"); return 1;
-    }
     KukaDev* d = new KukaDev();
     memset(d, 0, sizeof(*d));
     s->kuka = d;
@@ -426,6 +501,7 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
     for (float4** p : f4) { SRL_CUDA_OK(cudaMalloc(p, N * sizeof(float4))); SRL_CUDA_OK(cudaMemset(*p, 0, N * sizeof(float4))); }
     SRL_CUDA_OK(cudaMalloc(&d->cnt, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(d->cnt, 0, N * sizeof(int4)));
     SRL_CUDA_OK(cudaMalloc(&d->cnt2, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(d->cnt2, 0, N * sizeof(int4)));
+    SRL_CUDA_OK(cudaMalloc(&d->btn2, N * sizeof(float4))); SRL_CUDA_OK(cudaMemset(d->btn2, 0, N * sizeof(float4)));
     // live lanes per warp: spread a small batch over every warp scheduler (4 per SM), ONE warp each -- the PGS
     // sweep of a single warp already fills its scheduler's issue slots, a second resident warp only adds latency
     // (measured on B200, 4096 envs: 4 lanes/warp 11.4 ms per 128 steps, 7 lanes/warp 9.0 ms, 32 lanes/warp 8.9 ms)
@@ -440,8 +516,7 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
     float* snap = nullptr;
     SRL_CUDA_OK(cudaMalloc(&snap, 32 * sizeof(float)));
     { const int save_epw = d->epw; d->epw = 1;
-      if (d->P.action_joints) kuka_kernel<true><<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
-      else kuka_kernel<false><<<1, 32>>>(*d, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
+      KUKA_LAUNCH(d, 1, 32, 0, 1, KUKA_OP_SETTLE, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, snap);
       d->epw = save_epw; }
     SRL_CUDA_OK(cudaGetLastError());
     float h[32];
@@ -457,7 +532,7 @@ void kuka_free(srl_sim* s) {
     KukaDev* d = s->kuka;
     if (!d) return;
     for (int k = 0; k < 3; ++k) { cudaFree(d->q[k]); cudaFree(d->qd[k]); }
-    cudaFree(d->misc0); cudaFree(d->misc1); cudaFree(d->tgt); cudaFree(d->grip); cudaFree(d->eepos); cudaFree(d->cnt); cudaFree(d->cnt2);
+    cudaFree(d->misc0); cudaFree(d->misc1); cudaFree(d->tgt); cudaFree(d->grip); cudaFree(d->eepos); cudaFree(d->cnt); cudaFree(d->cnt2); cudaFree(d->btn2);
     delete d;
     s->kuka = nullptr;
 }
@@ -465,8 +540,7 @@ void kuka_free(srl_sim* s) {
 int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st) {
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
-    if (d->P.action_joints) kuka_kernel<true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
-    else kuka_kernel<false><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    KUKA_LAUNCH(d, grid, block, st, s->n, KUKA_OP_RESET, 0, nullptr, nullptr, mask, draws, obs, nullptr, nullptr, nullptr, nullptr, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -475,8 +549,7 @@ int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noi
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
-    if (d->P.action_joints) kuka_kernel<true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
-    else kuka_kernel<false><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
+    KUKA_LAUNCH(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -534,6 +607,18 @@ int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
         SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt, N * sizeof(int4), cudaMemcpyDeviceToHost));
         SRL_CUDA_OK(cudaMemcpy(ib.data(), d->cnt2, N * sizeof(int4), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < N; ++i) { I[4 * i] = ia[i].y; I[4 * i + 1] = ia[i].z; I[4 * i + 2] = ia[i].w & 1; I[4 * i + 3] = ib[i].x; }
+        return 0;
+    }
+    case SRL_F_TWO_BUTTON: {
+        if (!need(8, 8)) return 1;
+        std::vector<int4> ib(N);
+        SRL_CUDA_OK(pull(a, d->btn2));
+        SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        SRL_CUDA_OK(cudaMemcpy(ib.data(), d->cnt2, N * sizeof(int4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) {
+            D[8 * i] = d->P.two_buttons ? ia[i].y : 0; D[8 * i + 1] = d->P.two_buttons ? ib[i].w : 0; D[8 * i + 2] = (ia[i].w >> 5) & 1;
+            D[8 * i + 3] = a[i].z; D[8 * i + 4] = a[i].w; D[8 * i + 5] = d->P.btn_base[2]; D[8 * i + 6] = a[i].x; D[8 * i + 7] = a[i].y;
+        }
         return 0;
     }
     case SRL_F_EPISODE_STATS: {

@@ -57,6 +57,8 @@ struct KukaParams {
     int   is_discrete, random_target, force_down, shape_reward, action_repeat, max_steps, auto_reset;
     int   action_joints;   // joint-space actions: use_inverse_kinematics = False (kuka_button_gym_env.py:238, kuka.py:158-161)
     float qinit[7];        // initial arm joint vector (kuka.py:65-66): what joint-space set-points are relative to
+    int   two_buttons;     // Kuka2ButtonGymEnv: second button body, goal bookkeeping, IK damping 0.5 (kuka_2button_gym_env.py)
+    float two_tgt_z;       // Z_TABLE + BUTTON_DISTANCE_HEIGHT: the z of both two-button targets
     int   moving_button;   // KukaMovingButtonGymEnv: the button slides along y (kuka_moving_button_gym_env.py:109-119)
     float max_distance;
     uint64_t seed, env_offset;

@@ -103,7 +103,7 @@ int srl_sim_create(srl_sim** out, int env_kind, int num_envs, int device, const 
     if (s->cfg.timestep <= 0.f) s->cfg.timestep = 1.0f / 240.0f;
     s->seed = seed;
     s->auto_reset = !cfg->no_auto_reset;
-    s->max_steps = cfg->max_steps > 0 ? cfg->max_steps : (srl_is_mobile(env_kind) ? 250 : env_kind == SRL_ENV_KUKA_MOVING_BUTTON ? 1500 : 1000);
+    s->max_steps = cfg->max_steps > 0 ? cfg->max_steps : (srl_is_mobile(env_kind) ? 250 : (env_kind == SRL_ENV_KUKA_MOVING_BUTTON || env_kind == SRL_ENV_KUKA_2BUTTON) ? 1500 : 1000);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         srl_set_error("create: cudaEventCreate failed");
         delete s;

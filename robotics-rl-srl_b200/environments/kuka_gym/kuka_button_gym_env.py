@@ -205,14 +205,18 @@ class KukaButtonGymEnv(SRLGymEnv):
             raise NotImplementedError("image observations (raw_pixels) are out of scope of the batched simulator; "
                                       "use srl_model='ground_truth'")
 
-    def _reset_draws(self):
-        """np_random draws of reset() in the reference's order (:227-231, :250-266) -> the 18 reset values
-        (button x, y; 5 x (dx, dy, dz); signed button speed, 0 except for the moving-button variant)."""
+    def _draw_button_placement(self):
+        """np_random draws that place the button (:227-231) -> (x, y) handed to the kernel."""
         x_pos, y_pos = 0.5, 0
         if self._random_target:
             x_pos += 0.15 * self.np_random.uniform(-1, 1)
             y_pos += 0.3 * self.np_random.uniform(-1, 1)
-        draws = [x_pos, y_pos]
+        return [x_pos, y_pos]
+
+    def _reset_draws(self):
+        """np_random draws of reset() in the reference's order (:227-231, :250-266) -> the 18 reset values
+        (button x, y; 5 x (dx, dy, dz); signed button speed, 0 except for the moving-button variant)."""
+        draws = self._draw_button_placement()
         for _ in range(N_RANDOM_ACTIONS_AT_INIT):
             action = [0, 0, 0]
             if self._is_discrete:

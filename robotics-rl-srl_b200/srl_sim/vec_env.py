@@ -21,10 +21,11 @@ import numpy as np
 from . import _abi, spaces
 from .backend import default_backend
 
-_KUKA_IDS = ("KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0", "KukaMovingButtonGymEnv-v0")
+_KUKA_IDS = ("KukaButtonGymEnv-v0", "KukaRandButtonGymEnv-v0", "KukaMovingButtonGymEnv-v0", "Kuka2ButtonGymEnv-v0")
 _OBS_DIM = {"MobileRobot1DGymEnv-v0": 1}
 _N_ACTIONS = {"MobileRobot1DGymEnv-v0": 2, "MobileRobotGymEnv-v0": 4, "MobileRobot2TargetGymEnv-v0": 4,
-              "MobileRobotLineTargetGymEnv-v0": 4, "KukaButtonGymEnv-v0": 6, "KukaRandButtonGymEnv-v0": 6, "KukaMovingButtonGymEnv-v0": 6}
+              "MobileRobotLineTargetGymEnv-v0": 4, "KukaButtonGymEnv-v0": 6, "KukaRandButtonGymEnv-v0": 6, "KukaMovingButtonGymEnv-v0": 6,
+              "Kuka2ButtonGymEnv-v0": 6}
 
 
 class BatchedSRLVecEnv(object):
@@ -60,7 +61,9 @@ class BatchedSRLVecEnv(object):
         if env_id in _KUKA_IDS:
             from .model import load_kuka_scene
             blob = load_kuka_scene().blob
-            cfg["max_distance"] = env_kwargs.get("max_distance", 0.8)
+            two = env_id == "Kuka2ButtonGymEnv-v0"     # its constructor defaults differ (kuka_2button_gym_env.py:30-31)
+            cfg["max_distance"] = env_kwargs.get("max_distance", 2.0 if two else 0.8)
+            cfg["force_down"] = env_kwargs.get("force_down", not two)
         for k in ("max_steps", "envs_per_warp", "solver_iterations"):
             if k in env_kwargs:
                 cfg[k] = env_kwargs[k]

@@ -40,7 +40,9 @@ class _World(object):
                            ("okb_reset_joint", [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]),
                            ("okb_ik", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
                            ("okb_step", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4),
-                           ("okb_get", [ctypes.c_void_p, ctypes.c_void_p])):
+                           ("okb_get", [ctypes.c_void_p, ctypes.c_void_p]), ("okb_get2", [ctypes.c_void_p, ctypes.c_void_p]),
+                           ("okb_set_ik_damping", [ctypes.c_void_p, ctypes.c_double]),
+                           ("okb_set_button2_base", [ctypes.c_void_p, ctypes.c_double, ctypes.c_double])):
             getattr(self.lib, name).argtypes = args
             getattr(self.lib, name).restype = None
         blob = self.scene.blob
@@ -58,6 +60,12 @@ class _World(object):
         self.motors = np.zeros((12, 5))
         self.motors[:, 1:] = [DEFAULT_KP, DEFAULT_KD, 0.0, 0.0]
         self.button = dict(position_control=0, target=0.0, kp=DEFAULT_KP, kd=DEFAULT_KD, force=DEFAULT_FORCE)
+        self.n_buttons = 0
+
+    def state2(self):
+        out = np.zeros(4)
+        self.lib.okb_get2(self.h, out.ctypes.data)
+        return out
 
     def new_uid(self, kind):
         uid = self.next_uid
@@ -113,6 +121,10 @@ def loadURDF(path, *args, **kwargs):
     name = os.path.basename(str(path))
     if name.startswith("simple_button"):
         pos = args[0] if args else kwargs.get("basePosition")
+        w.n_buttons += 1
+        if w.n_buttons == 2:                 # Kuka2ButtonGymEnv loads simple_button_2.urdf as a second body (:68)
+            w.lib.okb_set_button2_base(w.h, float(pos[0]), float(pos[1]))
+            return w.new_uid("button2")
         w.lib.okb_set_button_base(w.h, float(pos[0]), float(pos[1]))
         return w.new_uid("button")
     if name == "table.urdf":
@@ -157,7 +169,7 @@ def setJointMotorControl2(bodyUniqueId=None, jointIndex=None, controlMode=None, 
     if kind == "kuka":
         if jointIndex in w.body_of_joint:
             w.motors[w.body_of_joint[jointIndex]] = [targetPosition, positionGain, velocityGain, force, maxVelocity]
-    elif kind == "button":
+    elif kind in ("button", "button2"):      # the two-button env arms both with the same command (:137-138)
         assert jointIndex == 1
         w.button = dict(position_control=1, target=targetPosition, kp=positionGain, kd=velocityGain, force=force)
 
@@ -172,9 +184,22 @@ def getEulerFromQuaternion(q):
     return (0.0, 0.0, 0.0)
 
 
-def calculateInverseKinematics(uid, link, pos, orn=None, *a, **k):
+def calculateInverseKinematics(uid, link, pos, orn=None, lowerLimits=None, upperLimits=None, jointRanges=None, restPoses=None,
+                               jointDamping=None, **k):
+    """RECALLED pybullet 1.8.6 argument handling (pybullet.c): the null-space task needs all four lists with one entry per
+    JOINT of the body (14 here) -- the reference passes 7 (kuka.py:34-40), so it is dropped; `jointDamping` likewise needs 14
+    entries (kuka.py:42-43 has them), otherwise the server's default 0.5 per DoF applies."""
     w = _world()
     assert link == 6 and orn is not None and np.allclose(orn, getQuaternionFromEuler([0, -math.pi, 0]))
+    n_joints = getNumJoints(uid)
+    null_space = all(x is not None and len(x) == n_joints for x in (lowerLimits, upperLimits, jointRanges, restPoses))
+    assert not null_space, "null-space IK is not restated (the reference never enables it: 7-entry lists on a 14-joint body)"
+    if jointDamping is not None and len(jointDamping) == n_joints:
+        assert len(set(jointDamping)) == 1
+        damping = float(jointDamping[0])
+    else:
+        damping = 0.5
+    w.lib.okb_set_ik_damping(w.h, damping)
     target = np.asarray(pos, dtype=np.float64).copy()
     out = np.zeros(12)
     w.lib.okb_ik(w.h, target.ctypes.data, out.ctypes.data)
@@ -207,6 +232,8 @@ def getContactPoints(bodyA=None, bodyB=None, linkIndexA=None, *a, **k):
     ka, kb = w.uids.get(bodyA), w.uids.get(bodyB)
     if ka == "button" and kb == "kuka" and linkIndexA == 1:
         return [()] if s[31] else []
+    if ka in ("button", "button2") and kb == "kuka" and linkIndexA is None:      # any link of that button body
+        return [()] if w.state2()[0 if ka == "button" else 1] else []
     if ka == "table" and kb == "kuka":
         return [()] if s[32] else []
     return []

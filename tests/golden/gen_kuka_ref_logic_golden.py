@@ -27,6 +27,7 @@ import torch  # noqa: E402,F401  (the reference imports it)
 from environments.kuka_gym.kuka_button_gym_env import KukaButtonGymEnv  # noqa: E402
 from environments.kuka_gym.kuka_rand_button_gym_env import KukaRandButtonGymEnv  # noqa: E402
 from environments.kuka_gym.kuka_moving_button_gym_env import KukaMovingButtonGymEnv  # noqa: E402
+from environments.kuka_gym.kuka_2button_gym_env import Kuka2ButtonGymEnv  # noqa: E402
 
 assert "/root/reference" in sys.modules[KukaButtonGymEnv.__module__].__file__, "must import the reference classes"
 
@@ -43,9 +44,12 @@ CASES = [
     ("moving_cont_rand", "KukaMovingButtonGymEnv", dict(is_discrete=False, random_target=True), 8, 400),
     ("joints", "KukaButtonGymEnv", dict(is_discrete=False, action_joints=True), 9, 400),
     ("joints_shaped_none", "KukaButtonGymEnv", dict(is_discrete=False, action_joints=True, shape_reward=True), 10, 300),
+    ("two_disc", "Kuka2ButtonGymEnv", dict(is_discrete=True, force_down=True), 11, 900),
+    ("two_disc_rand_shaped", "Kuka2ButtonGymEnv", dict(is_discrete=True, random_target=True, shape_reward=True, force_down=True), 12, 900),
+    ("two_cont_up", "Kuka2ButtonGymEnv", dict(is_discrete=False), 13, 500),
 ]
 CLASSES = {"KukaButtonGymEnv": KukaButtonGymEnv, "KukaRandButtonGymEnv": KukaRandButtonGymEnv,
-           "KukaMovingButtonGymEnv": KukaMovingButtonGymEnv}
+           "KukaMovingButtonGymEnv": KukaMovingButtonGymEnv, "Kuka2ButtonGymEnv": Kuka2ButtonGymEnv}
 
 
 def make_actions(tag, kwargs, n, seed):
@@ -74,6 +78,7 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
     env.seed(seed)
     np.random.seed(1234)                         # the reference's KukaRandButton also draws from the GLOBAL numpy RNG
     actions = make_actions(tag, kwargs, nsteps, seed)
+    prs = np.random.RandomState(900 + seed)
     rec = dict(action=actions, obs=[], reward=[], done=[], arm=[], target=[], reset_obs=[], reset_target=[], reset_at=[])
     t = 0
     while t < nsteps:
@@ -82,6 +87,20 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
         rec["reset_at"].append(t)
         done = False
         while not done and t < nsteps:
+            if tag.startswith("two_") and prs.rand() < 0.85:
+                # two-button cases: a greedy controller on the observation (arm - goal) presses the buttons one after the
+                # other, so that goal switching / the second-button termination are exercised; the chosen action is recorded
+                ob = np.asarray(o, np.float64)
+                if kwargs.get("is_discrete", True):
+                    if max(abs(ob[0]), abs(ob[1])) < 0.02:
+                        actions[t, 0] = 4
+                    elif abs(ob[0]) > abs(ob[1]):
+                        actions[t, 0] = 0 if ob[0] > 0 else 1
+                    else:
+                        actions[t, 0] = 2 if ob[1] > 0 else 3
+                else:
+                    d = -ob / max(1e-9, np.abs(ob[:2]).max())
+                    actions[t] = np.clip([d[0], d[1], -1.0 if np.abs(ob[:2]).max() < 0.02 else 0.0], -1, 1).astype(np.float32)
             if kwargs.get("is_discrete", True):
                 a = None if actions[t, 0] < 0 else int(actions[t, 0])
             else:
@@ -89,6 +108,8 @@ def run_case(tag, clsname, kwargs, seed, nsteps):
             o, r, done, _ = env.step(a)
             rec["obs"].append(np.asarray(o, np.float64)); rec["reward"].append(float(r)); rec["done"].append(bool(done))
             rec["arm"].append(np.array(env.getArmPos(), dtype=np.float64, copy=True)); rec["target"].append(np.array(env.getTargetPos(), dtype=np.float64, copy=True))
+            if tag.startswith("two_"):
+                rec.setdefault("goal", []).append(int(env.goal_id)); rec.setdefault("ncontacts", []).append(list(env.n_contacts))
             t += 1
     return {k: np.asarray(v) for k, v in rec.items()}
 

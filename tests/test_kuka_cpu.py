@@ -287,6 +287,9 @@ REF_LOGIC_CASES = {
     "moving_cont_rand": ("KukaMovingButtonGymEnv-v0", dict(is_discrete=False, random_target=True), 8),
     "joints": ("KukaButtonGymEnv-v0", dict(is_discrete=False, action_joints=True), 9),
     "joints_shaped_none": ("KukaButtonGymEnv-v0", dict(is_discrete=False, action_joints=True, shape_reward=True), 10),
+    "two_disc": ("Kuka2ButtonGymEnv-v0", dict(is_discrete=True, force_down=True), 11),
+    "two_disc_rand_shaped": ("Kuka2ButtonGymEnv-v0", dict(is_discrete=True, random_target=True, shape_reward=True, force_down=True), 12),
+    "two_cont_up": ("Kuka2ButtonGymEnv-v0", dict(is_discrete=False), 13),
 }
 
 
@@ -321,6 +324,8 @@ def replay_ref_logic_case(tag, pos_tol):
             else:
                 assert isinstance(r, int) and r == reward[t], (tag, "reward", t, r, reward[t])
             assert d == bool(done[t]), (tag, "done", t)
+            if tag.startswith("two_"):   # Kuka2Button bookkeeping: which button is the goal, contacts counted per button
+                assert env.goal_id == g[tag + "/goal"][t] and list(env.n_contacts) == list(g[tag + "/ncontacts"][t]), (tag, "goal", t)
             t += 1
         ep += 1
     env.close()
