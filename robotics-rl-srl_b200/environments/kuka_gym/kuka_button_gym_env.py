@@ -69,7 +69,7 @@ class KukaButtonGymEnv(SRLGymEnv):
     :param shape_reward: (bool) Set to true, reward = -distance_to_goal
     :param action_joints: (bool) Set actions to apply to the joint space (7 set-points relative to the initial joint
         vector; needs is_discrete=False -- the reference's own reset() fails for the discrete combination)
-    :param record_data: (bool) not supported (EpisodeSaver image recording)
+    :param record_data: (bool) Set to true, record the states / actions / rewards with ``EpisodeSaver`` (frames by name only)
     :param random_target: (bool) Set the button position to a random position on the table
     :param force_down: (bool) Set Down as the only vertical action allowed
     :param state_dim: (int) When learning states
@@ -87,8 +87,6 @@ class KukaButtonGymEnv(SRLGymEnv):
                  save_path='srl_zoo/data/', env_rank=0, srl_pipe=None, srl_model="raw_pixels", device=None, **_):
         super(KukaButtonGymEnv, self).__init__(srl_model=srl_model, relative_pos=RELATIVE_POS, env_rank=env_rank,
                                                srl_pipe=srl_pipe)
-        if record_data:
-            raise NotImplementedError("record_data (EpisodeSaver image recording) is out of scope of the simulator")
         if action_joints and is_discrete:
             # the reference constructs this combination but its reset() dies with an IndexError (a 5-element discrete
             # action reaches Kuka.applyAction's 9-element joint branch, kuka.py:158-161); fail early and clearly instead
@@ -143,6 +141,11 @@ class KukaButtonGymEnv(SRLGymEnv):
             self.observation_space = spaces.Box(low=0, high=255, shape=(self._height, self._width, 3), dtype=np.uint8)
         else:
             self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.state_dim,), dtype=np.float32)
+
+        if record_data:   # (:124-126) states, actions, rewards, targets; frames by name only (no rasteriser)
+            from state_representation.episode_saver import EpisodeSaver
+            self.saver = EpisodeSaver(name, max_distance, state_dim, globals_=getGlobals(), relative_pos=RELATIVE_POS,
+                                      learn_states=learn_states, path=save_path)
 
         self._backend = default_backend(device)
         self._sim = self._backend.make_sim(self._ENV_ID, 1, seed=0, model_blob=load_kuka_scene().blob,
@@ -201,7 +204,7 @@ class KukaButtonGymEnv(SRLGymEnv):
         self._env_step_counter = int(self._sim.get_state(_abi.F_STEP_COUNTER)[0, 0])
 
     def _require_state_obs(self):
-        if self.srl_model == "raw_pixels":
+        if self.srl_model == "raw_pixels" and self.saver is None:   # a recording run never looks at the image observation
             raise NotImplementedError("image observations (raw_pixels) are out of scope of the batched simulator; "
                                       "use srl_model='ground_truth'")
 
@@ -240,7 +243,16 @@ class KukaButtonGymEnv(SRLGymEnv):
         draws = self._backend.from_host(np.asarray([self._reset_draws()], dtype=np.float64))
         self._sim.reset(mask=None, reset_draws=draws, obs_out=self._obs_buf, stream=self._backend.stream())
         self._pull_state()
-        return self.getSRLState(self._observation)
+        if self.saver is not None:   # (:275-276)
+            self.saver.reset(None, self.getTargetPos(), self.getGroundTruth())
+        return self._state_or_image()
+
+    def _state_or_image(self):
+        """What reset() / step() return (:278-281, :365-368): the SRL state, or -- raw_pixels -- the image, which only a
+        recording run (that ignores it) can get here: an empty placeholder."""
+        if self.srl_model != "raw_pixels":
+            return self.getSRLState(self._observation)
+        return np.array(self._observation)
 
     def getExtendedObservation(self):
         """Image observation of the reference (:287-291); not rendered by the simulator."""
@@ -272,7 +284,9 @@ class KukaButtonGymEnv(SRLGymEnv):
         done = bool(be.to_host(self._done_buf)[0])
         self._pull_state()
         reward = rew if self._shape_reward else int(rew)
-        return self.getSRLState(self._observation), reward, done, {}
+        if self.saver is not None:   # (:362-363)
+            self.saver.step(None, self.action, reward, done, self.getGroundTruth())
+        return self._state_or_image(), reward, done, {}
 
     def render(self, mode='human', close=False):
         if mode != "rgb_array":

@@ -50,7 +50,7 @@ class MobileRobotGymEnv(SRLGymEnv):
     :param max_distance: (float) unused by this env (kept for signature compatibility)
     :param shape_reward: (bool) Set to true, reward = -distance_to_goal
     :param srl_model: (str) SRL model ("ground_truth" is the supported observation mode)
-    :param record_data: (bool) not supported (EpisodeSaver is out of scope)
+    :param record_data: (bool) Set to true, record the states / actions / rewards with ``EpisodeSaver`` (frames by name only)
     :param random_target: (bool) Set the target to a random position
     :param state_dim: (int) When learning states
     :param env_rank: (int) the number ID of the environment
@@ -66,8 +66,6 @@ class MobileRobotGymEnv(SRLGymEnv):
                  fpv=False, device=None, **_):
         super(MobileRobotGymEnv, self).__init__(srl_model=srl_model, relative_pos=RELATIVE_POS, env_rank=env_rank,
                                                 srl_pipe=srl_pipe)
-        if record_data:
-            raise NotImplementedError("record_data (EpisodeSaver image recording) is out of scope of the simulator")
         self._timestep = 1. / 240.
         self._urdf_root = urdf_root
         self._observation = []
@@ -96,6 +94,11 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.collision_margin = 0.1
         self.fpv = fpv
         self.srl_model = srl_model
+
+        if record_data:   # (:109-111)
+            from state_representation.episode_saver import EpisodeSaver
+            self.saver = EpisodeSaver(name, max_distance, state_dim, globals_=getGlobals(), relative_pos=RELATIVE_POS,
+                                      learn_states=learn_states, path=save_path)
 
         self.action_space = self._make_action_space()
         if self.srl_model == "ground_truth":
@@ -152,7 +155,7 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.target_pos = self._sim.get_state(_abi.F_TARGET_POS)[0].copy()
 
     def _require_state_obs(self):
-        if self.srl_model == "raw_pixels":
+        if self.srl_model == "raw_pixels" and self.saver is None:   # a recording run never looks at the image observation
             raise NotImplementedError("image observations (raw_pixels) are out of scope of the batched simulator; "
                                       "use srl_model='ground_truth'")
 
@@ -164,7 +167,14 @@ class MobileRobotGymEnv(SRLGymEnv):
         self._env_step_counter = 0
         self.has_bumped = False
         self._pull_state()
-        return self.getSRLState(self._observation)
+        if self.saver is not None:   # (:216-217)
+            self.saver.reset(None, self.getTargetPos(), self.getGroundTruth())
+        return self._state_or_image()
+
+    def _state_or_image(self):
+        if self.srl_model != "raw_pixels":
+            return self.getSRLState(self._observation)
+        return np.array(self._observation)
 
     def getObservation(self):
         """Image observation of the reference (:228-233); not rendered by the simulator."""
@@ -191,7 +201,9 @@ class MobileRobotGymEnv(SRLGymEnv):
         self._pull_state()
         self.has_bumped = bool(self._sim.get_state(_abi.F_COUNTERS)[0, 1])
         reward = rew if self._shape_reward else int(rew)
-        return self.getSRLState(self._observation), reward, done, {}
+        if self.saver is not None:   # (:274-275)
+            self.saver.step(None, action, reward, done, self.getGroundTruth())
+        return self._state_or_image(), reward, done, {}
 
     def render(self, mode='human', close=False):
         if mode != "rgb_array":

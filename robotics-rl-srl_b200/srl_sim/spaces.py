@@ -15,7 +15,10 @@ class Space(object):
         self.np_random = np.random.RandomState()
 
     def seed(self, seed=None):
-        self.np_random.seed(seed)
+        # hash-based like gym's ``seeding.np_random`` (srl_sim/seeding.py): the reference seeds its action spaces with values up
+        # to 1e10 (environments/dataset_generator.py:82,169), which a raw ``RandomState.seed`` (32-bit) would reject
+        from . import seeding
+        self.np_random, seed = seeding.np_random(seed)
         return [seed]
 
     def sample(self):

@@ -143,3 +143,35 @@ def test_monitor_files_and_joint_states_on_oracle(use_oracle_backend, tmp_path):
         kenv.close()
     with pytest.raises(NotImplementedError):
         BatchedSRLVecEnv("MobileRobotGymEnv-v0", 2, srl_model="joints")
+
+
+def test_dataset_generator_and_episode_saver_on_oracle(use_oracle_backend, tmp_path):
+    """environments.dataset_generator + EpisodeSaver (reference dataset_generator.py:37-257, episode_saver.py:90-162): file
+    layout, array bookkeeping, and that the fused 3-partition dataset equals the single-partition one (same episode seeds)."""
+    import json
+    from environments import dataset_generator
+    base = str(tmp_path) + "/"
+    common = ["--env", "MobileRobotGymEnv-v0", "--num-episode", "5", "--save-path", base, "--seed", "3", "-r"]
+    n1 = dataset_generator.main(common + ["--name", "one", "--num-cpu", "1"])
+    n3 = dataset_generator.main(common + ["--name", "three", "--num-cpu", "3"])
+    assert n1 == n3 == 5 * 251
+    for name in ("one", "three"):
+        d = base + name
+        assert json.load(open(d + "/dataset_config.json")) == {"relative_pos": True, "max_dist": "0.28"}
+        assert "MAX_STEPS" in json.load(open(d + "/env_globals.json"))
+        assert sorted(os.listdir(d))[-5:] == ["record_%03d" % k for k in range(5)]
+        assert not [p for p in os.listdir(base) if "_part-" in p]
+    a_pre, b_pre = np.load(base + "one/preprocessed_data.npz"), np.load(base + "three/preprocessed_data.npz")
+    a_gt, b_gt = np.load(base + "one/ground_truth.npz"), np.load(base + "three/ground_truth.npz")
+    assert a_pre["rewards"].shape == a_pre["actions"].shape == a_pre["episode_starts"].shape == (5 * 251,)
+    assert a_pre["episode_starts"].sum() == 5 and a_gt["ground_truth_states"].shape == (5 * 251, 2) and a_gt["target_positions"].shape == (5, 2)
+    for k in a_pre.files:
+        assert np.array_equal(a_pre[k], b_pre[k]), k
+    for k in ("target_positions", "ground_truth_states"):
+        assert np.array_equal(a_gt[k], b_gt[k]), k
+    assert [p.replace("three/", "one/") for p in b_gt["images_path"]] == list(a_gt["images_path"])
+    assert a_gt["images_path"][251] == "one/record_001/frame000000"
+    # Kuka with record_data: the default raw_pixels model is accepted for a recording run
+    k = dataset_generator.main(["--env", "KukaButtonGymEnv-v0", "--num-episode", "1", "--save-path", base, "--name", "kuka", "--max-distance", "0.8"])
+    g = np.load(base + "kuka/ground_truth.npz")
+    assert k == len(g["ground_truth_states"]) and g["target_positions"].shape == (1, 3)
