@@ -293,7 +293,7 @@ REF_LOGIC_CASES = {
 }
 
 
-def replay_ref_logic_case(tag, pos_tol):
+def replay_ref_logic_case(tag, pos_tol, max_steps=None):
     """Replay one case recorded from the reference's own Kuka classes (running on the oracle's physics through
     tests/golden/fake_pybullet.py) through OUR env classes on whatever backend is installed."""
     from environments.registry import registered_env
@@ -304,7 +304,7 @@ def replay_ref_logic_case(tag, pos_tol):
     actions, obs, reward, done = g[tag + "/action"], g[tag + "/obs"], g[tag + "/reward"], g[tag + "/done"]
     arm, target = g[tag + "/arm"], g[tag + "/target"]
     reset_at = list(g[tag + "/reset_at"])
-    n, t, ep = len(reward), 0, 0
+    n, t, ep = len(reward) if max_steps is None else min(max_steps, len(reward)), 0, 0
     while t < n:
         assert reset_at[ep] == t, (tag, "episode boundaries differ", t)
         o = env.reset()
@@ -317,7 +317,7 @@ def replay_ref_logic_case(tag, pos_tol):
             else:
                 a = None if np.isnan(actions[t, 0]) else actions[t].astype(np.float32)
             o, r, d, _ = env.step(a)
-            assert np.abs(np.asarray(o) - obs[t]).max() < pos_tol, (tag, "obs", t)
+            assert np.abs(np.asarray(o) - obs[t]).max() < pos_tol, (tag, "obs", t, np.asarray(o), obs[t], r, reward[t], getattr(env, "goal_id", None), getattr(env, "n_contacts", None))
             assert np.abs(np.asarray(env.getArmPos()) - arm[t]).max() < pos_tol and np.abs(env.getTargetPos() - target[t]).max() < max(1e-6, pos_tol * 1e-2)
             if kwargs.get("shape_reward", False):
                 assert abs(r - reward[t]) < max(pos_tol, 1e-5), (tag, "reward", t, r, reward[t])
