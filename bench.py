@@ -118,6 +118,19 @@ def workload_spec(workload):
                 step_bytes=MOBILE_STEP_BYTES, cfg=dict(is_discrete=True, random_target=True))
 
 
+def metric_and_config(workload, world):
+    """`metric` / `config` of the JSON line -- shared by the b200 arm and the reference arm (the driver compares the two lines)."""
+    spec = workload_spec(workload)
+    n, T = spec["n"], spec["T"]
+    metric = "env-steps/sec %s ground_truth @%d envs/GPU" % (spec["env_id"], n)
+    config = {"workload": "%s ground_truth, %d envs/GPU, one bench step = one fused rollout of T=%d env steps (random discrete actions%s)"
+                          % (spec["env_id"], n, T, " + N(0,0.01) step noise" if workload == "kuka" else ""),
+              "envs_per_gpu": n, "env_steps_per_bench_step": n * T,
+              "l2_flush_between_steps": "write 256 MB + read 256 MB between timed steps, outside the event bracket",
+              "parallelism": "env-shard x%d" % world}
+    return metric, config
+
+
 def model_blob(workload):
     if workload != "kuka":
         return None
@@ -197,10 +210,15 @@ def run_reference(args):
     value = n * T * args.steps / total
     sample = ("%d envs x %d steps per step, %d host threads (container CPU quota; %d CPUs visible), CPU oracle "
               "(PyBullet itself is not installable offline)" % (n, T, pool.threads, os.cpu_count() or 1))
-    line = {"impl": "reference", "metric": "env-steps/sec %s ground_truth" % spec["env_id"], "value": value, "unit": "env-steps/s",
+    metric, config = metric_and_config(args.workload, 1)
+    config["parallelism"] = "%d host threads, one env shard each (rank 0 only)" % pool.threads
+    config.pop("l2_flush_between_steps")           # a CPU run: nothing to flush
+    if T != spec["T"]:
+        config["reference_sample"] = "bounded sample: %d of the %d env steps per bench step" % (T, spec["T"])
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s ground_truth, %d envs, T=%d env steps per bench step" % (spec["env_id"], n, T)},
+            "config": config,
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": pool.threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -319,13 +337,12 @@ def run_b200(args):
         roof["note"] = ("latency/issue-bound fp32 kernel (150 strictly sequential PGS sweeps per env-step), not HBM-bound: "
                         "%.2f TFLOP/s of useful fp32 work; see DESIGN.md 'Measurement'" % fl)
         roof["fp32_tflops"] = fl
-    line = {"metric": "env-steps/sec %s ground_truth @%d envs/GPU" % (spec["env_id"], n), "value": value, "unit": "env-steps/s",
+    metric, config = metric_and_config(args.workload, world)
+    line = {"metric": metric, "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.workload == "kuka" else "f64", "data": "synthetic",
-            "config": {"workload": "%s ground_truth, %d envs/GPU, one bench step = one fused rollout of T=%d env steps (random discrete actions%s)"
-                                   % (spec["env_id"], n, T, " + N(0,0.01) step noise" if args.workload == "kuka" else ""),
-                       "envs_per_gpu": n, "env_steps_per_bench_step": n * T, "l2_flush_between_steps": "write 256 MB + read 256 MB between timed steps, outside the event bracket", "parallelism": "env-shard x%d" % world},
+            "config": config,
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": units * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof,
