@@ -37,6 +37,16 @@
 #ifndef KK_SWEEP_FFMA2
 #define KK_SWEEP_FFMA2 0
 #endif
+// Residual form of the fast sweep: the 12 motor rows have unit Jacobians and constant targets, so the loop can carry
+// r_i = v_i - target_i instead of v_i; a row is then  s = clamp(lam_i - r_i / D_i - ...)  without the `lam_i + target_i / D_i` add
+// (12 FADD and 12 registers less per sweep).  KK_SWEEP_UNROLL: sweeps per loop iteration (2 lets ptxas rotate the lam registers
+// instead of copying them: 15 MOV less per sweep, twice the loop body).
+#ifndef KK_SWEEP_RESID
+#define KK_SWEEP_RESID 1
+#endif
+#ifndef KK_SWEEP_UNROLL
+#define KK_SWEEP_UNROLL 1
+#endif
 
 struct f3 { float x, y, z; };
 KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -852,7 +862,19 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         float tk[KK_NB], kk[KK_NB];
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) { tk[i] = tgt[i] * invd[i]; kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f; }
-#pragma unroll 1
+#if KK_SWEEP_RESID
+        float c_wt[KK_MAXC];     // contact watch thresholds against the RESIDUAL velocities: c_tgt - J . target
+        for (int c = 0; c < nc; ++c) {
+            float off = 0.f;
+#pragma unroll
+            for (int j = 0; j < KK_NB; ++j) off = fmaf(cJ[c][j], tgt[j], off);
+            c_wt[c] = c_tgt[c] - off;
+        }
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) v[i] -= tgt[i];
+#endif
+        constexpr int sweep_unroll = KK_SWEEP_UNROLL;
+#pragma unroll sweep_unroll
         for (int it = 0; it < P.iters; ++it) {
             {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
                 float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
@@ -866,7 +888,11 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             float dprev = 0.f;
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {
+#if KK_SWEEP_RESID
+                const float e = fmaf(-invd[i], v[i], lam[i]);                  // v[i] holds v_i - target_i
+#else
                 const float e = fmaf(-invd[i], v[i], lam[i] + tk[i]);          // off the critical path
+#endif
                 const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        // critical path
                 if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             // deferred update from row i-1
                 const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
@@ -885,12 +911,20 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                     float jv = 0.f;
 #pragma unroll
                     for (int j = 0; j < ND; ++j) jv = fmaf(cJ[c][j], v[j], jv);
+#if KK_SWEEP_RESID && !KK_SWEEP_FFMA2
+                    act = act | (c_wt[c] - jv > 0.f);
+#else
                     act = act | (c_tgt[c] - jv > 0.f);
+#endif
                 }
                 if (act) { it0 = it; resume_mid_sweep = true; break; }
             }
             it0 = it + 1;
         }
+#if KK_SWEEP_RESID && !KK_SWEEP_FFMA2
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) v[i] += tgt[i];
+#endif
 #if KK_SWEEP_FFMA2
         KK_SYNC_V();
 #endif

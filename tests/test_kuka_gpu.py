@@ -309,7 +309,8 @@ def _parity_until_first_flag_shift(c, o, max_shifted_envs):
     """fp32 vs fp64 can move a contact ONSET by one step when the sphere-shape distance lands within float32 rounding
     (~3e-6 m, against ~1.2 mm of approach per step) of the 0.02 m manifold margin.  After such a shift the episode ends one
     step earlier/later and the env legitimately sees different actions, so each env is compared up to its first flag
-    difference, which must be exactly such a one-step shift; only a few envs may have one."""
+    difference, which must be exactly such a one-step shift (of a button contact, reward 1, or of a table contact, reward -1 and done);
+    only a few envs may have one."""
     T, n = o["rew"].shape
     shifted = 0
     for i in range(n):
@@ -319,10 +320,14 @@ def _parity_until_first_flag_shift(c, o, max_shifted_envs):
         if len(bad):
             shifted += 1
             t = t_end
-            assert {float(c["rew"][t, i]), float(o["rew"][t, i])} == {0.0, 1.0}          # a contact flag, on one side only ...
-            early, late = (c, o) if c["rew"][t, i] == 1.0 else (o, c)
-            assert late["rew"][t + 1, i] == 1.0 and early["rew"][t + 1, i] == 1.0          # ... that the other side raises one step later
-            assert np.abs(c["obs"][t, i] - o["obs"][t, i]).max() < POS_TOL
+            rc, ro = float(c["rew"][t, i]), float(o["rew"][t, i])
+            flag = -1.0 if -1.0 in (rc, ro) else 1.0          # table contact (-1, ends the episode) or button contact (1): same 0.02 m margin test
+            assert {rc, ro} - {flag} <= {0.0, 1.0} and rc != ro                            # a contact flag, on one side only ...
+            early, late = (c, o) if rc == flag else (o, c)
+            assert late["rew"][t + 1, i] == flag                                           # ... that the other side raises one step later
+            if flag == 1.0:                                                                # (a table contact ends the episode: the early side is already past its reset)
+                assert early["rew"][t + 1, i] == 1.0
+                assert np.abs(c["obs"][t, i] - o["obs"][t, i]).max() < POS_TOL
     assert shifted <= max_shifted_envs, shifted
     return shifted
 
