@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <initializer_list>
+#include <type_traits>
+#include <cuda_pipeline_primitives.h>
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -174,6 +176,9 @@ constexpr double S_THR_04 = 0x1.47ae147ae147cp-3;
 //  * pass 2 turns those into distance, reward, observation and the HBM stores; its steps are independent;
 //  * nothing per-step is spent on episode bookkeeping: the step counter, `done`, the episode length follow from t, and
 //    the unshaped episode return is an integer sum (rewards are -1 / 0 / 1: the float64 accumulation is exact either way).
+#ifndef MOBILE_RING
+#define MOBILE_RING 4               // chunks of actions in the shared-memory ring (MOBILE_RING - 1 in flight ahead of the one being stepped)
+#endif
 #ifndef MOBILE_PF
 #define MOBILE_PF 8                 // steps per chunk (measured on B200, 8192 envs x 1024 steps: 2 -> 96 us, 4 -> 67 us, 8 -> 54-58 us)
 #endif
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     SegmentAcc acc; acc.ret_i = 0; acc.ret_d = e.ep_ret;
     int t0 = t_start;
     size_t idx = (size_t)t_start * N + (size_t)i;          // element index of (t0, env i) in the [T, N] streams
+    const size_t idx0 = idx;
     const size_t chunk_stride = (size_t)PF * N;
     // The steps after the last full plain chunk -- at most PF - 1 plain ones and the step that ends the episode -- run as ONE
     // masked chunk; its actions are requested now, so their latency hides behind the whole main loop.
@@ -376,21 +382,51 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     int tail_valid = t_end - t_tail < PF ? t_end - t_tail : PF;
     if (!GEN) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(tl, actions, noise, N, idx + (size_t)n_full * chunk_stride, seed, genv, 0u, tail_valid);
     if (n_full > 0) {
-        // register ring of three chunks: the loads of chunk c + 2 are issued before chunk c is stepped.  One chunk ahead was
-        // not enough (ncu: 23 % of all stall samples sat on the `cur = nxt` copy waiting for the load -- with ~9 warps per SM
-        // writing 1.4 GB/ms the loaded memory latency exceeds one chunk's ~2000 cycles).
-        ActionChunk<DISCRETE, !FAST, PF> c0, c1, c2;
-        load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start);
-        if (!GEN && n_full > 1) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c1, actions, noise, N, idx + chunk_stride, seed, genv, 0u);
+        ActionChunk<DISCRETE, !FAST, PF> c0;
+        if (GEN) {
 #pragma unroll 1
-        for (; t0 < t_tail; t0 += PF, idx += chunk_stride) {
-            if (GEN) {
-                if (t0 != t_start) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start));
-            } else if (t0 + 3 * PF <= t_tail) {
-                load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c2, actions, noise, N, idx + 2 * chunk_stride, seed, genv, 0u);   // in flight for two chunks
+            for (; t0 < t_tail; t0 += PF, idx += chunk_stride) {
+                load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start));
+                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
             }
-            step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
-            if (!GEN) { c0 = c1; c1 = c2; }
+        } else {
+            // ACTION RING in shared memory, filled by cp.async (LDGSTS) MOBILE_RING - 1 chunks ahead of the chunk being stepped.
+            // Registers cannot carry loads that far: rotating a register ring copies values that are still in flight, and the copy
+            // waits for them (ncu: one instruction, the first use of a chunk's first action, held 31 % of all stall samples as
+            // `long_sb` with a 3-deep register ring, 23 % with a 2-deep one).  cp.async needs no destination register, each thread
+            // reads back only what it wrote itself (no barrier, only wait_group), and slot (stage, step) of the 32 lanes of a warp
+            // is one 128-byte row: conflict-free.
+            using Elem = typename std::conditional<DISCRETE, int32_t, float2>::type;
+            extern __shared__ __align__(16) unsigned char s_ring_raw[];
+            Elem* ring = reinterpret_cast<Elem*>(s_ring_raw);
+            const Elem* src = reinterpret_cast<const Elem*>(actions);
+            const int tid = threadIdx.x, nthr = blockDim.x;
+            auto issue = [&](int chunk) {       // chunk index within this segment; an empty group keeps the group count uniform
+                if (chunk < n_full) {
+                    size_t g = idx0 + (size_t)chunk * chunk_stride;
+                    Elem* dst = ring + (size_t)((chunk % MOBILE_RING) * PF) * nthr + tid;
+#pragma unroll
+                    for (int k = 0; k < PF; ++k) { __pipeline_memcpy_async(dst + (size_t)k * nthr, src + g, sizeof(Elem)); g += N; }
+                }
+                __pipeline_commit();
+            };
+#pragma unroll
+            for (int c = 0; c < MOBILE_RING - 1; ++c) issue(c);
+            int chunk = 0;
+#pragma unroll 1
+            for (; t0 < t_tail; t0 += PF, idx += chunk_stride, ++chunk) {
+                issue(chunk + MOBILE_RING - 1);
+                __pipeline_wait_prior(MOBILE_RING - 1);                   // everything up to and including `chunk` has landed
+                const Elem* slot = ring + (size_t)((chunk % MOBILE_RING) * PF) * nthr + tid;
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    if constexpr (DISCRETE) c0.a[k] = slot[(size_t)k * nthr];
+                    else { const float2 v = slot[(size_t)k * nthr]; c0.x[DISCRETE ? 0 : k] = v.x; c0.y[DISCRETE ? 0 : k] = v.y; }
+                    if (!FAST) c0.nz[FAST ? 0 : k] = noise ? __ldg(noise + idx + (size_t)k * N) : 0.f;
+                }
+                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+            }
+            __pipeline_wait_prior(0);
         }
     }
 #pragma unroll 1
@@ -423,7 +459,8 @@ int launch_rollout_variant(srl_sim* s, int T, const void* actions, const float* 
     int block = warps <= 148 * 4 ? 32 : 128;
     if (s->mobile_block > 0) block = s->mobile_block;
     const dim3 grid((unsigned)((s->n + block - 1) / block), (unsigned)nseg);
-    mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED, FAST><<<grid, block, 0, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
+    const size_t ring_bytes = GEN ? 0 : (size_t)MOBILE_RING * MOBILE_PF * block * (DISCRETE ? sizeof(int32_t) : sizeof(float2));
+    mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED, FAST><<<grid, block, ring_bytes, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
                                                                                        s->cfg.random_target != 0, s->auto_reset != 0,
                                                                                        s->max_steps, s->seed, s->cfg.global_env_offset);
     SRL_CUDA_OK(cudaGetLastError());
