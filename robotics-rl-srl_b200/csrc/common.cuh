@@ -28,6 +28,8 @@ struct MobileDev {
 
 struct KukaDev;  // kuka.cuh
 
+#define SRL_HOST_MAX_CHUNKS 16
+
 struct srl_sim {
     int kind;
     int n;
@@ -46,6 +48,11 @@ struct srl_sim {
     // device staging buffers for the *_host entry points (grown on demand)
     void* stage[5];
     size_t stage_cap[5];
+    // srl_sim_rollout_host pipeline: copy-in / kernel / copy-out streams and one (inputs landed, outputs ready) event pair per T-chunk
+    cudaStream_t host_st[3];
+    cudaEvent_t host_ev[2 * SRL_HOST_MAX_CHUNKS];
+    bool host_pipe_ready;
+    int host_chunks;    // SRL_HOST_CHUNKS override (0 = by bytes moved)
 };
 
 static inline bool srl_is_mobile(int kind) { return kind >= SRL_ENV_MOBILE && kind <= SRL_ENV_MOBILE_LINE_TARGET; }

@@ -3,6 +3,7 @@
 // pointers except in srl_sim_rollout_host.  There is no CPU path in this library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "common.cuh"
@@ -38,6 +39,19 @@ int ensure_stage(srl_sim* s, int slot, size_t bytes) {
     s->stage_cap[slot] = 0;
     SRL_CUDA_OK(cudaMalloc(&s->stage[slot], bytes));
     s->stage_cap[slot] = bytes;
+    return 0;
+}
+
+// Streams of the srl_sim_rollout_host pipeline.  They are ordinary (blocking) streams: each one orders itself after work already
+// queued on the legacy default stream -- where a preceding reset() / step() of a host-side caller runs -- and they do not
+// serialise against each other.
+int ensure_host_pipe(srl_sim* s) {
+    if (s->host_pipe_ready) return 0;
+    for (int k = 0; k < 3; ++k) SRL_CUDA_OK(cudaStreamCreate(&s->host_st[k]));
+    for (int k = 0; k < 2 * SRL_HOST_MAX_CHUNKS; ++k) SRL_CUDA_OK(cudaEventCreateWithFlags(&s->host_ev[k], cudaEventDisableTiming));
+    const char* env = getenv("SRL_HOST_CHUNKS");
+    s->host_chunks = env ? atoi(env) : 0;
+    s->host_pipe_ready = true;
     return 0;
 }
 
@@ -121,6 +135,8 @@ void srl_sim_destroy(srl_sim* s) {
     cudaDeviceSynchronize();
     if (srl_is_mobile(s->kind)) mobile_free(s); else kuka_free(s);
     for (int k = 0; k < 5; ++k) if (s->stage[k]) cudaFree(s->stage[k]);
+    for (int k = 0; k < 3; ++k) if (s->host_st[k]) cudaStreamDestroy(s->host_st[k]);
+    for (int k = 0; k < 2 * SRL_HOST_MAX_CHUNKS; ++k) if (s->host_ev[k]) cudaEventDestroy(s->host_ev[k]);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -178,22 +194,48 @@ int srl_sim_rollout_host(srl_sim* s, int T, const void* actions, const float* no
     DeviceGuard guard(s->device);
     const size_t N = (size_t)s->n, TN = (size_t)T * N;
     const size_t D = (size_t)srl_sim_obs_dim(s), A = (size_t)srl_sim_action_dim(s);
-    const size_t act_bytes = TN * A * 4, noise_bytes = TN * 4, obs_bytes = TN * D * 4, rew_bytes = TN * 4, done_bytes = TN;
-    cudaStream_t st = 0;
-    void *d_act = nullptr, *d_noise = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_done = nullptr;
-    if (actions) { if (ensure_stage(s, 0, act_bytes)) return 1; d_act = s->stage[0];
-                   SRL_CUDA_OK(cudaMemcpyAsync(d_act, actions, act_bytes, cudaMemcpyHostToDevice, st)); }
-    if (noise) { if (ensure_stage(s, 1, noise_bytes)) return 1; d_noise = s->stage[1];
-                 SRL_CUDA_OK(cudaMemcpyAsync(d_noise, noise, noise_bytes, cudaMemcpyHostToDevice, st)); }
-    if (obs_out) { if (ensure_stage(s, 2, obs_bytes)) return 1; d_obs = s->stage[2]; }
-    if (rew_out) { if (ensure_stage(s, 3, rew_bytes)) return 1; d_rew = s->stage[3]; }
-    if (done_out) { if (ensure_stage(s, 4, done_bytes)) return 1; d_done = s->stage[4]; }
-    int rc = launch_rollout(s, T, d_act, (const float*)d_noise, (float*)d_obs, (float*)d_rew, (uint8_t*)d_done, nullptr, nullptr, st);
-    if (rc) return rc;
-    if (obs_out) SRL_CUDA_OK(cudaMemcpyAsync(obs_out, d_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
-    if (rew_out) SRL_CUDA_OK(cudaMemcpyAsync(rew_out, d_rew, rew_bytes, cudaMemcpyDeviceToHost, st));
-    if (done_out) SRL_CUDA_OK(cudaMemcpyAsync(done_out, d_done, done_bytes, cudaMemcpyDeviceToHost, st));
-    SRL_CUDA_OK(cudaStreamSynchronize(st));
+    const size_t act_step = N * A * 4, noise_step = N * 4, obs_step = N * D * 4, rew_step = N * 4, done_step = N;   // bytes per env step
+    if (ensure_host_pipe(s)) return 1;
+    char *d_act = nullptr, *d_noise = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_done = nullptr;
+    if (actions) { if (ensure_stage(s, 0, T * act_step)) return 1; d_act = (char*)s->stage[0]; }
+    if (noise) { if (ensure_stage(s, 1, T * noise_step)) return 1; d_noise = (char*)s->stage[1]; }
+    if (obs_out) { if (ensure_stage(s, 2, T * obs_step)) return 1; d_obs = (char*)s->stage[2]; }
+    if (rew_out) { if (ensure_stage(s, 3, T * rew_step)) return 1; d_rew = (char*)s->stage[3]; }
+    if (done_out) { if (ensure_stage(s, 4, TN)) return 1; d_done = (char*)s->stage[4]; }
+    // The [T, N] streams are time-major, so a range of steps is a contiguous slice of every buffer: the rollout runs as a few
+    // T-chunks, chunk c's kernel overlapping the copy-in of chunk c + 1 and the copy-out of chunk c - 1 (PCIe is full duplex).
+    // Results do not depend on the chunking (a rollout of T steps == consecutive shorter rollouts; tests/test_*_gpu.py).
+    const size_t moved = (actions ? T * act_step : 0) + (noise ? T * noise_step : 0) + (obs_out ? T * obs_step : 0) +
+                         (rew_out ? T * rew_step : 0) + (done_out ? TN : 0);
+    int chunks = s->host_chunks > 0 ? s->host_chunks : (int)(moved / ((size_t)8 << 20));
+    if (chunks < 1) chunks = 1;
+    if (chunks > SRL_HOST_MAX_CHUNKS) chunks = SRL_HOST_MAX_CHUNKS;
+    if (chunks > T) chunks = T;
+    const int chunk_T = (T + chunks - 1) / chunks;
+    cudaStream_t st_in = s->host_st[0], st_run = s->host_st[1], st_out = s->host_st[2];
+    int c = 0;
+    for (int t0 = 0; t0 < T; t0 += chunk_T, ++c) {
+        const size_t tc = (size_t)(T - t0 < chunk_T ? T - t0 : chunk_T);
+        if (actions) SRL_CUDA_OK(cudaMemcpyAsync(d_act + t0 * act_step, (const char*)actions + t0 * act_step, tc * act_step, cudaMemcpyHostToDevice, st_in));
+        if (noise) SRL_CUDA_OK(cudaMemcpyAsync(d_noise + t0 * noise_step, (const char*)noise + t0 * noise_step, tc * noise_step, cudaMemcpyHostToDevice, st_in));
+        SRL_CUDA_OK(cudaEventRecord(s->host_ev[2 * c], st_in));
+    }
+    c = 0;
+    for (int t0 = 0; t0 < T; t0 += chunk_T, ++c) {
+        const int tc = T - t0 < chunk_T ? T - t0 : chunk_T;
+        SRL_CUDA_OK(cudaStreamWaitEvent(st_run, s->host_ev[2 * c], 0));
+        int rc = launch_rollout(s, tc, d_act ? d_act + t0 * act_step : nullptr, d_noise ? (const float*)(d_noise + t0 * noise_step) : nullptr,
+                                d_obs ? (float*)(d_obs + t0 * obs_step) : nullptr, d_rew ? (float*)(d_rew + t0 * rew_step) : nullptr,
+                                d_done ? (uint8_t*)(d_done + t0 * done_step) : nullptr, nullptr, nullptr, st_run);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        SRL_CUDA_OK(cudaEventRecord(s->host_ev[2 * c + 1], st_run));
+        SRL_CUDA_OK(cudaStreamWaitEvent(st_out, s->host_ev[2 * c + 1], 0));
+        if (obs_out) SRL_CUDA_OK(cudaMemcpyAsync((char*)obs_out + t0 * obs_step, d_obs + t0 * obs_step, tc * obs_step, cudaMemcpyDeviceToHost, st_out));
+        if (rew_out) SRL_CUDA_OK(cudaMemcpyAsync((char*)rew_out + t0 * rew_step, d_rew + t0 * rew_step, tc * rew_step, cudaMemcpyDeviceToHost, st_out));
+        if (done_out) SRL_CUDA_OK(cudaMemcpyAsync((char*)done_out + t0 * done_step, d_done + t0 * done_step, tc * done_step, cudaMemcpyDeviceToHost, st_out));
+    }
+    SRL_CUDA_OK(cudaStreamSynchronize(st_run));   // the state update is complete even when no output was requested
+    SRL_CUDA_OK(cudaStreamSynchronize(st_out));
     return 0;
 }
 
