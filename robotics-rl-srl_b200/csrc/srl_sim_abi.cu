@@ -207,7 +207,10 @@ int srl_sim_rollout_host(srl_sim* s, int T, const void* actions, const float* no
     // Results do not depend on the chunking (a rollout of T steps == consecutive shorter rollouts; tests/test_*_gpu.py).
     const size_t moved = (actions ? T * act_step : 0) + (noise ? T * noise_step : 0) + (obs_out ? T * obs_step : 0) +
                          (rew_out ? T * rew_step : 0) + (done_out ? TN : 0);
-    int chunks = s->host_chunks > 0 ? s->host_chunks : (int)(moved / ((size_t)8 << 20));
+    // Chunk count by bytes moved, one chunk per 32 MB (measured on B200, profiles/r01_e2e_chunks.txt: the 143 MB MobileRobot rollout runs
+    // 16 % faster in 4 chunks than in 1 and no better in 16; the 13 MB Kuka rollout is fastest unsplit -- every extra launch of its long
+    // kernel pays a tail of warps finishing at different times)
+    int chunks = s->host_chunks > 0 ? s->host_chunks : (int)(moved / ((size_t)32 << 20));
     if (chunks < 1) chunks = 1;
     if (chunks > SRL_HOST_MAX_CHUNKS) chunks = SRL_HOST_MAX_CHUNKS;
     if (chunks > T) chunks = T;

@@ -258,7 +258,14 @@ def test_full_size_properties_4096_envs(cuda_backend):
     assert np.abs(r["qd"][:, :7]).max() < 2.0
 
 
-def test_rollout_host_matches_device_rollout(cuda_backend):
+@pytest.mark.parametrize("host_chunks", [0, 3, 7])
+def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypatch):
+    """srl_sim_rollout_host pipelines the rollout in T-chunks (copy-in / kernel / copy-out streams); the chunking
+    (here forced through SRL_HOST_CHUNKS, read when the handle first uses the host path) must not change a bit."""
+    if host_chunks:
+        monkeypatch.setenv("SRL_HOST_CHUNKS", str(host_chunks))
+    else:
+        monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)
     n, T = 256, 64
     rs = np.random.RandomState(8)
     acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
@@ -268,9 +275,11 @@ def test_rollout_host_matches_device_rollout(cuda_backend):
     import torch
     torch.cuda.synchronize()
     obs = np.zeros((T, n, 3), np.float32); rew = np.zeros((T, n), np.float32); done = np.zeros((T, n), np.uint8)
+    launches0 = sim.launch_count
     sim.rollout_host(T, acts, noise, obs, rew, done)
     assert np.array_equal(obs, dev["obs"]) and np.array_equal(rew, dev["rew"]) and np.array_equal(done, dev["done"])
     assert sim.last_kernel_ms() > 0
+    assert sim.launch_count - launches0 == max(1, host_chunks)   # one launch per T-chunk
 
 
 def test_single_env_classes_on_cuda(cuda_lib):

@@ -126,7 +126,14 @@ def test_cuda_full_size_properties_and_sharding(cuda_backend):
         assert np.array_equal(whole[k], np.concatenate([lo[k], hi[k]], axis=-2 if k == "obs" else (1 if whole[k].ndim == 2 and k != "pos" else 0))), k
 
 
-def test_rollout_host_matches_device_rollout(cuda_backend):
+@pytest.mark.parametrize("host_chunks", [0, 3, 7])
+def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypatch):
+    """srl_sim_rollout_host pipelines the rollout in T-chunks (copy-in / kernel / copy-out streams); the chunking
+    (here forced through SRL_HOST_CHUNKS, read when the handle first uses the host path) must not change a bit."""
+    if host_chunks:
+        monkeypatch.setenv("SRL_HOST_CHUNKS", str(host_chunks))
+    else:
+        monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)
     kind, n, T = KINDS[0], 512, 300
     acts = np.random.RandomState(8).randint(0, 4, size=(T, n)).astype(np.int32)
     dev = _run(cuda_backend, kind, n, T, acts, seed=6)
@@ -135,9 +142,11 @@ def test_rollout_host_matches_device_rollout(cuda_backend):
     import torch
     torch.cuda.synchronize()
     obs = np.zeros((T, n, 2), np.float32); rew = np.zeros((T, n), np.float32); done = np.zeros((T, n), np.uint8)
+    launches0 = sim.launch_count
     sim.rollout_host(T, acts, None, obs, rew, done)
     assert np.array_equal(obs, dev["obs"]) and np.array_equal(rew, dev["rew"]) and np.array_equal(done, dev["done"])
     assert sim.last_kernel_ms() > 0
+    assert sim.launch_count - launches0 == max(1, host_chunks)   # one launch per T-chunk
 
 
 @pytest.mark.parametrize("kind", KINDS)
