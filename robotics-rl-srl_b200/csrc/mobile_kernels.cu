@@ -179,6 +179,9 @@ constexpr double S_THR_04 = 0x1.47ae147ae147cp-3;
 #ifndef MOBILE_RING
 #define MOBILE_RING 4               // chunks of actions in the shared-memory ring (MOBILE_RING - 1 in flight ahead of the one being stepped)
 #endif
+#ifndef MOBILE_TABLE_DECODE
+#define MOBILE_TABLE_DECODE 1       // discrete action -> (dx, dy) through a 4-entry shared-memory table (one LDS.128) instead of 8 integer instructions
+#endif
 #ifndef MOBILE_PF
 #define MOBILE_PF 8                 // steps per chunk (measured on B200, 8192 envs x 1024 steps: 2 -> 96 us, 4 -> 67 us, 8 -> 54-58 us)
 #endif
@@ -231,7 +234,7 @@ template <int KIND, bool DISCRETE, bool SHAPED, bool FAST, bool MAYDONE, int NS>
 __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, const ActionChunk<DISCRETE, !FAST, NS>& cur,
                                            int t0, int t_done, int t_start, size_t N, size_t idx0, double ep_ret0, double ep_len0,
                                            float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
-                                           float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int nvalid = NS) {
+                                           float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, const double2* delta_table, int nvalid = NS) {
     constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
     constexpr double mx = COLLISION_MARGIN + ROBOT_LENGTH / 2, my = COLLISION_MARGIN + ROBOT_WIDTH / 2;  // :257-258
     // ---------------- pass 1: the serial state chain (mobile_robot_env.py:237-268) ----------------
@@ -250,12 +253,18 @@ __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, co
             // dx = [-dv, dv, 0, 0][a], dy = [0, 0, -dv, dv][a] (:242-243; 1D_env.py:115), branch-free: even actions flip the
             // sign bit, the axis that does not move gets +0.0
             const int a = cur.a[DISCRETE ? k : 0];
+            if (MOBILE_TABLE_DECODE && FAST && KIND != SRL_ENV_MOBILE_1D) {
+                // the four (dx, dy) pairs of the constant dv = DELTA_POS; `a & 3` is Python's list index for a in [-4, 3]
+                const double2 d = delta_table[a & 3];
+                ax = d.x; ay = d.y;
+            } else {
             const int hi = __double2hiint(dv) ^ ((a & 1) ? 0 : (int)0x80000000u), lo = __double2loint(dv);
             if (KIND == SRL_ENV_MOBILE_1D) ax = __hiloint2double(hi, lo);
             else {
                 const bool along_x = (a & 2) == 0;
                 ax = __hiloint2double(along_x ? hi : 0, along_x ? lo : 0);
                 ay = __hiloint2double(along_x ? 0 : hi, along_x ? 0 : lo);
+            }
             }
         } else {
             // float32 action array * python float -> float32 product, then += into float64 (:250,255)
@@ -289,10 +298,17 @@ __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, co
     }
     e.has_bumped = (bump_mask >> ((MAYDONE ? nvalid : NS) - 1)) & 1u;
     // ---------------- pass 2: rewards and outputs, independent across the chunk (:345-363) ----------------
-    size_t idx = idx0;
+    // Addresses: one 64-bit base per output stream and chunk, plus the 32-bit element offsets k * N (loop-invariant, hoisted): a store
+    // address is then a single IMAD.WIDE.U32 instead of a carried 64-bit add (two instructions) per stream and step.
+    float chunk_ret = 0.f;
+    const uint32_t n32 = (uint32_t)N;                   // the launcher guarantees (NS - 1) * N < 2^32
+    float* const rew_c = rew + idx0; uint8_t* const done_c = done + idx0;
+    float* const obs1_c = obs + idx0; float2* const obs2_c = reinterpret_cast<float2*>(obs) + idx0;
+    float* const ep_ret_c = ep_ret + idx0; int32_t* const ep_len_c = ep_len + idx0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         if (MAYDONE && k >= nvalid) break;
+        const uint32_t idx = (uint32_t)k * n32;
         const bool bumped = (bump_mask >> k) & 1u;
         float reward_f;
         if (SHAPED) {
@@ -308,26 +324,27 @@ __device__ __forceinline__ void step_chunk(MobileEnvRegs& e, SegmentAcc& acc, co
             else if (TWO) reached = (reach_mask >> k) & 1u;
             else if (KIND == SRL_ENV_MOBILE_1D) reached = __dmul_rn(odx[k], odx[k]) <= S_THR_04;
             else reached = __dadd_rn(__dmul_rn(odx[k], odx[k]), __dmul_rn(ody[k], ody[k])) <= S_THR_04;
-            acc.ret_i += bumped ? -1 : (reached ? 1 : 0);
             reward_f = bumped ? -1.f : (reached ? 1.f : 0.f);
+            chunk_ret += reward_f;              // a sum of at most NS values from {-1, 0, 1}: exact in float32
+            if (MAYDONE) { acc.ret_i += (int)chunk_ret; chunk_ret = 0.f; }   // the tail chunk reads the running return at its done step
         }
-        if (FAST || rew) rew[idx] = reward_f;
+        if (FAST || rew) rew_c[idx] = reward_f;
         if (MAYDONE) {
             const int t = t0 + k;
             const bool is_done = t >= t_done;   // _termination (:336-343); `terminated` is never set
-            if (FAST || done) done[idx] = is_done ? 1 : 0;
+            if (FAST || done) done_c[idx] = is_done ? 1 : 0;
             if (is_done) {   // Monitor-style episode statistics (environments/utils.py:53-54)
-                if (ep_ret) ep_ret[idx] = (float)(SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i));
-                if (ep_len) ep_len[idx] = (int32_t)ep_len0 + (t - t_start + 1);
+                if (ep_ret) ep_ret_c[idx] = (float)(SHAPED ? acc.ret_d : __dadd_rn(ep_ret0, (double)acc.ret_i));
+                if (ep_len) ep_len_c[idx] = (int32_t)ep_len0 + (t - t_start + 1);
             }
-        } else if (FAST || done) done[idx] = 0;
+        } else if (FAST || done) done_c[idx] = 0;
         if (FAST || obs) {
-            if (KIND == SRL_ENV_MOBILE_1D) obs[idx] = (float)odx[k];
-            else if (TWO) reinterpret_cast<float2*>(obs)[idx] = make_float2(ox[TWO ? k : 0], oy[TWO ? k : 0]);
-            else reinterpret_cast<float2*>(obs)[idx] = make_float2((float)odx[k], (float)ody[k]);
+            if (KIND == SRL_ENV_MOBILE_1D) obs1_c[idx] = (float)odx[k];
+            else if (TWO) obs2_c[idx] = make_float2(ox[TWO ? k : 0], oy[TWO ? k : 0]);
+            else obs2_c[idx] = make_float2((float)odx[k], (float)ody[k]);
         }
-        idx += N;
     }
+    if (!SHAPED && !MAYDONE) acc.ret_i += (int)chunk_ret;
 }
 
 template <int KIND, bool DISCRETE, bool GEN, bool SHAPED, bool FAST>
@@ -337,6 +354,13 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
                                                              float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
                                                              bool random_target, bool auto_reset,
                                                              int max_steps, uint64_t seed, uint64_t env_offset) {
+    // dx = [-dv, dv, 0, 0][a], dy = [0, 0, -dv, dv][a] (mobile_robot_env.py:242-243) for the constant dv of the FAST instantiation
+    __shared__ double2 s_delta[4];
+    if (MOBILE_TABLE_DECODE && FAST && DISCRETE && KIND != SRL_ENV_MOBILE_1D) {
+        if (threadIdx.x < 4) s_delta[threadIdx.x] = threadIdx.x < 2 ? make_double2(threadIdx.x ? DELTA_POS : -DELTA_POS, 0.0)
+                                                                     : make_double2(0.0, threadIdx.x == 3 ? DELTA_POS : -DELTA_POS);
+        __syncthreads();   // before any thread leaves
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr bool TWO = (KIND == SRL_ENV_MOBILE_2TARGET);
@@ -387,7 +411,7 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
 #pragma unroll 1
             for (; t0 < t_tail; t0 += PF, idx += chunk_stride) {
                 load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(c0, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start));
-                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len, s_delta);
             }
         } else {
             // ACTION RING in shared memory, filled by cp.async (LDGSTS) MOBILE_RING - 1 chunks ahead of the chunk being stepped.
@@ -400,13 +424,14 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
             extern __shared__ __align__(16) unsigned char s_ring_raw[];
             Elem* ring = reinterpret_cast<Elem*>(s_ring_raw);
             const Elem* src = reinterpret_cast<const Elem*>(actions);
-            const int tid = threadIdx.x, nthr = blockDim.x;
+            const int tid = threadIdx.x;
+            constexpr int nthr = 128;     // ring row stride = the largest CTA (compile-time: slots are [base + immediate])
             auto issue = [&](int chunk) {       // chunk index within this segment; an empty group keeps the group count uniform
                 if (chunk < n_full) {
-                    size_t g = idx0 + (size_t)chunk * chunk_stride;
+                    const Elem* g = src + idx0 + (size_t)chunk * chunk_stride;
                     Elem* dst = ring + (size_t)((chunk % MOBILE_RING) * PF) * nthr + tid;
 #pragma unroll
-                    for (int k = 0; k < PF; ++k) { __pipeline_memcpy_async(dst + (size_t)k * nthr, src + g, sizeof(Elem)); g += N; }
+                    for (int k = 0; k < PF; ++k) __pipeline_memcpy_async(dst + (size_t)k * nthr, g + (uint32_t)k * (uint32_t)N, sizeof(Elem));
                 }
                 __pipeline_commit();
             };
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
                     else { const float2 v = slot[(size_t)k * nthr]; c0.x[DISCRETE ? 0 : k] = v.x; c0.y[DISCRETE ? 0 : k] = v.y; }
                     if (!FAST) c0.nz[FAST ? 0 : k] = noise ? __ldg(noise + idx + (size_t)k * N) : 0.f;
                 }
-                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len);
+                step_chunk<KIND, DISCRETE, SHAPED, FAST, false, PF>(e, acc, c0, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len, s_delta);
             }
             __pipeline_wait_prior(0);
         }
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(128) mobile_rollout_kernel(MobileDev in, Mobil
     for (; t0 < t_end; t0 += PF, idx += chunk_stride) {   // one iteration with auto-reset; more only when stepping on past `done`
         tail_valid = t_end - t0 < PF ? t_end - t0 : PF;
         if (GEN || t0 != t_tail) load_chunk<KIND, DISCRETE, GEN, !FAST, PF>(tl, actions, noise, N, idx, seed, genv, ts_start + (uint32_t)(t0 - t_start), tail_valid);
-        step_chunk<KIND, DISCRETE, SHAPED, FAST, true, PF>(e, acc, tl, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len, tail_valid);
+        step_chunk<KIND, DISCRETE, SHAPED, FAST, true, PF>(e, acc, tl, t0, t_done, t_start, N, idx, ep_ret0, ep_len0, obs, rew, done, ep_ret, ep_len, s_delta, tail_valid);
     }
     const int steps = t_end - t_start;
     e.counter = c_start + steps;                                   // :268
@@ -459,7 +484,7 @@ int launch_rollout_variant(srl_sim* s, int T, const void* actions, const float* 
     int block = warps <= 148 * 4 ? 32 : 128;
     if (s->mobile_block > 0) block = s->mobile_block;
     const dim3 grid((unsigned)((s->n + block - 1) / block), (unsigned)nseg);
-    const size_t ring_bytes = GEN ? 0 : (size_t)MOBILE_RING * MOBILE_PF * block * (DISCRETE ? sizeof(int32_t) : sizeof(float2));
+    const size_t ring_bytes = GEN ? 0 : (size_t)MOBILE_RING * MOBILE_PF * 128 * (DISCRETE ? sizeof(int32_t) : sizeof(float2));   // rows of 128 lanes whatever the CTA size
     mobile_rollout_kernel<KIND, DISCRETE, GEN, SHAPED, FAST><<<grid, block, ring_bytes, st>>>(s->mob, s->mob_alt, s->n, T, actions, noise, obs, rew, done, ep_ret, ep_len,
                                                                                        s->cfg.random_target != 0, s->auto_reset != 0,
                                                                                        s->max_steps, s->seed, s->cfg.global_env_offset);

@@ -46,8 +46,8 @@ class MlpPolicy(nn.Module):
     def dist(self, obs):
         logits = self.pi(obs)
         if self.discrete:
-            return torch.distributions.Categorical(logits=logits)
-        return torch.distributions.Normal(logits, self.logstd.exp())
+            return torch.distributions.Categorical(logits=logits, validate_args=False)   # validation synchronises: not allowed in a captured graph
+        return torch.distributions.Normal(logits, self.logstd.exp(), validate_args=False)
 
     def act(self, obs):
         d = self.dist(obs)
@@ -63,20 +63,23 @@ class MlpPolicy(nn.Module):
 
 
 class RunningNorm(object):
-    """VecNormalize's observation filter on the device: running mean / var, clip to +-10."""
+    """VecNormalize's observation filter on the device: running mean / var, clip to +-10.  All of its state (the sample
+    count included) lives in device tensors and is updated in place, so the update can sit inside a captured CUDA graph."""
 
     def __init__(self, dim, device, clip=10.0, eps=1e-8):
         self.mean = torch.zeros(dim, device=device, dtype=torch.float64)
         self.var = torch.ones(dim, device=device, dtype=torch.float64)
-        self.count, self.clip, self.eps = 1e-4, clip, eps
+        self.count = torch.full((), 1e-4, device=device, dtype=torch.float64)
+        self.clip, self.eps = clip, eps
 
     def update(self, x):
         x = x.double()
-        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), float(x.shape[0])
         delta, tot = bm - self.mean, self.count + bc
-        self.mean = self.mean + delta * bc / tot
-        self.var = (self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot) / tot
-        self.count = tot
+        new_var = (self.var * self.count + bv * bc + delta ** 2 * self.count * bc / tot) / tot
+        self.mean.add_(delta * bc / tot)
+        self.var.copy_(new_var)
+        self.count.copy_(tot)
 
     def __call__(self, x, update=True):
         if update:
@@ -84,8 +87,12 @@ class RunningNorm(object):
         return torch.clamp((x - self.mean.float()) / torch.sqrt(self.var.float() + self.eps), -self.clip, self.clip)
 
 
-def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1):
-    """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps)."""
+def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True):
+    """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
+
+    ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
+    launch per step, buffer writes -- a few dozen small kernels per env step) is captured ONCE into a CUDA graph and replayed
+    per update, so a rollout costs one graph launch instead of ~n_steps x 50 kernel launches from Python."""
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
     torch.manual_seed(seed)
     env_kwargs = dict(env_kwargs or {})
@@ -107,28 +114,54 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         with open(os.path.join(log_dir, "env_globals.json"), "w") as f:  # train.py:285-315
             json.dump({k: v for k, v in env_kwargs.items() if isinstance(v, (int, float, str, bool))}, f)
     env.sim.reset(obs_out=env._obs, stream=env.backend.stream())
-    obs = norm(env._obs.clone())
+    obs = norm(env._obs.clone())            # the current (filtered) observation; updated IN PLACE by the collection loop
     buf = dict(obs=torch.empty((T, N, D), device=dev), act=torch.empty((T, N) if env.is_discrete else (T, N, env.sim.action_dim), device=dev,
                                                                        dtype=torch.int64 if env.is_discrete else torch.float32),
                logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev), rew=torch.empty((T, N), device=dev),
-               done=torch.empty((T, N), device=dev))
-    history, ep_returns = [], []
-    t_start = time.time()
-    for update in range(1, n_updates + 1):
-        frac = 1.0 - (update - 1.0) / n_updates
-        for g in opt.param_groups:
-            g["lr"] = hp["learning_rate"] * frac                          # learning_rate = lambda f: f * 2.5e-4
+               done=torch.empty((T, N), device=dev), ep_ret=torch.empty((T, N), device=dev))
+    last_val = torch.empty(N, device=dev)
+
+    def collect():
+        """n_steps lockstep env steps under the current policy; everything stays on the device, nothing synchronises."""
         with torch.no_grad():
             for t in range(T):
                 a, logp, v = policy.act(obs)
                 buf["obs"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = obs, a, logp, v
                 act_dev = a.to(torch.int32) if env.is_discrete else torch.clamp(a, -1, 1).contiguous()
                 o, r, d, ep_ret, _ = env.step_tensors(act_dev)            # one kernel launch, tensors stay on the GPU
-                buf["rew"][t], buf["done"][t] = r, d.float()
-                if bool(d.any()):
-                    ep_returns.extend(ep_ret[d.bool()].tolist())
-                obs = norm(o.clone())
-            last_val = policy.vf(obs).squeeze(-1)
+                buf["rew"][t], buf["done"][t], buf["ep_ret"][t] = r, d.float(), ep_ret
+                obs.copy_(norm(o))
+            last_val.copy_(policy.vf(obs).squeeze(-1))
+
+    graph = None
+    if cuda_graph and env.backend.on_gpu:
+        # an even number of simulator launches per replay keeps the MobileRobot state double buffer (swapped by the host at every
+        # launch, so the pointers are baked into the captured kernels) in phase
+        if T % 2:
+            raise ValueError("cuda_graph=True needs an even n_steps")
+        side = torch.cuda.Stream(device=dev)      # library handles / workspaces are created outside the capture
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                policy.act(obs); norm(env._obs, update=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):       # capture only records the launches: neither the envs nor the filter advance
+            collect()
+
+    history, ep_returns = [], []
+    t_start = time.time()
+    for update in range(1, n_updates + 1):
+        frac = 1.0 - (update - 1.0) / n_updates
+        for g in opt.param_groups:
+            g["lr"] = hp["learning_rate"] * frac                          # learning_rate = lambda f: f * 2.5e-4
+        if graph is not None:
+            graph.replay()
+        else:
+            collect()
+        with torch.no_grad():
+            ep_returns.extend(buf["ep_ret"][buf["done"].bool()].tolist())
             # GAE(lambda)
             adv = torch.zeros((T, N), device=dev)
             lastgae = torch.zeros(N, device=dev)

@@ -7,11 +7,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_ppo2_learns_mobile_robot(cuda_lib):
+@pytest.mark.parametrize("cuda_graph", [True, False])
+def test_ppo2_learns_mobile_robot(cuda_lib, cuda_graph):
+    """cuda_graph=True replays the captured 128-step collection loop (policy + simulator launches) once per update;
+    cuda_graph=False issues the same launches eagerly.  Both must learn."""
     from srl_sim import backend
     backend.use_library(None, None)
     from rl_baselines.ppo2 import train
-    hist = train("MobileRobotGymEnv-v0", 1024, 1024 * 128 * 12, seed=0, env_kwargs=dict(is_discrete=True, shape_reward=True), verbose=0)
+    hist = train("MobileRobotGymEnv-v0", 1024, 1024 * 128 * 12, seed=0, env_kwargs=dict(is_discrete=True, shape_reward=True), verbose=0, cuda_graph=cuda_graph)
     rets = [h[1] for h in hist if np.isfinite(h[1])]
     # shaped reward = -distance per step over 251 steps: a random policy scores about -420; learning must clearly beat it
     assert rets[-1] > rets[0] + 60, rets
