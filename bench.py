@@ -38,6 +38,7 @@ MOBILE_ENVS_PER_GPU = 8192    # BASELINE.json configs[3]
 # Algorithmic HBM bytes (DESIGN.md "Measurement"): SoA state in + out once per launch, per-step I/O floor.
 KUKA_STATE_BYTES = 2 * 224            # 12 float4 + 2 int4 records, read + written once per launch
 KUKA_STEP_BYTES = 4 + 4 + 12 + 4 + 1  # action i32 + noise f32 in, obs f32[3] + reward f32 + done u8 out
+KUKA_WARP_INST_PER_LAUNCH = 4044192869  # ncu smsp__inst_executed.sum of one 4096-env x 128-step launch (profiles/r01_kuka_kernel_ncu_full.txt)
 KUKA_FLOP_PER_STEP = 1.0e5            # ~150 PGS sweeps x 13 rows x 2 x 13 + dynamics
 MOBILE_STATE_BYTES = 2 * 80
 MOBILE_STEP_BYTES = 4 + 8 + 4 + 1     # action in, obs f32[2] + reward + done out (in-kernel actions: no action read)
@@ -337,6 +338,15 @@ def run_b200(args):
         roof["note"] = ("latency/issue-bound fp32 kernel (150 strictly sequential PGS sweeps per env-step), not HBM-bound: "
                         "%.2f TFLOP/s of useful fp32 work; see DESIGN.md 'Measurement'" % fl)
         roof["fp32_tflops"] = fl
+        # what actually bounds this kernel: warp-instruction issue slots (one per scheduler per cycle, 4 schedulers per SM).
+        # Instructions per launch come from the committed ncu capture (like `traffic`), the time is this run's.
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        issue_peak = sms * 4 * clk * 1e-3
+        issue_ach = KUKA_WARP_INST_PER_LAUNCH / launch_s / 1e9
+        roof["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s", "frac": issue_ach / issue_peak,
+                         "warp_inst_per_launch": KUKA_WARP_INST_PER_LAUNCH,
+                         "source": "smsp__inst_executed.sum of profiles/r01_kuka_kernel_ncu_full.txt; peak = SMs x 4 schedulers x SM clock"}
     metric, config = metric_and_config(args.workload, world)
     line = {"metric": metric, "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,

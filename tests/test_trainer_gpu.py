@@ -30,3 +30,17 @@ def test_train_entry_point_runs_for_every_env(env_id, cuda_lib, tmp_path):
     assert len(hist) >= 1
     fps = main(["--algo", "random_agent", "--env", env_id, "--num-cpu", "4", "--num-timesteps", "400"])
     assert fps > 0
+
+
+def test_enjoy_replays_a_trained_agent(cuda_lib, tmp_path):
+    """replay.enjoy_baselines reloads args.json / env_globals.json / the saved policy and observation filter of a run
+    written by rl_baselines.train and reports finished episodes (the reference's test_enjoy.py asserts the exit code)."""
+    from srl_sim import backend
+    backend.use_library(None, None)
+    from rl_baselines.ppo2 import train
+    train("MobileRobotGymEnv-v0", 256, 256 * 128 * 2, seed=1, env_kwargs=dict(is_discrete=True), log_dir=str(tmp_path), verbose=0)
+    from replay.enjoy_baselines import main
+    n_done, mean_reward = main(["--log-dir", str(tmp_path), "--num-cpu", "16", "--num-timesteps", "300"])
+    assert n_done == 16 and np.isfinite(mean_reward)       # every MobileRobot episode lasts 251 steps
+    n_done, _ = main(["--log-dir", str(tmp_path), "--num-cpu", "4", "--num-timesteps", "260", "--deterministic", "--shape-reward"])
+    assert n_done == 4
