@@ -17,7 +17,9 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+REFERENCE_ROOT = os.environ.get("SRL_REFERENCE_ROOT", "/root/reference")   # a checkout of araffin/robotics-rl-srl
 
 
 class _Inert(types.ModuleType):
@@ -56,15 +58,27 @@ def make_pybullet_stub():
     return p
 
 
-def install(extra_path):
-    """Install the stubs into sys.modules and put the reference + our package on sys.path."""
+def install(extra_path, real_pybullet=False):
+    """Install the stubs into sys.modules and put the reference + our package on sys.path.
+    real_pybullet=True (only meaningful where the PyPI packages exist): keep the REAL `pybullet` / `pybullet_data`, and the
+    real `gym` if it imports -- this is the mode that records PyBullet's own arithmetic (gen_kuka_ref_logic_golden.py --real-pybullet)."""
     sys.path.insert(0, extra_path)  # robotics-rl-srl_b200 (for srl_sim.seeding / spaces)
     from srl_sim import seeding as _seeding, spaces as _spaces
 
-    sys.modules["pybullet"] = make_pybullet_stub()
-    pd = types.ModuleType("pybullet_data")
-    pd.getDataPath = lambda: "/nonexistent/pybullet_data"
-    sys.modules["pybullet_data"] = pd
+    have_gym = False
+    if real_pybullet:
+        import pybullet  # noqa: F401  (fails loudly when the package is absent)
+        import pybullet_data  # noqa: F401
+        try:
+            import gym  # noqa: F401
+            have_gym = True
+        except ImportError:
+            pass
+    else:
+        sys.modules["pybullet"] = make_pybullet_stub()
+        pd = types.ModuleType("pybullet_data")
+        pd.getDataPath = lambda: "/nonexistent/pybullet_data"
+        sys.modules["pybullet_data"] = pd
 
     gym = types.ModuleType("gym")
     gym.Env = _spaces.Env
@@ -74,9 +88,10 @@ def install(extra_path):
     gym.utils = types.ModuleType("gym.utils")
     gym.utils.seeding = types.ModuleType("gym.utils.seeding")
     gym.utils.seeding.np_random = _seeding.np_random
-    for name, mod in (("gym", gym), ("gym.spaces", gym.spaces), ("gym.utils", gym.utils),
-                      ("gym.utils.seeding", gym.utils.seeding)):
-        sys.modules[name] = mod
+    if not have_gym:
+        for name, mod in (("gym", gym), ("gym.spaces", gym.spaces), ("gym.utils", gym.utils),
+                          ("gym.utils.seeding", gym.utils.seeding)):
+            sys.modules[name] = mod
 
     sr = types.ModuleType("state_representation")
     sr.__path__ = []
