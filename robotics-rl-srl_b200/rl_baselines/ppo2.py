@@ -9,6 +9,11 @@ ent_coef=0.01, vf_coef=0.5, cliprange=0.2, gamma=0.99, lam=0.95, max_grad_norm=0
 (``VecNormalize(norm_obs=True, norm_reward=False)``, rl_baselines/utils.py:224-227), policy, GAE, optimisation -- stays on the
 GPU: the env step is ``srl_sim_step`` on torch tensors, no host round trip per step.
 This is a CONSUMER of the hot path (library GEMMs via torch are fine here); the product is the simulator underneath.
+
+Data-parallel over GPUs: under ``torchrun`` every rank owns ``num_envs`` envs (global env offset
+``rank * num_envs``, so env streams do not depend on the GPU count) and a replica of the policy.  Two collectives, none of
+them on the env-step path: ONE all-reduce of the flattened ~10^4-parameter gradient per minibatch, and ONE all-reduce of the
+observation filter's sufficient statistics ([2 D + 1] float64) per rollout.  NCCL on GPUs, gloo in the CPU tests.
 """
 import json
 import os
@@ -87,6 +92,43 @@ class RunningNorm(object):
         return torch.clamp((x - self.mean.float()) / torch.sqrt(self.var.float() + self.eps), -self.clip, self.clip)
 
 
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def merge_running_moments(norm, prior, all_reduce_sum, world):
+    """Merge the per-rank observation filters after a rollout.  Every rank started the rollout from the same ``prior`` =
+    (mean, var, count) and folded its own batches in; the sufficient statistics S = (count, count * mean, count * (var + mean^2))
+    are additive, so the filter that saw every rank's batches is  sum_r S_r - (world - 1) * S_prior.  One all-reduce of
+    2 D + 1 doubles; the result is identical on every rank."""
+    def stats(mean, var, count):
+        return torch.cat([count.reshape(1), count * mean, count * (var + mean * mean)])
+    d = norm.mean.numel()
+    s = stats(norm.mean, norm.var, norm.count)
+    all_reduce_sum(s)
+    s = s - (world - 1) * stats(*prior)
+    count, mean = s[0], s[1:1 + d] / s[0]
+    norm.count.copy_(count)
+    norm.mean.copy_(mean)
+    norm.var.copy_(torch.clamp(s[1 + d:] / count - mean * mean, min=0.0))
+
+
+def allreduce_mean_gradients(params, dist, world):
+    """Average the gradients over ranks with ONE collective: flatten, all-reduce (sum), scale, scatter back."""
+    grads = [p.grad for p in params]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
 def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
@@ -96,25 +138,41 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
     torch.manual_seed(seed)
     env_kwargs = dict(env_kwargs or {})
-    env = BatchedSRLVecEnv(env_id, num_envs, seed=seed, device=device, **env_kwargs)
-    dev = env.backend.torch_device
+    dist, rank, world = _dist_world()
+    env = BatchedSRLVecEnv(env_id, num_envs, seed=seed, device=device, global_env_offset=rank * num_envs, **env_kwargs)
+    on_gpu = env.backend.on_gpu
+    # device -1 is the CPU oracle installed by a test through srl_sim.backend.use_library (its buffers are numpy arrays,
+    # shared with torch below); the product backend is always a CUDA device
+    dev = env.backend.torch_device if on_gpu else torch.device("cpu")
+    e_obs, e_rew, e_done, e_ep_ret = [x if on_gpu else torch.from_numpy(x) for x in (env._obs, env._rew, env._done, env._ep_ret)]
     D = env.observation_space.shape[0]
     if env.is_discrete:
         policy = MlpPolicy(D, n_actions=env.action_space.n).to(dev)
     else:
         policy = MlpPolicy(D, action_dim=env.action_space.shape[0]).to(dev)
-    opt = torch.optim.Adam(policy.parameters(), lr=hp["learning_rate"], eps=1e-5)
+    params = list(policy.parameters())
+    if dist is not None:
+        for p in params:                      # same seed => same init; the broadcast makes it independent of library versions
+            dist.broadcast(p.data, 0)
+        torch.manual_seed(seed + rank)        # action sampling / minibatch permutations differ per rank
+    opt = torch.optim.Adam(params, lr=hp["learning_rate"], eps=1e-5)
     norm = RunningNorm(D, dev)
     N, T = num_envs, hp["n_steps"]
-    n_updates = max(1, int(num_timesteps) // (N * T))
-    if log_dir:
+    n_updates = max(1, int(num_timesteps) // (N * T * world))
+    if log_dir and rank == 0:
         os.makedirs(log_dir, exist_ok=True)
         with open(os.path.join(log_dir, "args.json"), "w") as f:       # train.py:282-283
             json.dump(dict(env=env_id, algo="ppo2", num_cpu=N, num_timesteps=num_timesteps, seed=seed, srl_model="ground_truth", **hp), f)
         with open(os.path.join(log_dir, "env_globals.json"), "w") as f:  # train.py:285-315
             json.dump({k: v for k, v in env_kwargs.items() if isinstance(v, (int, float, str, bool))}, f)
     env.sim.reset(obs_out=env._obs, stream=env.backend.stream())
-    obs = norm(env._obs.clone())            # the current (filtered) observation; updated IN PLACE by the collection loop
+    if dist is not None:                   # the reset batch goes through the same merge, so every rank starts from one filter
+        prior = (norm.mean.clone(), norm.var.clone(), norm.count.clone())
+        norm.update(e_obs)
+        merge_running_moments(norm, prior, dist.all_reduce, world)
+        obs = norm(e_obs.clone(), update=False)
+    else:
+        obs = norm(e_obs.clone())        # the current (filtered) observation; updated IN PLACE by the collection loop
     buf = dict(obs=torch.empty((T, N, D), device=dev), act=torch.empty((T, N) if env.is_discrete else (T, N, env.sim.action_dim), device=dev,
                                                                        dtype=torch.int64 if env.is_discrete else torch.float32),
                logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev), rew=torch.empty((T, N), device=dev),
@@ -128,13 +186,13 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 a, logp, v = policy.act(obs)
                 buf["obs"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = obs, a, logp, v
                 act_dev = a.to(torch.int32) if env.is_discrete else torch.clamp(a, -1, 1).contiguous()
-                o, r, d, ep_ret, _ = env.step_tensors(act_dev)            # one kernel launch, tensors stay on the GPU
-                buf["rew"][t], buf["done"][t], buf["ep_ret"][t] = r, d.float(), ep_ret
-                obs.copy_(norm(o))
+                env.step_tensors(act_dev)                                 # one kernel launch, tensors stay on the GPU
+                buf["rew"][t], buf["done"][t], buf["ep_ret"][t] = e_rew, e_done.float(), e_ep_ret
+                obs.copy_(norm(e_obs))
             last_val.copy_(policy.vf(obs).squeeze(-1))
 
     graph = None
-    if cuda_graph and env.backend.on_gpu:
+    if cuda_graph and on_gpu:
         # an even number of simulator launches per replay keeps the MobileRobot state double buffer (swapped by the host at every
         # launch, so the pointers are baked into the captured kernels) in phase
         if T % 2:
@@ -143,7 +201,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(3):
-                policy.act(obs); norm(env._obs, update=False)
+                policy.act(obs); norm(e_obs, update=False)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -156,10 +214,13 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         frac = 1.0 - (update - 1.0) / n_updates
         for g in opt.param_groups:
             g["lr"] = hp["learning_rate"] * frac                          # learning_rate = lambda f: f * 2.5e-4
+        prior = (norm.mean.clone(), norm.var.clone(), norm.count.clone()) if dist is not None else None
         if graph is not None:
             graph.replay()
         else:
             collect()
+        if dist is not None:                   # one all-reduce of 2 D + 1 doubles per rollout
+            merge_running_moments(norm, prior, dist.all_reduce, world)
         with torch.no_grad():
             ep_returns.extend(buf["ep_ret"][buf["done"].bool()].tolist())
             # GAE(lambda)
@@ -189,16 +250,24 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 loss = pg - hp["ent_coef"] * ent.mean() + hp["vf_coef"] * vf_loss
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
-                nn.utils.clip_grad_norm_(policy.parameters(), hp["max_grad_norm"])
+                if dist is not None:           # one all-reduce of the flattened gradient per minibatch
+                    allreduce_mean_gradients(params, dist, world)
+                nn.utils.clip_grad_norm_(params, hp["max_grad_norm"])
                 opt.step()
-        steps = update * N * T
+        steps = update * N * T * world
         fps = steps / (time.time() - t_start)
         window = ep_returns[-max(40, N):]                                  # episode_window (train.py:180)
-        mean_ret = float(np.mean(window)) if window else float("nan")
+        if dist is not None:
+            from srl_sim.distributed import allgather_episode_stats
+            mean_ret, n_ep = allgather_episode_stats(float(np.sum(window)), len(window), device=dev if on_gpu else None)
+            mean_ret = mean_ret if n_ep else float("nan")
+        else:
+            mean_ret = float(np.mean(window)) if window else float("nan")
         history.append((steps, mean_ret, fps))
-        if verbose:
+        if verbose and rank == 0:
             print("update %d/%d  steps %d  mean episode return %.3f  episodes %d  fps %.0f" % (update, n_updates, steps, mean_ret, len(ep_returns), fps))
-    if log_dir:
+    if log_dir and rank == 0:
         torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean, obs_var=norm.var), os.path.join(log_dir, "ppo2_model.pt"))
     env.close()
+    train.last_policy, train.last_norm = policy, norm      # for callers that want the trained objects (tests, enjoy)
     return history

@@ -1,7 +1,8 @@
 """
 Mirror of the reference's training entry point ``python -m rl_baselines.train`` (rl_baselines/train.py:172-333) for the
 algorithms this repo provides as consumers of the simulator: ``ppo2`` (rl_baselines/ppo2.py) and ``random_agent``
-(rl_baselines/random_agent.py:28-42).  Same flag names; ``--num-cpu`` is the number of envs in the batch.
+(rl_baselines/random_agent.py:28-42).  Same flag names; ``--num-cpu`` is the number of envs in the batch (per GPU when launched
+with ``torchrun --nproc-per-node N -m rl_baselines.train``: data-parallel PPO2, see rl_baselines/ppo2.py).
 """
 import argparse
 import os
@@ -31,7 +32,17 @@ def main(argv=None):
     num_timesteps = int(1.1 * args.num_timesteps)      # the reference trains 10 % longer (train.py:319)
     if args.algo == "ppo2":
         from rl_baselines.ppo2 import train
-        return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs, log_dir=log_dir, device=args.device)
+        from srl_sim.distributed import rank_world
+        rank, world, local_rank = rank_world()
+        device = args.device
+        if world > 1:      # torchrun: one process per GPU, --num-cpu envs on EACH rank, gradients averaged over NCCL
+            import torch
+            import torch.distributed as dist
+            device = local_rank
+            torch.cuda.set_device(device)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs, log_dir=log_dir, device=device)
     from rl_baselines.random_agent import train
     return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs)
 

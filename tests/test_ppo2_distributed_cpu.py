@@ -1,0 +1,90 @@
+"""
+Data-parallel PPO2 on CPU: world-size-2 `gloo`, the simulator behind the C-ABI replaced by the CPU oracle
+(test infrastructure, installed explicitly through srl_sim.backend.use_library).  Checks the two collectives of the trainer:
+the per-minibatch gradient all-reduce keeps the replicas bit-identical, and the per-rollout merge of the observation
+filter equals a single filter that saw every rank's batches.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ORACLE_LIB, PKG
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, outdir):
+    import sys
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from srl_sim import backend
+    from srl_sim._abi import SimLibrary
+    backend.use_library(SimLibrary(ORACLE_LIB), -1)
+    from rl_baselines import ppo2
+    hist = ppo2.train("MobileRobotGymEnv-v0", 8, 8 * 16 * 2 * 3, seed=3, env_kwargs=dict(is_discrete=True, shape_reward=True, max_steps=20),
+                      hyperparams=dict(n_steps=16), verbose=0, cuda_graph=False, log_dir=os.path.join(outdir, "log"), device=None)
+    policy, norm = ppo2.train.last_policy, ppo2.train.last_norm
+    flat = torch.cat([p.detach().reshape(-1) for p in policy.parameters()]).numpy()
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), params=flat, mean=norm.mean.numpy(), var=norm.var.numpy(), count=norm.count.numpy(),
+             steps=[h[0] for h in hist], ret=[h[1] for h in hist])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ppo2_keeps_replicas_identical(tmp_path, oracle_lib):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert np.array_equal(a["params"], b["params"])                    # averaged gradients => bit-identical replicas
+    for k in ("mean", "var", "count"):
+        assert np.array_equal(a[k], b[k]), k                           # the merged filter is the same on both ranks
+    # 3 updates x 2 ranks x 8 envs x 16 steps, +1 reset batch per rank (the filter also sees the reset observation) + the 1e-4 prior
+    assert float(a["count"]) == pytest.approx(3 * 2 * 8 * 16 + 2 * 8 + 1e-4)
+    assert list(a["steps"]) == [256, 512, 768]                         # global env steps
+    assert np.array_equal(a["ret"], b["ret"], equal_nan=True)                            # all-gathered episode statistics
+    assert np.isfinite(a["ret"][-1])                                   # max_steps=20 => 21-step episodes finish from the second rollout on
+    assert os.path.isfile(os.path.join(str(tmp_path), "log", "ppo2_model.pt"))   # rank 0 alone writes the run directory
+
+
+def test_merge_running_moments_equals_one_filter_over_all_batches():
+    import sys
+    sys.path.insert(0, PKG)
+    from rl_baselines.ppo2 import RunningNorm, merge_running_moments
+    rng = np.random.default_rng(0)
+    dev = torch.device("cpu")
+    prior_batch = torch.from_numpy(rng.normal(1.0, 2.0, (50, 3)))
+    batches = [[torch.from_numpy(rng.normal(r, 1.0 + r, (16, 3))) for _ in range(5)] for r in range(3)]
+    ranks = []
+    for r in range(3):
+        f = RunningNorm(3, dev); f.update(prior_batch)
+        ranks.append(f)
+    prior = (ranks[0].mean.clone(), ranks[0].var.clone(), ranks[0].count.clone())
+    for f, bs in zip(ranks, batches):
+        for x in bs:
+            f.update(x)
+    # a sum over "ranks" that runs in-process: the all-reduce callback adds the other ranks' statistics
+    def make_all_reduce(me):
+        def all_reduce(s):
+            for j, g in enumerate(ranks_stats):
+                if j != me:
+                    s.add_(g)
+        return all_reduce
+    ranks_stats = [torch.cat([f.count.reshape(1), f.count * f.mean, f.count * (f.var + f.mean ** 2)]) for f in ranks]
+    for i, f in enumerate(ranks):
+        merge_running_moments(f, prior, make_all_reduce(i), world=3)
+    whole = RunningNorm(3, dev); whole.update(prior_batch)
+    whole.update(torch.cat([x for bs in batches for x in bs]))
+    for f in ranks:
+        assert torch.allclose(f.mean, whole.mean, rtol=0, atol=1e-12)
+        assert torch.allclose(f.var, whole.var, rtol=1e-12, atol=1e-12)
+        assert float(f.count) == pytest.approx(float(whole.count), rel=1e-14)
