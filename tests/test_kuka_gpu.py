@@ -282,6 +282,32 @@ def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypa
     assert sim.launch_count - launches0 == max(1, host_chunks)   # one launch per T-chunk
 
 
+@pytest.mark.parametrize("zero_copy", ["1", "0"])
+def test_rollout_host_pinned_buffers_zero_copy(cuda_backend, zero_copy, monkeypatch):
+    """With pinned (device-mapped) host output buffers an unsplit srl_sim_rollout_host lets the kernel store obs / reward / done
+    straight into them (no device->host copy); SRL_HOST_ZEROCOPY=0 forces the staged copies.  Same bits either way, and some
+    outputs pinned / some pageable is allowed."""
+    import torch
+    monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)
+    monkeypatch.setenv("SRL_HOST_ZEROCOPY", zero_copy)
+    n, T = 256, 64
+    rs = np.random.RandomState(9)
+    acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
+    dev = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=7)
+    sim = cuda_backend.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=7)
+    sim.reset(stream=cuda_backend.stream())
+    torch.cuda.synchronize()
+    obs = torch.full((T, n, 3), float("nan")).pin_memory(); rew = torch.full((T, n), float("nan")).pin_memory()
+    done = np.full((T, n), 255, np.uint8)                                  # pageable on purpose
+    sim.rollout_host(T, torch.from_numpy(acts).pin_memory(), torch.from_numpy(noise).pin_memory(), obs, rew, done)
+    assert np.array_equal(obs.numpy(), dev["obs"]) and np.array_equal(rew.numpy(), dev["rew"]) and np.array_equal(done, dev["done"])
+    obs.fill_(float("nan"))
+    sim2 = cuda_backend.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=7)
+    sim2.reset(stream=cuda_backend.stream())
+    sim2.rollout_host(T, acts, noise, obs, None, None)                      # only one output requested
+    assert np.array_equal(obs.numpy(), dev["obs"])
+
+
 def test_single_env_classes_on_cuda(cuda_lib):
     from srl_sim import backend
     backend.use_library(None, None)

@@ -149,6 +149,24 @@ def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypa
     assert sim.launch_count - launches0 == max(1, host_chunks)   # one launch per T-chunk
 
 
+@pytest.mark.parametrize("zero_copy", ["1", "0"])
+def test_rollout_host_pinned_buffers_zero_copy(cuda_backend, zero_copy, monkeypatch):
+    """Pinned host output buffers: an unsplit srl_sim_rollout_host stores straight into them (SRL_HOST_ZEROCOPY=0: staged copies)."""
+    import torch
+    monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)
+    monkeypatch.setenv("SRL_HOST_ZEROCOPY", zero_copy)
+    kind, n, T = KINDS[0], 512, 300
+    acts = np.random.RandomState(9).randint(0, 4, size=(T, n)).astype(np.int32)
+    dev = _run(cuda_backend, kind, n, T, acts, seed=7)
+    sim = cuda_backend.make_sim(kind, n, seed=7)
+    sim.reset(stream=cuda_backend.stream())
+    torch.cuda.synchronize()
+    obs = torch.full((T, n, 2), float("nan")).pin_memory(); rew = torch.full((T, n), float("nan")).pin_memory()
+    done = torch.full((T, n), 255, dtype=torch.uint8).pin_memory()
+    sim.rollout_host(T, torch.from_numpy(acts).pin_memory(), None, obs, rew, done)
+    assert np.array_equal(obs.numpy(), dev["obs"]) and np.array_equal(rew.numpy(), dev["rew"]) and np.array_equal(done.numpy(), dev["done"])
+
+
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("no_auto_reset", [False, True])
 def test_cuda_ragged_counters_and_consecutive_rollouts(kind, no_auto_reset, cuda_backend, oracle_backend):
