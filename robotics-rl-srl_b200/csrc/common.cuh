@@ -53,7 +53,7 @@ struct srl_sim {
     cudaEvent_t host_ev[2 * SRL_HOST_MAX_CHUNKS];
     bool host_pipe_ready;
     int host_chunks;    // SRL_HOST_CHUNKS override (0 = by bytes moved)
-    bool host_zero_copy; // single-chunk rollouts store obs / reward / done straight into pinned, device-mapped host buffers (SRL_HOST_ZEROCOPY=0 disables)
+    bool host_zero_copy; // single-chunk rollouts store obs / reward / done straight into pinned, device-mapped host buffers (opt-in: SRL_HOST_ZEROCOPY=1)
 };
 
 static inline bool srl_is_mobile(int kind) { return kind >= SRL_ENV_MOBILE && kind <= SRL_ENV_MOBILE_LINE_TARGET; }

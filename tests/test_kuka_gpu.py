@@ -285,7 +285,7 @@ def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypa
 @pytest.mark.parametrize("zero_copy", ["1", "0"])
 def test_rollout_host_pinned_buffers_zero_copy(cuda_backend, zero_copy, monkeypatch):
     """With pinned (device-mapped) host output buffers an unsplit srl_sim_rollout_host lets the kernel store obs / reward / done
-    straight into them (no device->host copy); SRL_HOST_ZEROCOPY=0 forces the staged copies.  Same bits either way, and some
+    straight into them (no device->host copy); SRL_HOST_ZEROCOPY=1 (opt-in; 0 = the default staged copies).  Same bits either way, and some
     outputs pinned / some pageable is allowed."""
     import torch
     monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)

@@ -151,7 +151,7 @@ def test_rollout_host_matches_device_rollout(cuda_backend, host_chunks, monkeypa
 
 @pytest.mark.parametrize("zero_copy", ["1", "0"])
 def test_rollout_host_pinned_buffers_zero_copy(cuda_backend, zero_copy, monkeypatch):
-    """Pinned host output buffers: an unsplit srl_sim_rollout_host stores straight into them (SRL_HOST_ZEROCOPY=0: staged copies)."""
+    """Pinned host output buffers: an unsplit srl_sim_rollout_host stores straight into them (opt-in SRL_HOST_ZEROCOPY=1; 0 = the default staged copies)."""
     import torch
     monkeypatch.delenv("SRL_HOST_CHUNKS", raising=False)
     monkeypatch.setenv("SRL_HOST_ZEROCOPY", zero_copy)
