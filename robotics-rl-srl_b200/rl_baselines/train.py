@@ -42,7 +42,11 @@ def main(argv=None):
             torch.cuda.set_device(device)
             if not dist.is_initialized():
                 dist.init_process_group("nccl", device_id=torch.device("cuda", device))
-        return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs, log_dir=log_dir, device=device)
+        try:
+            return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs, log_dir=log_dir, device=device)
+        finally:
+            if world > 1 and dist.is_initialized():
+                dist.destroy_process_group()
     from rl_baselines.random_agent import train
     return train(args.env, args.num_cpu, num_timesteps, seed=args.seed, env_kwargs=env_kwargs)
 
