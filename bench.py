@@ -38,7 +38,7 @@ MOBILE_ENVS_PER_GPU = 8192    # BASELINE.json configs[3]
 # Algorithmic HBM bytes (DESIGN.md "Measurement"): SoA state in + out once per launch, per-step I/O floor.
 KUKA_STATE_BYTES = 2 * 224            # 12 float4 + 2 int4 records, read + written once per launch
 KUKA_STEP_BYTES = 4 + 4 + 12 + 4 + 1  # action i32 + noise f32 in, obs f32[3] + reward f32 + done u8 out
-KUKA_WARP_INST_PER_LAUNCH = 4044192869  # ncu smsp__inst_executed.sum of one 4096-env x 128-step launch (profiles/r01_kuka_kernel_ncu_full.txt)
+KUKA_WARP_INST_PER_LAUNCH = 3904811262  # ncu smsp__inst_executed.sum of one 4096-env x 128-step launch (profiles/r01_kuka_kernel_ncu_full.txt)
 KUKA_FLOP_PER_STEP = 1.0e5            # ~150 PGS sweeps x 13 rows x 2 x 13 + dynamics
 MOBILE_STATE_BYTES = 2 * 80
 MOBILE_STEP_BYTES = 4 + 8 + 4 + 1     # action in, obs f32[2] + reward + done out (in-kernel actions: no action read)
@@ -368,7 +368,7 @@ def run_b200(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/); filled in per round, None until measured.
-TRAFFIC_BYTES = {"kuka": 65799168, "mobile": 86867968}  # profiles/r01_*_ncu_full.txt
+TRAFFIC_BYTES = {"kuka": 108501760, "mobile": 86471680}  # profiles/r01_*_ncu_full.txt
 
 
 def main():
