@@ -129,12 +129,15 @@ def allreduce_mean_gradients(params, dist, world):
         off += n
 
 
-def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True):
+def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True,
+          phase_times=None):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
     ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
     launch per step, buffer writes -- a few dozen small kernels per env step) is captured ONCE into a CUDA graph and replayed
-    per update, so a rollout costs one graph launch instead of ~n_steps x 50 kernel launches from Python."""
+    per update, so a rollout costs one graph launch instead of ~n_steps x 50 kernel launches from Python.
+    ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
+    ``collect`` / ``gae`` / ``optimise`` in it (a profiling aid: the synchronisations cost throughput)."""
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
     torch.manual_seed(seed)
     env_kwargs = dict(env_kwargs or {})
@@ -155,9 +158,17 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         for p in params:                      # same seed => same init; the broadcast makes it independent of library versions
             dist.broadcast(p.data, 0)
         torch.manual_seed(seed + rank)        # action sampling / minibatch permutations differ per rank
-    opt = torch.optim.Adam(params, lr=hp["learning_rate"], eps=1e-5)
-    norm = RunningNorm(D, dev)
     N, T = num_envs, hp["n_steps"]
+    # The GAE recursion and the minibatch step (forward, losses, backward, gradient clip, Adam) are captured into CUDA graphs too:
+    # ~1000 and ~150 small launches respectively that cost more on the host than on the GPU.  Data-parallel runs keep the eager
+    # minibatch step (its gradient all-reduce sits between backward and the optimiser step).
+    graph_update = bool(cuda_graph and on_gpu and dist is None and (T * N) % hp["nminibatches"] == 0)
+    if graph_update:      # a captured optimiser needs its step counter and its learning rate on the device
+        lr_t = torch.tensor(float(hp["learning_rate"]), device=dev, dtype=torch.float32)
+        opt = torch.optim.Adam(params, lr=lr_t, eps=1e-5, capturable=True)
+    else:
+        opt = torch.optim.Adam(params, lr=hp["learning_rate"], eps=1e-5)
+    norm = RunningNorm(D, dev)
     n_updates = max(1, int(num_timesteps) // (N * T * world))
     if log_dir and rank == 0:
         os.makedirs(log_dir, exist_ok=True)
@@ -208,52 +219,107 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         with torch.cuda.graph(graph):       # capture only records the launches: neither the envs nor the filter advance
             collect()
 
-    history, ep_returns = [], []
-    t_start = time.time()
-    for update in range(1, n_updates + 1):
-        frac = 1.0 - (update - 1.0) / n_updates
-        for g in opt.param_groups:
-            g["lr"] = hp["learning_rate"] * frac                          # learning_rate = lambda f: f * 2.5e-4
-        prior = (norm.mean.clone(), norm.var.clone(), norm.count.clone()) if dist is not None else None
-        if graph is not None:
-            graph.replay()
-        else:
-            collect()
-        if dist is not None:                   # one all-reduce of 2 D + 1 doubles per rollout
-            merge_running_moments(norm, prior, dist.all_reduce, world)
+    # ---- advantage estimation and the minibatch step on static buffers (so that both can be captured) ----
+    adv, ret = torch.zeros((T, N), device=dev), torch.zeros((T, N), device=dev)
+    flat = {k: v.reshape((T * N,) + v.shape[2:]) for k, v in buf.items()}
+    flat_adv, flat_ret = adv.reshape(-1), ret.reshape(-1)
+    mb = max(1, T * N // hp["nminibatches"])
+    idx_static = torch.zeros(mb, dtype=torch.int64, device=dev)
+
+    def gae():
+        """GAE(lambda), the reference's backward recursion over the rollout."""
         with torch.no_grad():
-            ep_returns.extend(buf["ep_ret"][buf["done"].bool()].tolist())
-            # GAE(lambda)
-            adv = torch.zeros((T, N), device=dev)
             lastgae = torch.zeros(N, device=dev)
             for t in reversed(range(T)):
                 nonterminal = 1.0 - buf["done"][t]
                 nextval = last_val if t == T - 1 else buf["val"][t + 1]
                 delta = buf["rew"][t] + hp["gamma"] * nextval * nonterminal - buf["val"][t]
                 lastgae = delta + hp["gamma"] * hp["lam"] * nonterminal * lastgae
-                adv[t] = lastgae
-            ret = adv + buf["val"]
-        flat = {k: v.reshape((T * N,) + v.shape[2:]) for k, v in buf.items()}
-        flat_adv, flat_ret = adv.reshape(-1), ret.reshape(-1)
-        mb = T * N // hp["nminibatches"]
+                adv[t].copy_(lastgae)
+            torch.add(adv, buf["val"], out=ret)
+
+    def minibatch_step(idx):
+        logp, ent, v = policy.evaluate(flat["obs"][idx], flat["act"][idx])
+        a_mb = flat_adv[idx]
+        a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+        ratio = torch.exp(logp - flat["logp"][idx])
+        pg = torch.max(-a_mb * ratio, -a_mb * torch.clamp(ratio, 1 - hp["cliprange"], 1 + hp["cliprange"])).mean()
+        vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -hp["cliprange"], hp["cliprange"])
+        vf_loss = 0.5 * torch.max((v - flat_ret[idx]) ** 2, (vclip - flat_ret[idx]) ** 2).mean()
+        loss = pg - hp["ent_coef"] * ent.mean() + hp["vf_coef"] * vf_loss
+        loss.backward()
+        if dist is not None:           # one all-reduce of the flattened gradient per minibatch
+            allreduce_mean_gradients(params, dist, world)
+        nn.utils.clip_grad_norm_(params, hp["max_grad_norm"])
+        opt.step()
+
+    gae_graph = None
+    if graph is not None:              # same conditions as the collection graph; elementwise work only, nothing to warm up
+        gae_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gae_graph):
+            gae()
+    mb_graph, mb_warm = None, 0        # the minibatch step is captured after three eager warm-up steps (real ones) on a side stream
+
+    history, ep_returns = [], []
+
+    def tick(name=None, since=0.0):
+        if phase_times is None:
+            return 0.0
+        if on_gpu:
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None:
+            phase_times[name] = phase_times.get(name, 0.0) + now - since
+        return now
+    t_start = time.time()
+    for update in range(1, n_updates + 1):
+        frac = 1.0 - (update - 1.0) / n_updates
+        if graph_update:
+            lr_t.fill_(hp["learning_rate"] * frac)                        # learning_rate = lambda f: f * 2.5e-4
+        else:
+            for g in opt.param_groups:
+                g["lr"] = hp["learning_rate"] * frac
+        prior = (norm.mean.clone(), norm.var.clone(), norm.count.clone()) if dist is not None else None
+        t_ph = tick()
+        if graph is not None:
+            graph.replay()
+        else:
+            collect()
+        if dist is not None:                   # one all-reduce of 2 D + 1 doubles per rollout
+            merge_running_moments(norm, prior, dist.all_reduce, world)
+        t_ph = tick("collect", t_ph)
+        ep_returns.extend(buf["ep_ret"][buf["done"].bool()].tolist())
+        if gae_graph is not None:
+            gae_graph.replay()
+        else:
+            gae()
+        t_ph = tick("gae", t_ph)
         for _ in range(hp["noptepochs"]):
             perm = torch.randperm(T * N, device=dev)
             for s in range(0, T * N, mb):
-                idx = perm[s:s + mb]
-                logp, ent, v = policy.evaluate(flat["obs"][idx], flat["act"][idx])
-                a_mb = flat_adv[idx]
-                a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
-                ratio = torch.exp(logp - flat["logp"][idx])
-                pg = torch.max(-a_mb * ratio, -a_mb * torch.clamp(ratio, 1 - hp["cliprange"], 1 + hp["cliprange"])).mean()
-                vclip = flat["val"][idx] + torch.clamp(v - flat["val"][idx], -hp["cliprange"], hp["cliprange"])
-                vf_loss = 0.5 * torch.max((v - flat_ret[idx]) ** 2, (vclip - flat_ret[idx]) ** 2).mean()
-                loss = pg - hp["ent_coef"] * ent.mean() + hp["vf_coef"] * vf_loss
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                if dist is not None:           # one all-reduce of the flattened gradient per minibatch
-                    allreduce_mean_gradients(params, dist, world)
-                nn.utils.clip_grad_norm_(params, hp["max_grad_norm"])
-                opt.step()
+                if not graph_update:
+                    opt.zero_grad(set_to_none=True)
+                    minibatch_step(perm[s:s + mb])
+                    continue
+                idx_static.copy_(perm[s:s + mb])
+                if mb_graph is not None:
+                    mb_graph.replay()
+                elif mb_warm < 3:          # warm-up iterations run on a side stream (torch's whole-network capture recipe)
+                    cur = torch.cuda.current_stream(dev)
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        opt.zero_grad(set_to_none=True)
+                        minibatch_step(idx_static)
+                    cur.wait_stream(side)
+                    mb_warm += 1
+                else:
+                    mb_graph = torch.cuda.CUDAGraph()
+                    opt.zero_grad(set_to_none=True)
+                    with torch.cuda.graph(mb_graph):   # gradients are allocated from the graph's pool and re-created by every replay
+                        minibatch_step(idx_static)
+                    mb_graph.replay()                  # the capture only recorded this minibatch: now run it
+        t_ph = tick("optimise", t_ph)
         steps = update * N * T * world
         fps = steps / (time.time() - t_start)
         window = ep_returns[-max(40, N):]                                  # episode_window (train.py:180)

@@ -88,3 +88,17 @@ def test_merge_running_moments_equals_one_filter_over_all_batches():
         assert torch.allclose(f.mean, whole.mean, rtol=0, atol=1e-12)
         assert torch.allclose(f.var, whole.var, rtol=1e-12, atol=1e-12)
         assert float(f.count) == pytest.approx(float(whole.count), rel=1e-14)
+
+
+def test_single_process_ppo2_runs_on_the_oracle_backend(use_oracle_backend):
+    """The trainer's eager path (no CUDA graphs) end to end on CPU: collection, GAE, minibatch steps, phase timing, history."""
+    from rl_baselines import ppo2
+    pt = {}
+    hist = ppo2.train("MobileRobotGymEnv-v0", 16, 16 * 32 * 3, seed=1, env_kwargs=dict(is_discrete=True, shape_reward=True, max_steps=20),
+                      hyperparams=dict(n_steps=32), verbose=0, device=None, phase_times=pt)
+    assert [h[0] for h in hist] == [512, 1024, 1536]
+    assert all(np.isfinite(h[1]) and h[1] < 0 for h in hist)           # shaped reward = -distance: every finished episode has a negative return
+    assert set(pt) == {"collect", "gae", "optimise"} and all(v > 0 for v in pt.values())
+    hist_c = ppo2.train("MobileRobotGymEnv-v0", 8, 8 * 16 * 2, seed=2, env_kwargs=dict(is_discrete=False, max_steps=20), hyperparams=dict(n_steps=16),
+                        verbose=0, device=None)                        # continuous actions: the Normal policy head
+    assert len(hist_c) == 2
