@@ -72,9 +72,10 @@ class RunningNorm(object):
     count included) lives in device tensors and is updated in place, so the update can sit inside a captured CUDA graph."""
 
     def __init__(self, dim, device, clip=10.0, eps=1e-8):
-        self.mean = torch.zeros(dim, device=device, dtype=torch.float64)
-        self.var = torch.ones(dim, device=device, dtype=torch.float64)
-        self.count = torch.full((), 1e-4, device=device, dtype=torch.float64)
+        # one contiguous float64 record {mean[dim], var[dim], count} (the layout srl_obs_filter updates in place); the attributes are views
+        self.state = torch.cat([torch.zeros(dim, dtype=torch.float64), torch.ones(dim, dtype=torch.float64),
+                                torch.full((1,), 1e-4, dtype=torch.float64)]).to(device)
+        self.mean, self.var, self.count = self.state[:dim], self.state[dim:2 * dim], self.state[2 * dim]
         self.clip, self.eps = clip, eps
 
     def update(self, x):
@@ -130,12 +131,16 @@ def allreduce_mean_gradients(params, dist, world):
 
 
 def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True,
-          phase_times=None):
+          phase_times=None, fused_act=False):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
     ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
     launch per step, buffer writes -- a few dozen small kernels per env step) is captured ONCE into a CUDA graph and replayed
     per update, so a rollout costs one graph launch instead of ~n_steps x 50 kernel launches from Python.
+    ``fused_act``: run the per-step policy work through the library's own kernels (``srl_policy_act``: both towers, sample, log-prob,
+    value and the rollout-buffer writes in one launch; ``srl_obs_filter``: the observation filter in one launch; include/srl_policy.h)
+    instead of ~60 small torch kernels: an env step of the collection loop is then three launches.  Sampling then uses the library's
+    counter-based streams (keyed by seed and global env index) instead of torch's generator.
     ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
     ``collect`` / ``gae`` / ``optimise`` in it (a profiling aid: the synchronisations cost throughput)."""
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
@@ -189,6 +194,14 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev), rew=torch.empty((T, N), device=dev),
                done=torch.empty((T, N), device=dev), ep_ret=torch.empty((T, N), device=dev))
     last_val = torch.empty(N, device=dev)
+    fused = None
+    if fused_act:
+        if not on_gpu:
+            raise ValueError("fused_act=True needs the CUDA library (there is no CPU fallback)")
+        from srl_sim.policy import FusedPolicy
+        fused = FusedPolicy(env.backend.library, policy, norm.state, seed=seed, env_offset=rank * num_envs, clip=norm.clip, eps=norm.eps)
+        act_dev = torch.zeros(N if env.is_discrete else (N, env.sim.action_dim), device=dev, dtype=torch.int32 if env.is_discrete else torch.float32)
+        done_u8 = torch.zeros((T, N), device=dev, dtype=torch.uint8)
 
     def collect():
         """n_steps lockstep env steps under the current policy; everything stays on the device, nothing synchronises."""
@@ -202,6 +215,20 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 obs.copy_(norm(e_obs))
             last_val.copy_(policy.vf(obs).squeeze(-1))
 
+    def collect_fused():
+        """The same rollout as ``collect`` in three launches per env step: policy step, simulator step, observation filter.  The
+        simulator writes reward / done / episode return straight into the rollout buffers."""
+        with torch.no_grad():
+            st = env.backend.stream()
+            for t in range(T):
+                fused.act(N, obs, act_dev, buf["logp"][t], buf["val"][t], obs_buf=buf["obs"][t], act_buf=buf["act"][t], stream=st)
+                env.sim.step(act_dev, None, env._obs, buf["rew"][t], done_u8[t], buf["ep_ret"][t], env._ep_len, stream=st)
+                fused.filter(N, env._obs, obs, update=True, stream=st)
+            buf["done"].copy_(done_u8)
+            last_val.copy_(policy.vf(obs).squeeze(-1))
+
+    if fused is not None:
+        collect = collect_fused
     graph = None
     if cuda_graph and on_gpu:
         # an even number of simulator launches per replay keeps the MobileRobot state double buffer (swapped by the host at every
@@ -213,6 +240,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(3):
                 policy.act(obs); norm(e_obs, update=False)
+            if fused is not None:         # first launches outside the capture (one-off function attributes); they change nothing that matters:
+                fused.act(N, obs, act_dev, buf["logp"][0], buf["val"][0], stream=env.backend.stream())     # scratch rows, one sampling counter
+                fused.filter(N, env._obs, obs, update=False, stream=env.backend.stream())                   # re-normalises the current observation
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -333,7 +363,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         if verbose and rank == 0:
             print("update %d/%d  steps %d  mean episode return %.3f  episodes %d  fps %.0f" % (update, n_updates, steps, mean_ret, len(ep_returns), fps))
     if log_dir and rank == 0:
-        torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean, obs_var=norm.var), os.path.join(log_dir, "ppo2_model.pt"))
+        torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean.clone(), obs_var=norm.var.clone()), os.path.join(log_dir, "ppo2_model.pt"))
     env.close()
     train.last_policy, train.last_norm = policy, norm      # for callers that want the trained objects (tests, enjoy)
     return history

@@ -1,0 +1,131 @@
+"""
+GPU tests of the PPO2 consumer helpers (include/srl_policy.h): the sm_100a kernels against the CPU checker built from the same
+per-env header (oracle/libpolicy_ref.so, itself pinned against torch in tests/test_policy_cpu.py), against torch on the device,
+and inside the trainer (captured collection loop of three launches per env step).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_policy_cpu import REF_LIB, _policy, _ref_act, ref  # noqa: F401  (the CPU checker fixture and helpers)
+
+pytestmark = pytest.mark.gpu
+
+
+def _fused(cuda_lib, pol, D, seed, env_offset=0):
+    from rl_baselines.ppo2 import RunningNorm
+    from srl_sim.policy import FusedPolicy
+    norm = RunningNorm(D, torch.device("cuda", 0))
+    return FusedPolicy(cuda_lib, pol, norm.state, seed=seed, env_offset=env_offset), norm
+
+
+@pytest.mark.parametrize("discrete,obs_dim,n_out,n", [(True, 3, 6, 4096), (True, 2, 4, 1000), (True, 8, 8, 77), (False, 3, 3, 4096), (False, 3, 7, 333)])
+def test_policy_act_kernel_matches_checker_and_torch(cuda_lib, ref, discrete, obs_dim, n_out, n):
+    pol_cpu = _policy(obs_dim, discrete, n_out, seed=5)
+    import copy
+    pol = copy.deepcopy(pol_cpu).cuda()
+    fused, _ = _fused(cuda_lib, pol, obs_dim, seed=7, env_offset=10)
+    obs_cpu = torch.randn(n, obs_dim) * 1.5
+    obs = obs_cpu.cuda()
+    act_env = torch.zeros(n if discrete else (n, n_out), dtype=torch.int32 if discrete else torch.float32, device="cuda")
+    act_buf = torch.zeros(n if discrete else (n, n_out), dtype=torch.int64 if discrete else torch.float32, device="cuda")
+    logp, val, obs_buf = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros((n, obs_dim), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for counter in range(3):                                        # the launch itself advances the sampling counter
+        fused.act(n, obs, act_env, logp, val, obs_buf=obs_buf, act_buf=act_buf, stream=st)
+        torch.cuda.synchronize()
+        assert fused.rng.tolist()[1:] == [counter + 1, 0]
+        r_env, r_buf, r_logp, r_val, _ = _ref_act(ref, pol_cpu, obs_cpu, seed=7, counter=counter, env_offset=10)
+        assert torch.equal(obs_buf, obs)
+        assert np.abs(val.cpu().numpy() - r_val).max() < 1e-5
+        if discrete:
+            same = act_env.cpu().numpy() == r_env              # expf / tanhf differ by an ulp between host and device: a CDF boundary can move
+            assert same.mean() > 0.999 and np.array_equal(act_env.cpu().numpy(), act_buf.cpu().numpy().astype(np.int32))
+            assert np.abs(logp.cpu().numpy() - r_logp)[same].max() < 1e-5
+            with torch.no_grad():
+                t_logp = torch.log_softmax(pol.pi(obs), -1).gather(1, act_buf[:, None]).squeeze(1)
+        else:
+            assert np.abs(act_buf.cpu().numpy() - r_buf).max() < 1e-4 and np.abs(logp.cpu().numpy() - r_logp).max() < 1e-3
+            assert torch.equal(act_env, act_buf.clamp(-1, 1))
+            with torch.no_grad():
+                t_logp = torch.distributions.Normal(pol.pi(obs), pol.logstd.exp()).log_prob(act_buf).sum(-1)
+        with torch.no_grad():
+            assert (val - pol.vf(obs).squeeze(-1)).abs().max().item() < 5e-5      # cuBLAS may use TF32-free fp32 with another summation order
+        assert (logp - t_logp).abs().max().item() < 2e-4
+        if counter == 0:
+            first = act_buf.clone()
+    assert not torch.equal(first, act_buf)                          # a new counter, new samples
+
+
+def test_policy_act_sees_optimizer_updates_and_replays_in_a_graph(cuda_lib):
+    """The struct holds pointers into the live parameters, and everything a launch reads lives in device memory: a captured
+    launch replays with the updated weights and an advancing sampling counter."""
+    pol = _policy(3, True, 6, seed=1).cuda()
+    fused, _ = _fused(cuda_lib, pol, 3, seed=2)
+    n = 2048
+    obs = torch.randn(n, 3, device="cuda")
+    act_env = torch.zeros(n, dtype=torch.int32, device="cuda"); logp = torch.zeros(n, device="cuda"); val = torch.zeros(n, device="cuda")
+    fused.act(n, obs, act_env, logp, val, stream=torch.cuda.current_stream().cuda_stream)       # warm-up outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fused.act(n, obs, act_env, logp, val, stream=torch.cuda.current_stream().cuda_stream)
+    g.replay(); torch.cuda.synchronize()
+    a1, v1 = act_env.clone(), val.clone()
+    g.replay(); torch.cuda.synchronize()
+    assert fused.rng.tolist()[1] == 3 and not torch.equal(a1, act_env) and torch.equal(v1, val)
+    with torch.no_grad():
+        pol.vf[-1].bias.add_(1.0)
+    g.replay(); torch.cuda.synchronize()
+    assert (val - (v1 + 1.0)).abs().max().item() < 1e-5
+
+
+def test_obs_filter_kernel_matches_running_norm(cuda_lib):
+    from rl_baselines.ppo2 import RunningNorm
+    pol = _policy(3, True, 6, seed=1).cuda()
+    fused, norm = _fused(cuda_lib, pol, 3, seed=0)
+    expect = RunningNorm(3, torch.device("cuda", 0))
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    st = torch.cuda.current_stream().cuda_stream
+    for it, n in enumerate((4096, 4096, 1000, 37)):
+        x = torch.randn(n, 3, device="cuda", generator=gen) * torch.tensor([0.3, 2.0, 9.0], device="cuda") + (it + 1.0)
+        out = torch.zeros_like(x)
+        fused.filter(n, x, out, update=True, stream=st)
+        ref_out = expect(x)
+        torch.cuda.synchronize()
+        assert torch.allclose(norm.mean, expect.mean, rtol=0, atol=1e-11) and torch.allclose(norm.var, expect.var, rtol=1e-11, atol=1e-11)
+        assert float(norm.count) == pytest.approx(float(expect.count), rel=1e-14)
+        assert (out - ref_out).abs().max().item() < 2e-6 and out.abs().max().item() <= 10.0
+    frozen = norm.state.clone()
+    x = torch.randn(500, 3, device="cuda", generator=gen) * 40.0
+    out = torch.zeros_like(x)
+    fused.filter(500, x, out, update=False, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(norm.state, frozen) and (out - expect(x, update=False)).abs().max().item() < 2e-6
+    assert (out.abs() == 10.0).any()
+
+
+@pytest.mark.parametrize("cuda_graph", [True, False])
+def test_ppo2_with_fused_policy_step_learns(cuda_lib, cuda_graph):
+    """The trainer with fused_act=True (policy step, simulator step and observation filter = three launches per env step, captured
+    or eager) learns the shaped MobileRobot task like the torch path of tests/test_trainer_gpu.py does."""
+    from srl_sim import backend
+    backend.use_library(None, None)
+    from rl_baselines.ppo2 import train
+    hist = train("MobileRobotGymEnv-v0", 1024, 1024 * 128 * 12, seed=0, env_kwargs=dict(is_discrete=True, shape_reward=True), verbose=0,
+                 cuda_graph=cuda_graph, fused_act=True)
+    rets = [h[1] for h in hist if np.isfinite(h[1])]
+    assert rets[-1] > rets[0] + 60, rets
+
+
+@pytest.mark.parametrize("env_id,kw", [("KukaButtonGymEnv-v0", dict(is_discrete=True)), ("KukaButtonGymEnv-v0", dict(is_discrete=False)),
+                                       ("MobileRobot1DGymEnv-v0", dict(is_discrete=True))])
+def test_ppo2_with_fused_policy_step_runs_on_other_action_spaces(cuda_lib, env_id, kw):
+    from srl_sim import backend
+    backend.use_library(None, None)
+    from rl_baselines.ppo2 import train
+    hist = train(env_id, 64, 64 * 128 * 2, seed=3, env_kwargs=kw, verbose=0, fused_act=True)
+    assert len(hist) == 2 and hist[-1][0] == 64 * 128 * 2
