@@ -40,7 +40,7 @@ def test_policy_act_kernel_matches_checker_and_torch(cuda_lib, ref, discrete, ob
         assert fused.rng.tolist()[1:] == [counter + 1, 0]
         r_env, r_buf, r_logp, r_val, _ = _ref_act(ref, pol_cpu, obs_cpu, seed=7, counter=counter, env_offset=10)
         assert torch.equal(obs_buf, obs)
-        assert np.abs(val.cpu().numpy() - r_val).max() < 1e-5
+        assert (np.abs(val.cpu().numpy() - r_val) <= 1e-5 + 2e-6 * np.abs(r_val)).all()       # a few float32 ulps: values reach +-30 here
         if discrete:
             same = act_env.cpu().numpy() == r_env              # expf / tanhf differ by an ulp between host and device: a CDF boundary can move
             assert same.mean() > 0.999 and np.array_equal(act_env.cpu().numpy(), act_buf.cpu().numpy().astype(np.int32))
@@ -48,13 +48,15 @@ def test_policy_act_kernel_matches_checker_and_torch(cuda_lib, ref, discrete, ob
             with torch.no_grad():
                 t_logp = torch.log_softmax(pol.pi(obs), -1).gather(1, act_buf[:, None]).squeeze(1)
         else:
-            assert np.abs(act_buf.cpu().numpy() - r_buf).max() < 1e-4 and np.abs(logp.cpu().numpy() - r_logp).max() < 1e-3
+            assert (np.abs(act_buf.cpu().numpy() - r_buf) <= 1e-4 + 1e-5 * np.abs(r_buf)).all() and np.abs(logp.cpu().numpy() - r_logp).max() < 2e-3
             assert torch.equal(act_env, act_buf.clamp(-1, 1))
             with torch.no_grad():
                 t_logp = torch.distributions.Normal(pol.pi(obs), pol.logstd.exp()).log_prob(act_buf).sum(-1)
         with torch.no_grad():
-            assert (val - pol.vf(obs).squeeze(-1)).abs().max().item() < 5e-5      # cuBLAS may use TF32-free fp32 with another summation order
-        assert (logp - t_logp).abs().max().item() < 2e-4
+            t_val = pol.vf(obs).squeeze(-1)
+            assert ((val - t_val).abs() <= 5e-5 + 5e-6 * t_val.abs()).all().item()       # cuBLAS sums in another order
+        # Box: log-prob = -z^2 / 2 with z = (x - mean) / std; means reach +-30 and std is ~0.4, so float32 ulps of the mean show up as ~1e-4 here
+        assert (logp - t_logp).abs().max().item() < (2e-4 if discrete else 2e-3)
         if counter == 0:
             first = act_buf.clone()
     assert not torch.equal(first, act_buf)                          # a new counter, new samples
