@@ -102,3 +102,10 @@ def test_single_process_ppo2_runs_on_the_oracle_backend(use_oracle_backend):
     hist_c = ppo2.train("MobileRobotGymEnv-v0", 8, 8 * 16 * 2, seed=2, env_kwargs=dict(is_discrete=False, max_steps=20), hyperparams=dict(n_steps=16),
                         verbose=0, device=None)                        # continuous actions: the Normal policy head
     assert len(hist_c) == 2
+
+
+def test_fused_policy_step_has_no_cpu_fallback(use_oracle_backend):
+    """fused_act=True is the sm_100a kernels of include/srl_policy.h or nothing: on the CPU oracle backend the trainer refuses."""
+    from rl_baselines import ppo2
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ppo2.train("MobileRobotGymEnv-v0", 8, 8 * 16, seed=0, hyperparams=dict(n_steps=16), verbose=0, device=None, fused_act=True)
