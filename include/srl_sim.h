@@ -86,7 +86,8 @@ typedef struct srl_cfg {
                                    1 = single-env gym semantics (terminal obs, caller resets)  */
     float    max_distance;      /* Kuka safety-sphere radius (0.8); unused for MobileRobot     */
     float    timestep;          /* 0 = 1/240                                                   */
-    uint32_t reserved0;         /* must be 0 (keeps the 64-bit member aligned)                 */
+    uint32_t prefetch_resets;   /* Kuka, opt-in (0 = off): keep a ready post-reset state per env so that a lockstep
+                                   step never runs reset() inside the launch; refreshed by srl_sim_prefetch_resets  */
     uint64_t global_env_offset; /* global index of local env 0 (multi-GPU sharding)            */
 } srl_cfg;
 
@@ -163,6 +164,15 @@ int srl_sim_rollout(srl_sim* sim, int T, const void* actions, const float* noise
  * makes; bench.py's `e2e` leg times it. */
 int srl_sim_rollout_host(srl_sim* sim, int T, const void* actions, const float* noise,
                          float* obs_out, float* rew_out, uint8_t* done_out);
+
+/* Opt-in (srl_cfg.prefetch_resets): refresh the next-episode records of the envs that consumed theirs.  The post-reset state of
+ * an episode is a pure function of (seed, global env index, episode index), so it can be produced ahead of time: launch this on a
+ * SIDE stream after every srl_sim_step (it may overlap later step launches of the same handle) and join the stream when the
+ * rollout ends.  A step whose env finishes an episode then copies the record in instead of running reset()'s five random
+ * micro-steps inside the launch; if no record is ready it resets in the launch as before -- results never depend on the timing.
+ * No-op (returns 0) for handles without the feature.  Reference: the reset() a SubprocVecEnv worker runs between two steps
+ * (kuka_button_gym_env.py:214-281 via rl_baselines/utils.py:216-220). */
+int srl_sim_prefetch_resets(srl_sim* sim, void* stream);
 
 /* Debug / single-env accessors (host arrays, synchronising; not on the hot path).  Derived link-state fields
  * (SRL_F_ROBOT_POS, SRL_F_EE_POS) reflect the last step or reset; they are not recomputed by set_state. */

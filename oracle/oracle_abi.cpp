@@ -134,6 +134,14 @@ int srl_sim_rollout(srl_sim* s, int T, const void* actions, const float* noise, 
     return 0;
 }
 
+/* The CPU oracle resets inside the step (there is no launch whose latency a ready record could shorten): the entry point exists so that
+ * both libraries export the same symbols; srl_cfg.prefetch_resets is ignored here, which is the behaviour the CUDA library must reproduce. */
+int srl_sim_prefetch_resets(srl_sim* s, void* stream) {
+    (void)stream;
+    if (!s) { oracle_set_error("prefetch_resets: null handle"); return 1; }
+    return 0;
+}
+
 int srl_sim_rollout_host(srl_sim* s, int T, const void* actions, const float* noise, float* obs_out,
                          float* rew_out, uint8_t* done_out) {
     return srl_sim_rollout(s, T, actions, noise, obs_out, rew_out, done_out, NULL, NULL, NULL);

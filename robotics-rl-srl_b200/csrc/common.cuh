@@ -42,6 +42,7 @@ struct srl_sim {
     MobileDev mob_alt;  // the other half of the double buffer (rollouts write here, then swap)
     int mobile_block;   // CTA-size override (0 = heuristic)
     KukaDev* kuka;
+    void* kuka_next;    // next-episode records (kuka_kernels.cu: KukaNextHost), only with srl_cfg.prefetch_resets
     uint64_t launches;
     cudaEvent_t ev0, ev1;
     bool ev_valid;
@@ -74,5 +75,6 @@ void kuka_free(srl_sim* s);
 int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st);
 int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew,
                         uint8_t* done, float* ep_ret, int32_t* ep_len, cudaStream_t st);
+int kuka_launch_prefetch(srl_sim* s, cudaStream_t st);
 int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes);
 int kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes);

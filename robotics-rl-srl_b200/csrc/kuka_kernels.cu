@@ -32,22 +32,41 @@ struct KukaDev {
     int epw;         // live lanes per warp
 };
 
+// "Next episode" records (opt-in, srl_cfg.prefetch_resets): the post-reset state of every env's NEXT episode -- a pure function of
+// (seed, global env index, episode index) -- produced ahead of time by op = PREFETCH on a side stream, so that a LOCKSTEP step
+// whose env finishes an episode copies a record in instead of running reset()'s five random micro-steps inside the launch
+// (measured: every steady-state launch of 4096 envs contains such an env and costs 343 us instead of ~70, profiles/r01_step_launch_timing.txt).
+// Same member names as KukaDev's state arrays: env_load / env_store work on either.
+struct KukaNext {
+    float4* q[3]; float4* qd[3];
+    float4 *misc0, *misc1, *tgt, *grip, *eepos;
+    int4 *cnt, *cnt2;
+    float4* btn2;
+    uint8_t* valid;     // [N] 1 = record complete and not yet consumed
+    int32_t* episode;   // [N] episode index the record was produced for (a record for another episode is dropped)
+};
+
 namespace {
 
 constexpr float DELTA_V = 0.03f, DELTA_V_CONTINUOUS = 0.0035f, DELTA_THETA = 0.1f;   // kuka_button_gym_env.py:27-29
 constexpr double NOISE_STD = 0.01, NOISE_STD_CONTINUOUS = 0.0001, NOISE_STD_JOINTS = 0.002;   // :31-33
 constexpr int N_CONTACTS_BEFORE_TERMINATION = 5, N_STEPS_OUTSIDE_SAFETY_SPHERE = 5000, N_RANDOM_ACTIONS_AT_INIT = 5;
 
-template <bool TWOB>
-KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
+// CG: read through L2 only (__ldcg) -- for records another kernel may have completed while this one was already running
+template <bool CG, class T>
+KK_DEV T ld_state(const T* p) { return CG ? __ldcg(p) : *p; }
+
+template <bool TWOB, bool CG = false, class Arr = KukaDev>
+KK_DEV void env_load(const Arr& d, int i, KukaEnv& e) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float4 a = d.q[k][i], b = d.qd[k][i];
+        const float4 a = ld_state<CG>(d.q[k] + i), b = ld_state<CG>(d.qd[k] + i);
         e.q[4 * k] = a.x; e.q[4 * k + 1] = a.y; e.q[4 * k + 2] = a.z; e.q[4 * k + 3] = a.w;
         e.qd[4 * k] = b.x; e.qd[4 * k + 1] = b.y; e.qd[4 * k + 2] = b.z; e.qd[4 * k + 3] = b.w;
     }
-    const float4 m0 = d.misc0[i], m1 = d.misc1[i], tg = d.tgt[i], gr = d.grip[i], ep = d.eepos[i];
-    const int4 c = d.cnt[i], c2 = d.cnt2[i];
+    const float4 m0 = ld_state<CG>(d.misc0 + i), m1 = ld_state<CG>(d.misc1 + i), tg = ld_state<CG>(d.tgt + i), gr = ld_state<CG>(d.grip + i),
+                 ep = ld_state<CG>(d.eepos + i);
+    const int4 c = ld_state<CG>(d.cnt + i), c2 = ld_state<CG>(d.cnt2 + i);
     e.ee[0] = m0.x; e.ee[1] = m0.y; e.ee[2] = m0.z; e.qb = m0.w;
     e.qdb = m1.x; e.bbx = m1.y; e.bby = m1.z; e.ep_ret = m1.w;
     e.tgt[0] = tg.x; e.tgt[1] = tg.y; e.tgt[2] = tg.z; e.bbz = tg.w;
@@ -59,15 +78,15 @@ KK_DEV void env_load(const KukaDev& d, int i, KukaEnv& e) {
     e.by64 = __hiloint2double(c2.w, __float_as_int(ep.w));
     e.qb2 = 0.f; e.qdb2 = 0.f; e.bb2x = 0.f; e.bb2y = 0.f; e.n_contacts2 = 0; e.goal_id = 0; e.cany0 = 0; e.cany1 = 0;
     if (TWOB) {
-        const float4 b2 = d.btn2[i];
+        const float4 b2 = ld_state<CG>(d.btn2 + i);
         e.qb2 = b2.x; e.qdb2 = b2.y; e.bb2x = b2.z; e.bb2y = b2.w;
         e.n_contacts2 = c2.w; e.by64 = 0.0;
         e.cany0 = (c.w >> 3) & 1; e.cany1 = (c.w >> 4) & 1; e.goal_id = (c.w >> 5) & 1;
     }
 }
 
-template <bool TWOB>
-KK_DEV void env_store(const KukaDev& d, int i, const KukaEnv& e) {
+template <bool TWOB, class Arr = KukaDev>
+KK_DEV void env_store(const Arr& d, int i, const KukaEnv& e) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         d.q[k][i] = make_float4(e.q[4 * k], e.q[4 * k + 1], e.q[4 * k + 2], e.q[4 * k + 3]);
@@ -176,7 +195,7 @@ KK_DEV int env_index(int n, int epw) {
     return i < n ? i : -1;
 }
 
-enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2 };
+enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2, KUKA_OP_PREFETCH = 3 };
 
 // ONE kernel for reset, lockstep step and fused T-step rollout.  Every thread runs a single micro-step loop
 //     forward kinematics + collision detection  ->  [finish the env step whose physics just ran: reward, done,
@@ -186,16 +205,20 @@ enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2 };
 //   op = ROLLOUT: T env steps (step() + step2() + _reward() + _termination() + VecEnv auto-reset)
 //   op = RESET  : reset() of the masked envs with optional host-supplied draws
 //   op = SETTLE : the 500 zero-action steps of reset() (:242-247), identical for every episode -> snapshot
-template <bool JOINTS, bool TWOB>
+//   op = PREFETCH (PREFETCH instantiation only): reset() of the env's NEXT episode into its `nx` record, for the envs whose record is
+//                 not valid -- the very instructions of the in-launch reset, so a record and an in-launch reset agree bit for bit
+// PREFETCH = false (the default instantiations): `nx` is ignored and the kernel is what it was before the feature existed.
+template <bool JOINTS, bool TWOB, bool PREFETCH = false>
 __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
                                                        const void* __restrict__ actions, const float* __restrict__ noise,
                                                        const uint8_t* __restrict__ mask, const double* __restrict__ draws,
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done, float* __restrict__ ep_ret,
-                                                       int32_t* __restrict__ ep_len, float* __restrict__ snap) {
+                                                       int32_t* __restrict__ ep_len, float* __restrict__ snap, const KukaNext nx) {
     const int i = env_index(n, d.epw);
     if (i < 0) return;
     if (op == KUKA_OP_RESET && mask && !mask[i]) return;
+    if constexpr (PREFETCH) { if (op == KUKA_OP_PREFETCH && nx.valid[i]) return; }
     const KukaParams& P = d.P;
     const uint64_t genv = P.env_offset + (uint64_t)i;
     const size_t N = (size_t)n;
@@ -223,6 +246,13 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         e.qb = 0.f; e.qdb = 0.f; e.bbx = P.btn_base[0]; e.bby = P.btn_base[1]; e.bbz = P.btn_base[2]; e.bspeed = 0.f; e.by64 = 0.0;
         if (TWOB) { e.qb2 = 0.f; e.qdb2 = 0.f; e.bb2x = P.btn_base[0]; e.bb2y = -P.btn_base[1]; }
         in_reset = true; reset_left = 500;
+    }
+    bool consumed = false;       // PREFETCH: the env just took its next-episode record (reset_end is already part of it)
+    if constexpr (PREFETCH) {
+        if (op == KUKA_OP_PREFETCH) {   // e.episode (live state) is the index the env's next reset() will draw with
+            reset_begin<TWOB>(P, e, nullptr, genv);
+            in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
+        }
     }
     for (;;) {
         kuka_fk<true, TWOB>(P, e, k, ct);  // link states of the configuration just reached + collision detection for the next step
@@ -275,6 +305,22 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 if (ep_len) ep_len[off] = e.ep_len;
             }
             if (is_done && P.auto_reset) {   // SubprocVecEnv worker: reset and return the post-reset observation
+                if constexpr (PREFETCH) {
+                    if (op == KUKA_OP_ROLLOUT && reinterpret_cast<volatile const uint8_t*>(nx.valid)[i]) {
+                        __threadfence();     // the record was written before the flag (message passing with op = PREFETCH)
+                        const bool match = reinterpret_cast<volatile const int32_t*>(nx.episode)[i] == (int)e.episode;
+                        reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 0;   // consumed, or produced for another episode (explicit reset in between): refreshed by the next PREFETCH
+                        if (match) {
+                            const uint32_t total_steps = e.total_steps;         // the only field that runs across episodes
+                            env_load<TWOB, true>(nx, i, e);
+                            e.total_steps = total_steps;
+                            saved_cb = e.cbutton; saved_ct = e.ctable;           // what the in-launch reset leaves behind: the manifold flags of its last micro-step
+                            if (TWOB) { saved_a0 = e.cany0; saved_a1 = e.cany1; }
+                            consumed = true; in_reset = true; reset_left = 0;
+                            continue;          // kinematics of the post-reset configuration, then the observation (below)
+                        }
+                    }
+                }
                 d17 = nullptr;
                 reset_begin<TWOB>(P, e, nullptr, genv);
                 in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
@@ -290,7 +336,8 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 snap[24] = e.ee[0]; snap[25] = e.ee[1]; snap[26] = e.ee[2]; snap[27] = e.qb; snap[28] = e.qdb;
                 return;
             }
-            reset_end<TWOB>(P, e);
+            if (!(PREFETCH && consumed)) reset_end<TWOB>(P, e);
+            consumed = false;
             if (obs) {  // getSRLState after reset (:278-279)
                 float* o = obs + 3 * (op == KUKA_OP_RESET ? (size_t)i : (size_t)t * N + (size_t)i);
                 o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2];
@@ -387,6 +434,15 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     }
     e.cbutton = saved_cb; e.ctable = saved_ct;
     if (TWOB) { e.cany0 = saved_a0; e.cany1 = saved_a1; }
+    if constexpr (PREFETCH) {
+        if (op == KUKA_OP_PREFETCH) {      // record first, then the episode it is for, then the flag
+            env_store<TWOB>(nx, i, e);
+            nx.episode[i] = (int)e.episode - 1;
+            __threadfence();
+            reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 1;
+            return;
+        }
+    }
     env_store<TWOB>(d, i, e);
 }
 
@@ -477,11 +533,17 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
 #define KUKA_LAUNCH(d, grid, block, st, ...)                                                                            \
     do {                                                                                                                \
         if ((d)->P.two_buttons) {                                                                                       \
-            if ((d)->P.action_joints) kuka_kernel<true, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                \
-            else kuka_kernel<false, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                                    \
-        } else if ((d)->P.action_joints) kuka_kernel<true, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);            \
-        else kuka_kernel<false, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__);                                       \
+            if ((d)->P.action_joints) kuka_kernel<true, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});    \
+            else kuka_kernel<false, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});                        \
+        } else if ((d)->P.action_joints) kuka_kernel<true, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{}); \
+        else kuka_kernel<false, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});                           \
     } while (0)
+
+// Host-side owner of the next-episode records of one handle (srl_sim::kuka_next); the kernel gets the pointer block by value.
+struct KukaNextHost {
+    KukaNext nx;
+    bool enabled;
+};
 
 void grid_for(const srl_sim* s, const KukaDev* d, int& grid, int& block) {
     const int warps = (s->n + d->epw - 1) / d->epw;
@@ -525,6 +587,20 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
     for (int i = 0; i < KK_NB; ++i) { d->P.snap_q[i] = h[i]; d->P.snap_qd[i] = h[KK_NB + i]; }
     d->P.snap_ee[0] = h[24]; d->P.snap_ee[1] = h[25]; d->P.snap_ee[2] = h[26]; d->P.snap_qb = h[27]; d->P.snap_qdb = h[28];
     s->launches += 1;
+    // opt-in next-episode records (single-button kinds with IK actions and auto-reset: the instantiation that exists)
+    if (s->cfg.prefetch_resets && s->auto_reset && !d->P.two_buttons && !d->P.action_joints) {
+        KukaNextHost* nh = new KukaNextHost();
+        memset(nh, 0, sizeof(*nh));
+        s->kuka_next = nh;
+        KukaNext& nx = nh->nx;
+        float4** g4[] = {&nx.q[0], &nx.q[1], &nx.q[2], &nx.qd[0], &nx.qd[1], &nx.qd[2], &nx.misc0, &nx.misc1, &nx.tgt, &nx.grip, &nx.eepos, &nx.btn2};
+        for (float4** p : g4) { SRL_CUDA_OK(cudaMalloc(p, N * sizeof(float4))); SRL_CUDA_OK(cudaMemset(*p, 0, N * sizeof(float4))); }
+        SRL_CUDA_OK(cudaMalloc(&nx.cnt, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(nx.cnt, 0, N * sizeof(int4)));
+        SRL_CUDA_OK(cudaMalloc(&nx.cnt2, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(nx.cnt2, 0, N * sizeof(int4)));
+        SRL_CUDA_OK(cudaMalloc(&nx.valid, N)); SRL_CUDA_OK(cudaMemset(nx.valid, 0, N));
+        SRL_CUDA_OK(cudaMalloc(&nx.episode, N * sizeof(int32_t))); SRL_CUDA_OK(cudaMemset(nx.episode, 0xff, N * sizeof(int32_t)));
+        nh->enabled = true;
+    }
     return 0;
 }
 
@@ -535,6 +611,14 @@ void kuka_free(srl_sim* s) {
     cudaFree(d->misc0); cudaFree(d->misc1); cudaFree(d->tgt); cudaFree(d->grip); cudaFree(d->eepos); cudaFree(d->cnt); cudaFree(d->cnt2); cudaFree(d->btn2);
     delete d;
     s->kuka = nullptr;
+    if (KukaNextHost* nh = static_cast<KukaNextHost*>(s->kuka_next)) {
+        KukaNext& nx = nh->nx;
+        for (int k = 0; k < 3; ++k) { cudaFree(nx.q[k]); cudaFree(nx.qd[k]); }
+        cudaFree(nx.misc0); cudaFree(nx.misc1); cudaFree(nx.tgt); cudaFree(nx.grip); cudaFree(nx.eepos); cudaFree(nx.cnt); cudaFree(nx.cnt2);
+        cudaFree(nx.btn2); cudaFree(nx.valid); cudaFree(nx.episode);
+        delete nh;
+        s->kuka_next = nullptr;
+    }
 }
 
 int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, float* obs, cudaStream_t st) {
@@ -549,8 +633,25 @@ int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noi
                         float* ep_ret, int32_t* ep_len, cudaStream_t st) {
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
-    KUKA_LAUNCH(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
+    const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);
+    if (nh && nh->enabled)      // the rollout path that takes a ready next-episode record instead of resetting inside the launch
+        kuka_kernel<false, false, true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nh->nx);
+    else
+        KUKA_LAUNCH(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Refresh the next-episode records of the envs that consumed theirs (or never had one).  Asynchronous on `st`; meant for a side stream, it may
+// run concurrently with step / rollout launches of the same handle (flag + fence hand-over, see KukaNext).  A no-op when the feature is off.
+int kuka_launch_prefetch(srl_sim* s, cudaStream_t st) {
+    KukaDev* d = s->kuka;
+    const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);
+    if (!nh || !nh->enabled) return 0;
+    int grid, block; grid_for(s, d, grid, block);
+    kuka_kernel<false, false, true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_PREFETCH, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nh->nx);
+    SRL_CUDA_OK(cudaGetLastError());
+    s->launches += 1;
     return 0;
 }
 

@@ -197,6 +197,13 @@ int srl_sim_rollout(srl_sim* s, int T, const void* actions, const float* noise, 
     return launch_rollout(s, T, actions, noise, obs_out, rew_out, done_out, ep_ret_out, ep_len_out, (cudaStream_t)stream);
 }
 
+int srl_sim_prefetch_resets(srl_sim* s, void* stream) {
+    if (!s) { srl_set_error("prefetch_resets: null handle"); return 1; }
+    if (!srl_is_kuka(s->kind)) return 0;
+    DeviceGuard guard(s->device);
+    return kuka_launch_prefetch(s, (cudaStream_t)stream);
+}
+
 int srl_sim_rollout_host(srl_sim* s, int T, const void* actions, const float* noise, float* obs_out, float* rew_out,
                          uint8_t* done_out) {
     if (!s) { srl_set_error("rollout_host: null handle"); return 1; }

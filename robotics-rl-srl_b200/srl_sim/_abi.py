@@ -61,7 +61,7 @@ class SrlCfg(Structure):
         ("no_auto_reset", c_int32),
         ("max_distance", c_float),
         ("timestep", c_float),
-        ("reserved0", c_uint32),
+        ("prefetch_resets", c_uint32),
         ("global_env_offset", c_uint64),
     ]
 
@@ -78,6 +78,7 @@ _EXPORTS = [
     ("srl_sim_step", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("srl_sim_rollout", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("srl_sim_rollout_host", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("srl_sim_prefetch_resets", c_int, [c_void_p, c_void_p]),
     ("srl_sim_get_state", c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     ("srl_sim_set_state", c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     ("srl_sim_launch_count", c_uint64, [c_void_p]),
@@ -166,7 +167,7 @@ class Sim(object):
         c.no_auto_reset = int(cfg.pop("no_auto_reset", False))
         c.max_distance = float(cfg.pop("max_distance", 0.8))
         c.timestep = float(cfg.pop("timestep", 0.0))
-        c.reserved0 = 0
+        c.prefetch_resets = int(bool(cfg.pop("prefetch_resets", False)))
         c.global_env_offset = int(cfg.pop("global_env_offset", 0))
         if cfg:
             raise TypeError("unknown cfg keys: %s" % sorted(cfg))
@@ -218,6 +219,11 @@ class Sim(object):
         rc = self._lib.srl_sim_rollout_host(self.handle, int(T), _ptr(actions), _ptr(noise), _ptr(obs_out),
                                             _ptr(rew_out), _ptr(done_out))
         self.library.check(rc, "srl_sim_rollout_host")
+
+    def prefetch_resets(self, stream=None):
+        """Refresh the next-episode records (handles created with ``prefetch_resets=True``; a no-op otherwise).  Meant for a side stream."""
+        rc = self._lib.srl_sim_prefetch_resets(self.handle, stream)
+        self.library.check(rc, "srl_sim_prefetch_resets")
 
     # -- state access ------------------------------------------------------------------------
     def get_state(self, field):

@@ -64,7 +64,7 @@ class BatchedSRLVecEnv(object):
             two = env_id == "Kuka2ButtonGymEnv-v0"     # its constructor defaults differ (kuka_2button_gym_env.py:30-31)
             cfg["max_distance"] = env_kwargs.get("max_distance", 2.0 if two else 0.8)
             cfg["force_down"] = env_kwargs.get("force_down", not two)
-        for k in ("max_steps", "envs_per_warp", "solver_iterations"):
+        for k in ("max_steps", "envs_per_warp", "solver_iterations", "prefetch_resets"):
             if k in env_kwargs:
                 cfg[k] = env_kwargs[k]
         self.sim = self.backend.make_sim(env_id, self.num_envs, seed=seed, model_blob=blob, **cfg)
