@@ -131,7 +131,7 @@ def allreduce_mean_gradients(params, dist, world):
 
 
 def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True,
-          phase_times=None, fused_act=False, prefetch_resets=False):
+          phase_times=None, fused_act=False, prefetch_resets=False, episode_window=40):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
     ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
@@ -375,7 +375,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         t_ph = tick("optimise", t_ph)
         steps = update * N * T * world
         fps = steps / (time.time() - t_start)
-        window = ep_returns[-max(40, N):]                                  # episode_window (train.py:180)
+        window = ep_returns[-max(episode_window, N):]                      # --episode_window (train.py:182), at least one episode per env
         if dist is not None:
             from srl_sim.distributed import allgather_episode_stats
             mean_ret, n_ep = allgather_episode_stats(float(np.sum(window)), len(window), device=dev if on_gpu else None)

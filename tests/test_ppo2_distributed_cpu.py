@@ -109,3 +109,24 @@ def test_fused_policy_step_has_no_cpu_fallback(use_oracle_backend):
     from rl_baselines import ppo2
     with pytest.raises(ValueError, match="no CPU fallback"):
         ppo2.train("MobileRobotGymEnv-v0", 8, 8 * 16, seed=0, hyperparams=dict(n_steps=16), verbose=0, device=None, fused_act=True)
+
+
+def test_train_entry_point_flags_on_the_oracle_backend(use_oracle_backend, tmp_path):
+    """`python -m rl_baselines.train` with the reference's flag names (train.py:177-208): `--hyperparam name:value` pairs are typed and
+    checked like base_classes.parserHyperParam does, `-joints` needs `-c`, the run directory gets args.json / env_globals.json / the model."""
+    import glob
+    import json
+    from rl_baselines.train import main, parserHyperParam
+    assert parserHyperParam(["n_steps:16", "gamma:0.9"]) == {"n_steps": 16, "gamma": 0.9}
+    with pytest.raises(AssertionError, match="not in list of valid hyperparameters"):
+        parserHyperParam(["batch:3"])
+    with pytest.raises(ValueError, match="continuous only"):
+        main(["--env", "KukaButtonGymEnv-v0", "-joints", "--device", "-1"])
+    hist = main(["--algo", "ppo2", "--env", "MobileRobotGymEnv-v0", "--num-cpu", "8", "--num-timesteps", "300", "--hyperparam", "n_steps:16", "noptepochs:2",
+                 "--episode_window", "5", "-r", "--shape-reward", "--log-dir", str(tmp_path), "--device", "-1", "--seed", "4"])
+    assert [h[0] for h in hist] == [128, 256]                        # 1.1 x 300 steps (train.py:319) in updates of 8 envs x 16 steps
+    run = glob.glob(os.path.join(str(tmp_path), "MobileRobotGymEnv-v0", "ground_truth", "ppo2", "*"))[0]
+    args = json.load(open(os.path.join(run, "args.json")))
+    assert args["n_steps"] == 16 and args["noptepochs"] == 2 and args["num_cpu"] == 8 and args["seed"] == 4
+    assert json.load(open(os.path.join(run, "env_globals.json")))["random_target"] is True
+    assert os.path.isfile(os.path.join(run, "ppo2_model.pt"))
