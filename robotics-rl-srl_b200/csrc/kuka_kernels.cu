@@ -309,11 +309,14 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                     if (op == KUKA_OP_ROLLOUT && reinterpret_cast<volatile const uint8_t*>(nx.valid)[i]) {
                         __threadfence();     // the record was written before the flag (message passing with op = PREFETCH)
                         const bool match = reinterpret_cast<volatile const int32_t*>(nx.episode)[i] == (int)e.episode;
-                        reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 0;   // consumed, or produced for another episode (explicit reset in between): refreshed by the next PREFETCH
                         if (match) {
                             const uint32_t total_steps = e.total_steps;         // the only field that runs across episodes
                             env_load<TWOB, true>(nx, i, e);
                             e.total_steps = total_steps;
+                            __threadfence();   // the record is read before the flag is cleared: a PREFETCH thread that sees 0 may overwrite it
+                        }
+                        reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 0;   // consumed, or produced for another episode (explicit reset in between): refreshed by the next PREFETCH
+                        if (match) {
                             saved_cb = e.cbutton; saved_ct = e.ctable;           // what the in-launch reset leaves behind: the manifold flags of its last micro-step
                             if (TWOB) { saved_a0 = e.cany0; saved_a1 = e.cany1; }
                             consumed = true; in_reset = true; reset_left = 0;
