@@ -2,11 +2,11 @@
 """
 bench.py -- env-steps/sec of the B200-native batched simulator (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload kuka|mobile]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload kuka|mobile] [--no-secondary]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-Default workload = BASELINE.json configs[1]: KukaButtonGymEnv-v0, ground_truth, 4096 envs per GPU,
+Headline workload = BASELINE.json configs[1]: KukaButtonGymEnv-v0, ground_truth, 4096 envs per GPU,
 synthetic random discrete actions + N(0, 0.01) step noise.  One bench "step" = ONE fused rollout of
 T = 128 env steps over the whole batch (the n_steps of the reference's PPO2 runner,
 rl_baselines/rl_algorithm/ppo2.py:58-72): a single kernel launch, 4096 x 128 env-steps.
@@ -14,12 +14,18 @@ rl_baselines/rl_algorithm/ppo2.py:58-72): a single kernel launch, 4096 x 128 env
   value : env-steps/s, actions/noise already resident in HBM, outputs left in HBM (CUDA events, max over ranks)
   e2e   : the same metric through the host-facing C-ABI call (srl_sim_rollout_host): pinned HOST action/noise
           buffers in, pinned HOST obs/reward/done out, copies inside the timed region
-  roofline     : algorithmic HBM bytes of one launch / device time of that launch vs the measured copy peak
+  roofline     : what bounds the dominant kernel, computed from THIS run's launch time and the committed ncu capture of
+                 the very same SASS (profiles/r02_*_ncu.json; the ncu-derived terms are withheld when the hash differs)
   cpu_baseline : the CPU oracle (double precision, oracle/liboracle_sim.so, kind "port") on the host cores
+  secondary    : the other two measurable BASELINE.json configs, in the same line so that the driver's record carries them:
+                 mobile_config4   = configs[3], MobileRobotGymEnv-v0, 8192 envs/GPU, T = 1024 fused rollouts, at every N
+                 plumbing_config1 = configs[0], MobileRobotGymEnv-v0, 4 env OBJECTS behind the reference-shaped
+                                    (Dummy)VecEnv plumbing, random agent, 1600 steps (rank 0)
   --impl reference : the reference arm.  PyBullet is not installable here, so it times the oracle -- the CPU
-          restatement of the reference's step -- with every host thread, on the same config.
+          restatement of the reference's step -- with every host thread, on the same configs.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,10 +44,15 @@ MOBILE_ENVS_PER_GPU = 8192    # BASELINE.json configs[3]
 # Algorithmic HBM bytes (DESIGN.md "Measurement"): SoA state in + out once per launch, per-step I/O floor.
 KUKA_STATE_BYTES = 2 * 224            # 12 float4 + 2 int4 records, read + written once per launch
 KUKA_STEP_BYTES = 4 + 4 + 12 + 4 + 1  # action i32 + noise f32 in, obs f32[3] + reward f32 + done u8 out
-KUKA_WARP_INST_PER_LAUNCH = 3904811262  # ncu smsp__inst_executed.sum of one 4096-env x 128-step launch (profiles/r01_kuka_kernel_ncu_full.txt)
-KUKA_FLOP_PER_STEP = 1.0e5            # ~150 PGS sweeps x 13 rows x 2 x 13 + dynamics
+# Algorithmic fp32 work of one Kuka env step = one applyAction + stepSimulation in steady state (no active contact):
+#   150 sweeps x [12 motor rows x (2 x 12 flop velocity update + 6 flop row) + 3 button rows x 8 flop] = 150 x 384 = 57 600
+#   + once per step: FK 3.2 k, CRBA + RNEA 4.8 k, Cholesky + M^-1 2.2 k, IK (7x7 normal equations) 2.4 k, rows / integration 0.6 k = 13.2 k
+# SURVEY.md 8(d) quotes 1.6e5: it assumed 20 constraint rows of width 50 (contact, friction and limit rows always present);
+# in steady state the solve has 15 rows of width 12, which is what the kernel (and PyBullet) actually iterates.
+KUKA_FLOP_PER_STEP = 150 * (12 * (2 * 12 + 6) + 3 * 8) + 13200   # 70 800
 MOBILE_STATE_BYTES = 2 * 80
 MOBILE_STEP_BYTES = 4 + 8 + 4 + 1     # action in, obs f32[2] + reward + done out (in-kernel actions: no action read)
+FP32_LANES_PER_SM = 128
 
 
 def effective_cores():
@@ -67,39 +78,71 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed regions (B200_PROFILING.md recipe), through NVML at ~100 Hz (a bench of 20
+    launches lasts ~0.15 s: nvidia-smi at 5 Hz saw one sample of it); falls back to nvidia-smi polling when NVML is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
-        self.samples = []
+        self.sm, self.mx, self.reasons, self.n = [], [], set(), 0
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._phys = phys
+        except Exception:
+            self._nvml = None
+            self._phys = gpu_index
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+        self.n += 1
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self._phys)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            s = [x.strip() for x in out.split(",")]
+            if s[1].replace(".", "").isdigit():
+                self.sm.append(float(s[1]))
+            if s[2].replace(".", "").isdigit():
+                self.mx.append(float(s[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+            self.n += 1
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.01 if self._nvml is not None else 0.2)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons), "samples": self.n,
+                "source": "nvml @100 Hz over the device-timed and the e2e region" if self._nvml is not None else "nvidia-smi @5 Hz"}
 
 
 def make_inputs(workload, n, T, seed):
@@ -139,14 +182,91 @@ def model_blob(workload):
     return load_kuka_scene().blob
 
 
+# ------------------------------------------------------------------- committed ncu captures, keyed by SASS hash ----
+KERNEL_PATTERN = {"kuka": "kuka_kernelILb0ELb0ELb0E", "mobile": "mobile_rollout_kernelILi4ELb1ELb0ELb0ELb1E"}
+
+
+def kernel_sass_sha16(lib_path, workload):
+    """sha256 (16 hex digits) of the SASS of the workload's dominant kernel as shipped in `lib_path` (cuobjdump -sass, the text of that
+    one function with addresses / encodings).  The ncu-derived constants of the roofline block are only valid for this exact code."""
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    pat, keep, lines = KERNEL_PATTERN[workload], False, []
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            keep = pat in ln
+        if keep:
+            lines.append(ln.rstrip())
+    if not lines:
+        return None
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()[:16]
+
+
+def load_profile(workload, lib_path):
+    """profiles/r02_<workload>_ncu.json (written by scripts/ncu_to_json.py from an `ncu --set full` capture of this bench) if it was taken
+    from the SASS that is loaded now; otherwise (None, reason)."""
+    p = os.path.join(ROOT, "profiles", "r02_%s_ncu.json" % workload)
+    if not os.path.isfile(p):
+        return None, "no committed capture (%s)" % os.path.relpath(p, ROOT)
+    with open(p) as f:
+        prof = json.load(f)
+    sha = kernel_sass_sha16(lib_path, workload)
+    if sha is None:
+        return None, "cuobjdump unavailable: cannot check that the capture matches the loaded kernel"
+    if prof.get("sass_sha16") != sha:
+        return None, "stale capture: %s was taken from SASS %s, the loaded kernel is %s" % (os.path.basename(p), prof.get("sass_sha16"), sha)
+    return prof, "profiles/%s (sass %s)" % (os.path.basename(p), sha)
+
+
+def roofline_block(workload, spec, n, T, launch_s, clocks, lib_path, sms):
+    peaks, peak_src = _peaks()
+    launch_bytes = n * (spec["state_bytes"] + T * spec["step_bytes"])
+    hbm_ach = launch_bytes / launch_s / 1e9
+    prof, prof_note = load_profile(workload, lib_path)
+    hbm = {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+           "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_src, "algorithmic_bytes_per_launch": launch_bytes}
+    traffic = prof.get("dram_bytes_per_launch") if prof else None
+    if workload != "kuka":
+        roof = dict(hbm)
+        roof.update({"bound": "hbm", "traffic": traffic, "kernel": "mobile_rollout_kernel", "ncu_capture": prof_note})
+        if prof:
+            roof["note"] = ("frac is by ALGORITHMIC bytes; ncu saw %.1f MB reach DRAM per launch (the rest of the outputs is still in the 126 MB L2 "
+                            "when the kernel ends), so part of this rate is L2-assisted" % (traffic / 1e6))
+        return roof
+    clk_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    issue_peak = sms * 4 * clk_mhz * 1e-3                       # G warp-instructions/s: one per scheduler per cycle
+    fp32_peak = sms * FP32_LANES_PER_SM * 2 * clk_mhz * 1e-6    # TFLOP/s, theoretical (no fp32 peak in MEASURED_PEAKS.json)
+    fl = n * T * KUKA_FLOP_PER_STEP / launch_s / 1e12
+    roof = {"bound": "fp32-issue", "unit": "G warp-inst/s", "peak": issue_peak, "achieved": None, "frac": None, "lane_util": None,
+            "useful_lane_frac": None, "traffic": traffic, "kernel": "kuka_kernel", "ncu_capture": prof_note,
+            "peak_source": "SMs x 4 schedulers x SM clock under load (%d x 4 x %.0f MHz)" % (sms, clk_mhz),
+            "fp32": {"achieved": fl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fl / fp32_peak, "flop_per_env_step": KUKA_FLOP_PER_STEP,
+                     "peak_source": "theoretical: SMs x 128 lanes x 2 x SM clock (MEASURED_PEAKS.json has no fp32 figure)"},
+            "hbm": hbm,
+            "note": "issue-bound fp32 kernel (150 strictly sequential PGS sweeps per env step), not HBM-bound; frac = warp instructions issued / "
+                    "issue slots, lane_util = live threads per warp instruction / 32, useful_lane_frac = frac x lane_util"}
+    if prof:
+        ach = prof["warp_inst_per_launch"] / launch_s / 1e9
+        roof.update({"achieved": ach, "frac": ach / issue_peak, "lane_util": prof["threads_per_warp_inst"] / 32.0,
+                     "useful_lane_frac": ach / issue_peak * prof["threads_per_warp_inst"] / 32.0,
+                     "warp_inst_per_launch": prof["warp_inst_per_launch"]})
+    return roof
+
+
 # ------------------------------------------------------------------------------- CPU oracle legs --------
-def _oracle_backend():
+def _oracle_library():
     from srl_sim._abi import SimLibrary
-    from srl_sim.backend import Backend
     path = os.path.join(ROOT, "oracle", "liboracle_sim.so")
     if not os.path.isfile(path):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    return Backend(SimLibrary(path), -1)
+    return SimLibrary(path)
+
+
+def _oracle_backend():
+    from srl_sim.backend import Backend
+    return Backend(_oracle_library(), -1)
 
 
 class OraclePool(object):
@@ -182,11 +302,14 @@ class OraclePool(object):
         return time.perf_counter() - t0
 
 
+def cpu_sample_T(workload):
+    return workload_spec(workload)["T"] if workload == "kuka" else 256
+
+
 def cpu_baseline(workload, cores):
     spec = workload_spec(workload)
     # bounded sample: a slice of the same workload worth ~10-30 s of single-core work
-    T = spec["T"] if workload == "kuka" else 256
-    n = spec["n"] if workload == "kuka" else spec["n"]
+    T, n = cpu_sample_T(workload), spec["n"]
     pool = OraclePool(workload, n, T, cores)
     pool.step()  # warm-up (page in, caches)
     dt = min(pool.step() for _ in range(2))
@@ -195,58 +318,95 @@ def cpu_baseline(workload, cores):
                       "loop), %d host threads" % (n, T, spec["env_id"], pool.threads)}
 
 
+def plumbing_config1(library, device, steps=1600, num_cpu=4, seed=0):
+    """BASELINE.json configs[0] / BASELINE.md B3: MobileRobotGymEnv-v0, ground_truth, 4 env OBJECTS behind the reference-shaped VecEnv
+    plumbing (createEnvs -> makeEnv thunks -> DummyVecEnv -> VecFrameStack -> VecNormalize), stepped by the random agent's loop
+    (/root/reference/rl_baselines/random_agent.py:28-42) for 1600 env steps (/root/reference/tests/test_pipeline.py:14, NUM_TIMESTEP).
+    `library`/`device`: the sm_100a library on a GPU (product) or the oracle with device -1 (reference arm)."""
+    import types
+    from srl_sim import backend as srl_backend
+    from rl_baselines.utils import createEnvs
+    prev = srl_backend._override
+    srl_backend.use_library(library, device)
+    try:
+        args = types.SimpleNamespace(env="MobileRobotGymEnv-v0", num_cpu=num_cpu, seed=seed, num_stack=1, srl_model="ground_truth",
+                                     per_env_objects=True, log_dir=None)
+        envs = createEnvs(args, env_kwargs=dict(is_discrete=True))
+        envs.action_space.seed(seed)
+        envs.reset()
+        n_updates = steps // num_cpu
+        for _ in range(20):                                              # warm-up
+            envs.step([envs.action_space.sample() for _ in range(num_cpu)])
+        t0 = time.perf_counter()
+        ndone = 0
+        for _ in range(n_updates):
+            _, _, dones, _ = envs.step([envs.action_space.sample() for _ in range(num_cpu)])
+            ndone += int(np.sum(dones))
+        dt = time.perf_counter() - t0
+        envs.close()
+    finally:
+        srl_backend._override = prev
+    return {"metric": "env-steps/sec MobileRobotGymEnv-v0 ground_truth, %d env objects, random agent (reference-shaped VecEnv plumbing)" % num_cpu,
+            "value": n_updates * num_cpu / dt, "unit": "env-steps/s", "env_steps": n_updates * num_cpu, "episodes_finished": ndone,
+            "launches_per_env_step": 1, "note": "one N=1 simulator launch + one synchronising read-back per env object and step: Python / launch-latency bound"}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's own step on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    spec = workload_spec(args.workload)
     cores = effective_cores()
-    n, T = spec["n"], spec["T"] if args.workload == "kuka" else 256
-    pool = OraclePool(args.workload, n, T, cores)
-    for _ in range(args.warmup):
-        pool.step()
-    times = [pool.step() for _ in range(args.steps)]
-    total = sum(times)
+
+    def run(workload, steps, warmup):
+        spec = workload_spec(workload)
+        n, T = spec["n"], cpu_sample_T(workload)
+        pool = OraclePool(workload, n, T, cores)
+        for _ in range(warmup):
+            pool.step()
+        times = [pool.step() for _ in range(steps)]
+        return n, T, pool.threads, sum(times)
+
+    spec = workload_spec(args.workload)
+    n, T, threads, total = run(args.workload, args.steps, args.warmup)
     value = n * T * args.steps / total
     sample = ("%d envs x %d steps per step, %d host threads (container CPU quota; %d CPUs visible), CPU oracle "
-              "(PyBullet itself is not installable offline)" % (n, T, pool.threads, os.cpu_count() or 1))
+              "(PyBullet itself is not installable offline)" % (n, T, threads, os.cpu_count() or 1))
     metric, config = metric_and_config(args.workload, 1)
-    config["parallelism"] = "%d host threads, one env shard each (rank 0 only)" % pool.threads
-    config.pop("l2_flush_between_steps")           # a CPU run: nothing to flush
+    config["parallelism"] = "%d host threads, one env shard each (rank 0 only)" % threads
+    config["l2_flush_between_steps"] = "n/a (CPU run)"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        config["reference_shard"] = ("rank 0 alone steps ONE %d-env shard on all host threads (the CPU is saturated by it); the b200 arm steps one shard per GPU "
+                                     "-- the two lines compare throughput with throughput" % n)
     if T != spec["T"]:
         config["reference_sample"] = "bounded sample: %d of the %d env steps per bench step" % (T, spec["T"])
     line = {"impl": "reference", "metric": metric, "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": pool.threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_secondary and args.workload == "kuka":
+        sec = {}
+        mn, mT, mth, mtot = run("mobile", 3, 1)
+        sec["mobile_config4"] = {"metric": metric_and_config("mobile", 1)[0], "value": mn * mT * 3 / mtot, "unit": "env-steps/s", "cores": mth,
+                                 "sample": "%d envs x %d steps per step x 3 (bounded sample of the T=1024 rollout), CPU oracle" % (mn, mT)}
+        sec["plumbing_config1"] = plumbing_config1(_oracle_library(), -1)
+        sec["plumbing_config1"]["impl"] = "CPU oracle behind the same Python env objects (stand-in for PyBullet + SubprocVecEnv)"
+        line["secondary"] = sec
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------- GPU arm -------------
-def run_b200(args):
+def measure_b200(be, workload, args, rank, world, local_rank, dist, sampler_holder):
+    """Device-timed and end-to-end throughput of one workload on this rank's GPU; max over ranks.  Returns a dict on every rank."""
     import torch
-    import torch.distributed as dist
-    from srl_sim._abi import load_cuda_library
-    from srl_sim.backend import Backend
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    be = Backend(load_cuda_library(), local_rank)
-    spec = workload_spec(args.workload)
+    spec = workload_spec(workload)
     n, T, D = spec["n"], spec["T"], spec["obs_dim"]
-    sim = be.make_sim(spec["env_id"], n, seed=args.seed, model_blob=model_blob(args.workload), global_env_offset=rank * n, **spec["cfg"])
+    sim = be.make_sim(spec["env_id"], n, seed=args.seed, model_blob=model_blob(workload), global_env_offset=rank * n, **spec["cfg"])
     st = be.stream()
     sim.reset(stream=st)
-    acts_h, noise_h = make_inputs(args.workload, n, T, args.seed + 1000 * rank)
+    acts_h, noise_h = make_inputs(workload, n, T, args.seed + 1000 * rank)
     acts = be.from_host(acts_h)
     noise = None if noise_h is None else be.from_host(noise_h)
     obs = be.zeros((T, n, D), np.float32); rew = be.zeros((T, n), np.float32); done = be.zeros((T, n), np.uint8)
@@ -263,17 +423,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    steps, warmup = args.steps, max(args.warmup, 3)
+    for _ in range(warmup):
         step()
     barrier()
     launches0 = sim.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     wall0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         # evict L2 between timed iterations (outside the event bracket): WRITE a buffer larger than L2, then READ another
         # one so that the timed kernel starts from a cold L2 holding clean lines -- otherwise it would also pay the DRAM
         # write-back of up to 126 MB of the flush buffer's dirty lines, which is not its traffic
@@ -287,7 +448,6 @@ def run_b200(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     launches = sim.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through srl_sim_rollout_host ----
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -302,73 +462,97 @@ def run_b200(args):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
     h2d = h_acts.numel() * 4 + (0 if h_noise is None else h_noise.numel() * 4)
     d2h = h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel()
 
-    # ---- max over ranks; optional cross-rank episode-return all-gather (the only collective; off the step path) ----
+    # ---- max over ranks; cross-rank episode-return all-gather (the only collective; off the step path) ----
     tms = torch.tensor([total_ms, e2e_s * 1e3, wall * 1e3], device=be.torch_device, dtype=torch.float64)
     d = done.bool()
     ep_stats = torch.stack([ep_ret[d].sum().double(), d.sum().double()])
+    slow_rank = None
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        per_rank = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(per_rank, tms)
+        per_rank = torch.stack(per_rank)
+        slow_rank = {"rank": int(per_rank[:, 0].argmax().item()), "device_ms_per_step_by_rank": [float(x) / steps for x in per_rank[:, 0].tolist()]}
+        tms = per_rank.max(0).values
         gathered = [torch.zeros_like(ep_stats) for _ in range(world)]
         dist.all_gather(gathered, ep_stats)
         ep_stats = torch.stack(gathered).sum(0)
     total_ms, e2e_ms, wall_ms = [float(x) for x in tms.tolist()]
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks, peak_src = _peaks()
+    sim.close()
+    del flush, flush_rd
+    torch.cuda.empty_cache()
     units = n * T * world
-    value = units * args.steps / (total_ms * 1e-3)
-    launch_bytes = n * (spec["state_bytes"] + T * spec["step_bytes"])
-    launch_s = (total_ms / args.steps) * 1e-3
-    achieved = launch_bytes / launch_s / 1e9
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": TRAFFIC_BYTES.get(args.workload), "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_src,
-            "algorithmic_bytes_per_launch": launch_bytes, "kernel": "kuka_kernel" if args.workload == "kuka" else "mobile_rollout_kernel"}
-    if args.workload == "kuka":
-        fl = n * T * KUKA_FLOP_PER_STEP / launch_s / 1e12
-        roof["note"] = ("latency/issue-bound fp32 kernel (150 strictly sequential PGS sweeps per env-step), not HBM-bound: "
-                        "%.2f TFLOP/s of useful fp32 work; see DESIGN.md 'Measurement'" % fl)
-        roof["fp32_tflops"] = fl
-        # what actually bounds this kernel: warp-instruction issue slots (one per scheduler per cycle, 4 schedulers per SM).
-        # Instructions per launch come from the committed ncu capture (like `traffic`), the time is this run's.
-        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        clk = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        issue_peak = sms * 4 * clk * 1e-3
-        issue_ach = KUKA_WARP_INST_PER_LAUNCH / launch_s / 1e9
-        roof["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s", "frac": issue_ach / issue_peak,
-                         "warp_inst_per_launch": KUKA_WARP_INST_PER_LAUNCH,
-                         "source": "smsp__inst_executed.sum of profiles/r01_kuka_kernel_ncu_full.txt; peak = SMs x 4 schedulers x SM clock"}
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    launch_s = (total_ms / steps) * 1e-3
+    res = {"value": units * steps / (total_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+           "gpu_launches": launches, "clocks": clocks,
+           "e2e": {"value": units * steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "wall_ms_total_incl_flush": wall_ms, "episodes_finished": int(ep_stats[1].item()),
+           "episode_return_mean": float(ep_stats[0].item() / max(1.0, ep_stats[1].item()))}
+    if slow_rank:
+        res["slowest_rank"] = slow_rank
+    if rank == 0:
+        res["roofline"] = roofline_block(workload, spec, n, T, launch_s, clocks, be.library.path, sms)
+    return res
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from srl_sim._abi import load_cuda_library
+    from srl_sim.backend import Backend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = Backend(load_cuda_library(), local_rank)
+    main = measure_b200(be, args.workload, args, rank, world, local_rank, dist, None)
+    secondary = {}
+    if not args.no_secondary and args.workload == "kuka":
+        m = measure_b200(be, "mobile", args, rank, world, local_rank, dist, None)
+        if rank == 0:
+            mmetric, mconfig = metric_and_config("mobile", world)
+            m.update({"metric": mmetric, "config": mconfig, "dtype": "f64", "scaling": "weak", "n_gpus": world})
+            secondary["mobile_config4"] = m
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    if not args.no_secondary and args.workload == "kuka":
+        try:
+            secondary["plumbing_config1"] = plumbing_config1(be.library, local_rank)
+        except Exception as ex:      # never lose the headline line to the secondary leg
+            secondary["plumbing_config1"] = {"error": repr(ex)}
     metric, config = metric_and_config(args.workload, world)
-    line = {"metric": metric, "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+    line = {"metric": metric, "value": main["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.workload == "kuka" else "f64", "data": "synthetic",
             "config": config,
-            "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": units * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roof,
-            "wall_ms_total_incl_flush": wall_ms,
-            "episodes_finished": int(ep_stats[1].item()),
-            "episode_return_mean": float(ep_stats[0].item() / max(1.0, ep_stats[1].item()))}
+            "clocks": main["clocks"], "gpu_launches": main["gpu_launches"],
+            "e2e": main["e2e"], "roofline": main["roofline"],
+            "wall_ms_total_incl_flush": main["wall_ms_total_incl_flush"],
+            "episodes_finished": main["episodes_finished"], "episode_return_mean": main["episode_return_mean"]}
+    if "slowest_rank" in main:
+        line["slowest_rank"] = main["slowest_rank"]
+    if secondary:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, effective_cores())
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/); filled in per round, None until measured.
-TRAFFIC_BYTES = {"kuka": 108501760, "mobile": 86471680}  # profiles/r01_*_ncu_full.txt
 
 
 def main():
@@ -380,6 +564,7 @@ def main():
     ap.add_argument("--workload", default="kuka", choices=["kuka", "mobile"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[3] / configs[0] legs (A/B scripts, ncu captures)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

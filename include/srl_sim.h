@@ -87,7 +87,8 @@ typedef struct srl_cfg {
     float    max_distance;      /* Kuka safety-sphere radius (0.8); unused for MobileRobot     */
     float    timestep;          /* 0 = 1/240                                                   */
     uint32_t prefetch_resets;   /* Kuka, opt-in (0 = off): keep a ready post-reset state per env so that a lockstep
-                                   step never runs reset() inside the launch; refreshed by srl_sim_prefetch_resets  */
+                                   step never runs reset() inside the launch; the records are advanced by a helper CTA
+                                   appended to every step / rollout launch (bulk fill: srl_sim_prefetch_resets)        */
     uint64_t global_env_offset; /* global index of local env 0 (multi-GPU sharding)            */
 } srl_cfg;
 
@@ -106,8 +107,11 @@ enum srl_state_field {
     SRL_F_COUNTERS      = 8,  /* i32[N,4] Kuka: n_contacts, n_steps_outside, terminated, episode index */
     SRL_F_EPISODE_STATS = 9,  /* f64[N,2] running episode return, length                       */
     SRL_F_BUTTON_BASE   = 10, /* f64[N,3] Kuka: button base link origin (x, y, z)              */
-    SRL_F_TWO_BUTTON    = 11  /* f64[N,8] Kuka2Button (read-only): n_contacts[0], n_contacts[1], goal_id, second button base x y z,
+    SRL_F_TWO_BUTTON    = 11, /* f64[N,8] Kuka2Button (read-only): n_contacts[0], n_contacts[1], goal_id, second button base x y z,
                                  second glider q, qd (kuka_2button_gym_env.py:34,40-43)          */
+    SRL_F_NEXT_RECORD   = 12  /* i32[N,3] Kuka with srl_cfg.prefetch_resets (read-only, CUDA library): next-episode record
+                                 complete (0/1), random reset micro-steps applied to an incomplete record (0-4), episode index
+                                 the record is for; all zero / -1 without the feature                         */
 };
 
 int srl_sim_abi_version(void);
@@ -165,12 +169,16 @@ int srl_sim_rollout(srl_sim* sim, int T, const void* actions, const float* noise
 int srl_sim_rollout_host(srl_sim* sim, int T, const void* actions, const float* noise,
                          float* obs_out, float* rew_out, uint8_t* done_out);
 
-/* Opt-in (srl_cfg.prefetch_resets): refresh the next-episode records of the envs that consumed theirs.  The post-reset state of
- * an episode is a pure function of (seed, global env index, episode index), so it can be produced ahead of time: launch this on a
- * SIDE stream after every srl_sim_step (it may overlap later step launches of the same handle) and join the stream when the
- * rollout ends.  A step whose env finishes an episode then copies the record in instead of running reset()'s five random
- * micro-steps inside the launch; if no record is ready it resets in the launch as before -- results never depend on the timing.
- * No-op (returns 0) for handles without the feature.  Reference: the reset() a SubprocVecEnv worker runs between two steps
+/* Opt-in (srl_cfg.prefetch_resets): next-episode records.  The post-reset state of an episode is a pure function of (seed, global
+ * env index, episode index), so it can be produced ahead of time; a step whose env finishes an episode then copies the record in
+ * instead of running reset()'s five random micro-steps inside the launch; if no record is ready it resets in the launch as
+ * before -- results never depend on which of the two happened.  With the option on, EVERY srl_sim_step / srl_sim_rollout launch
+ * carries one extra helper CTA that advances up to 128 incomplete records by one random micro-step per env step of the launch,
+ * so no call is needed in steady state (and a captured CUDA graph of step launches just works).  This entry point is the BULK
+ * fill: it completes the records of all envs that have none, in one launch of its own -- call it once after srl_sim_reset of all
+ * envs if the first episodes are short.  Stream-ordered like every other call; when `stream` differs from the stream of the
+ * handle's step launches the library orders the two with events (it never overlaps them).  No-op (returns 0) for handles
+ * without the feature.  Reference: the reset() a SubprocVecEnv worker runs between two steps
  * (kuka_button_gym_env.py:214-281 via rl_baselines/utils.py:216-220). */
 int srl_sim_prefetch_resets(srl_sim* sim, void* stream);
 

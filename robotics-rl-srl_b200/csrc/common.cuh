@@ -43,6 +43,10 @@ struct srl_sim {
     int mobile_block;   // CTA-size override (0 = heuristic)
     KukaDev* kuka;
     void* kuka_next;    // next-episode records (kuka_kernels.cu: KukaNextHost), only with srl_cfg.prefetch_resets
+    cudaEvent_t pf_ev;  // end of the last bulk record fill (srl_sim_prefetch_resets); the next rollout launch waits for it
+    bool pf_pending;
+    cudaEvent_t roll_ev; // end of the last rollout launch of a handle with records; a bulk fill waits for it
+    bool roll_ev_valid;
     uint64_t launches;
     cudaEvent_t ev0, ev1;
     bool ev_valid;

@@ -29,23 +29,23 @@
 #ifndef KK_ROLL_DYN
 #define KK_ROLL_DYN 0
 #endif
-// Packed-FP32 sweep (Blackwell FFMA2, `fma.rn.f32x2` / __ffma2_rn): v += A[:, i] * delta as 6 two-wide FMAs instead of 12.
-// It needs the FULL matrix in pair-column layout (144 registers instead of the 78 of the symmetric half).  Tried in round 1 and
-// left OFF: ptxas emits the 61 FFMA2 but also 66 MOVs to build the (delta, delta) pairs and align register pairs, and with
-// 255 registers exhausted 14 spill loads land inside the sweep -- 303 SASS instructions per sweep against 256 for the scalar
-// form (static count, cuobjdump), so the issue-bound sweep would get slower, not faster.
-#ifndef KK_SWEEP_FFMA2
-#define KK_SWEEP_FFMA2 0
-#endif
-// Residual form of the fast sweep: the 12 motor rows have unit Jacobians and constant targets, so the loop can carry
-// r_i = v_i - target_i instead of v_i; a row is then  s = clamp(lam_i - r_i / D_i - ...)  without the `lam_i + target_i / D_i` add
-// (12 FADD and 12 registers less per sweep).  KK_SWEEP_UNROLL: sweeps per loop iteration (2 lets ptxas rotate the lam registers
-// instead of copying them: 15 MOV less per sweep, twice the loop body).
-#ifndef KK_SWEEP_RESID
-#define KK_SWEEP_RESID 1
-#endif
+// Sweeps per loop iteration (2 lets ptxas rotate the lam registers instead of copying them, but doubles the loop body beyond the ~6 KB L0
+// instruction cache: measured slower in both rounds).  Packed FP32 (FFMA2, `fma.rn.f32x2`) was tried in both rounds and is NOT used: on
+// B200 an FFMA2 issues at HALF the rate of an FFMA (scripts/microbench/fma_issue.cu: 2.29 vs 1.09 cycles per instruction from one warp
+// per scheduler), so packing the row update buys nothing (profiles/r02_fma_issue_microbench.txt).
 #ifndef KK_SWEEP_UNROLL
 #define KK_SWEEP_UNROLL 1
+#endif
+// Saturating form of the fast sweep (round 2): the motor impulses are carried as lam' = (lam + max_imp) / (2 max_imp) in [0, 1], so the
+// projection onto [-max_imp, +max_imp] is the .SAT modifier of the FFMA that produces the new impulse -- the two FMNMX leave the sweep and the
+// loop-carried path of a row shrinks from FFMA -> FMNMX -> FMNMX -> FADD (18 cycles) to FFMA.SAT -> FADD (8).  The residual velocities are carried
+// as r'_j = sigma_j (v_j - target_j) and M^-1 as sigma_i sigma_j A_ij (sigma = 2 max_imp), which keeps the matrix symmetric (78 registers).
+#ifndef KK_SWEEP_SAT
+#define KK_SWEEP_SAT 1
+#endif
+// lam += d in place instead of lam = s (one FADD on the FMA pipe per row instead of a half-rate MOV at the loop end)
+#ifndef KK_SWEEP_LAM_ACC
+#define KK_SWEEP_LAM_ACC 1
 #endif
 
 struct f3 { float x, y, z; };
@@ -807,63 +807,40 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         // FAST PATH (no arm joint on a limit): straight-line sweep, registers only.  Contact rows of the manifold are
         // WATCHED: while every normal row is separating (lam = 0 and J v >= target) it and its friction rows are exact
         // no-ops; the first time one would activate, the solve continues in the general loop from that very row.
-        // The loop-carried dependency runs through consecutive motor rows; it is shortened from
-        //   FFMA(v_i) -> FADD -> FFMA -> FMNMX -> FMNMX -> FADD        (26 cycles)   to
-        //   FFMA -> FMNMX -> FMNMX -> FADD                               (18 cycles)
-        // by folding the previous row's contribution to v_i into the impulse update algebraically:
-        //   lam_i + (tgt_i - v_i) / D_i  =  [lam_i + tgt_i/D_i - v'_i/D_i]  -  (A_{i,i-1}/D_i) * delta_{i-1}
-        // where v'_i lacks only the previous row's update (applied off the critical path afterwards).
-#if KK_SWEEP_FFMA2
-        float tk[KK_NB];
-        float2 Ac[KK_NB][KK_NB / 2];   // column i of the symmetric A, as (row 2p, row 2p+1) pairs
-        float2 vp[KK_NB / 2];
+        // The 12 motor rows have unit Jacobians and constant targets, so the loop carries the residuals r_i = v_i - target_i, and the
+        // previous row's contribution to r_i is folded into the impulse update algebraically,
+        //   lam_i - r_i / D_i  =  [lam_i - r'_i / D_i]  -  (A_{i,i-1} / D_i) * delta_{i-1},
+        // where r'_i lacks only the previous row's update (applied off the critical path afterwards).
+        float c_wt[KK_MAXC];     // contact watch thresholds against the residual velocities: c_tgt - J . target
+#if KK_SWEEP_SAT
+        // Saturating form: impulses as lam' = (lam + max_imp) / sigma in [0, 1] with sigma = 2 max_imp, residuals as sigma_j r_j, the matrix as
+        // sigma_i sigma_j A_ij (symmetric: 78 registers); the clamp is the .SAT of the FFMA on the loop-carried path (FFMA.SAT -> FADD per row).
+        float cs[KK_NB], kk[KK_NB];
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) A[i][j] *= P.sat_ss[i * (i + 1) / 2 + j];
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) {
-            tk[i] = tgt[i] * invd[i];
-#pragma unroll
-            for (int p2 = 0; p2 < KK_NB / 2; ++p2) Ac[i][p2] = make_float2(KK_A(2 * p2, i), KK_A(2 * p2 + 1, i));
+            cs[i] = invd[i] * P.sat_isig2[i];                  // 1 / (sigma_i^2 A_ii)
+            kk[i] = i > 0 ? cs[i] * A[i][i - 1] : 0.f;
+            v[i] = (v[i] - tgt[i]) * P.sat_sig[i];
+            lam[i] = 0.5f;                                     // lam = 0
         }
+        float cJw[KK_MAXC][ND];   // contact watch: Jacobian rows against the scaled residuals
+        for (int c = 0; c < nc; ++c) {
+            float off = 0.f;
 #pragma unroll
-        for (int p2 = 0; p2 < KK_NB / 2; ++p2) vp[p2] = make_float2(v[2 * p2], v[2 * p2 + 1]);
-#define KK_V(j) (((j) & 1) ? vp[(j) >> 1].y : vp[(j) >> 1].x)
-#define KK_AC(j, i) (((j) & 1) ? Ac[i][(j) >> 1].y : Ac[i][(j) >> 1].x)
-#pragma unroll 1
-        for (int it = 0; it < P.iters; ++it) {
-            {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
-                float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
-                v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
-                s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
-                v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
-                s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
-                v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
-            }
-            KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
-            float dprev = 0.f;
+            for (int j = 0; j < KK_NB; ++j) { off = fmaf(cJ[c][j], tgt[j], off); cJw[c][j] = cJ[c][j] * P.sat_isig[j]; }
 #pragma unroll
-            for (int i = 0; i < KK_NB; ++i) {
-                const float e = fmaf(-invd[i], KK_V(i), lam[i] + tk[i]);                                  // off the critical path
-                const float sraw = i > 0 ? fmaf(-(invd[i] * KK_AC(i - 1 < 0 ? 0 : i - 1, i)), dprev, e) : e;   // critical path
-                if (i > 0) KK_V(i) = fmaf(KK_AC(i - 1 < 0 ? 0 : i - 1, i), dprev, KK_V(i));               // deferred update from row i-1
-                const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
-                const float d = s - lam[i];
-                lam[i] = s;
-                const float2 d2 = make_float2(d, d);
-#pragma unroll
-                for (int p2 = 0; p2 < KK_NB / 2; ++p2) {
-                    if (2 * p2 == i + 1) vp[p2].y = fmaf(Ac[i][p2].y, d, vp[p2].y);          // (i+1, i+2): i+1 is updated by the next row
-                    else if (2 * p2 + 1 == i + 1) vp[p2].x = fmaf(Ac[i][p2].x, d, vp[p2].x);   // (i, i+1)
-                    else vp[p2] = __ffma2_rn(Ac[i][p2], d2, vp[p2]);
-                }
-                dprev = d;
-            }
-#define KK_SYNC_V() { _Pragma("unroll") for (int p3 = 0; p3 < KK_NB / 2; ++p3) { v[2 * p3] = vp[p3].x; v[2 * p3 + 1] = vp[p3].y; } }
-            if (nc > 0) KK_SYNC_V();
+            for (int j = KK_NB; j < ND; ++j) cJw[c][j] = cJ[c][j];
+            c_wt[c] = c_tgt[c] - off;
+        }
+#define KK_WATCH_J(c, j) cJw[c][j]
 #else
-        float tk[KK_NB], kk[KK_NB];
+        float kk[KK_NB];
 #pragma unroll
-        for (int i = 0; i < KK_NB; ++i) { tk[i] = tgt[i] * invd[i]; kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f; }
-#if KK_SWEEP_RESID
-        float c_wt[KK_MAXC];     // contact watch thresholds against the RESIDUAL velocities: c_tgt - J . target
+        for (int i = 0; i < KK_NB; ++i) kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f;
         for (int c = 0; c < nc; ++c) {
             float off = 0.f;
 #pragma unroll
@@ -872,61 +849,92 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         }
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) v[i] -= tgt[i];
+#define KK_WATCH_J(c, j) cJ[c][j]
 #endif
-        constexpr int sweep_unroll = KK_SWEEP_UNROLL;
+        // loop invariants of the button rows in vector registers (opaque copies: no uniform-register / constant-bank reloads inside the sweep)
+        float bminv, nbminv, lo_hi, hi_hi, lo_t, hi_t;
+        asm volatile("mov.f32 %0, %1;" : "=f"(bminv) : "f"(P.btn_minv));
+        asm volatile("mov.f32 %0, %1;" : "=f"(nbminv) : "f"(-P.btn_minv));
+        asm volatile("mov.f32 %0, %1;" : "=f"(lo_hi) : "f"(bl_lo_hi));
+        asm volatile("mov.f32 %0, %1;" : "=f"(hi_hi) : "f"(bl_hi_hi));
+        asm volatile("mov.f32 %0, %1;" : "=f"(lo_t) : "f"(bl_lo_t));
+        asm volatile("mov.f32 %0, %1;" : "=f"(hi_t) : "f"(bl_hi_t));
+        bool act = false;        // a watched contact row would activate in sweep `it - 1`
+        int it = 0;
+        if (P.iters > 0) {
+            int left = P.iters;
+            asm volatile("mov.u32 %0, %0;" : "+r"(left));
+            constexpr int sweep_unroll = KK_SWEEP_UNROLL;
 #pragma unroll sweep_unroll
-        for (int it = 0; it < P.iters; ++it) {
-            {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
-                float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
-                v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
-                s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
-                v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
-                s = fminf(fmaxf(fmaf(bl_hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), bl_hi_hi);
-                v[KK_NB] = fmaf(-P.btn_minv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
-            }
-            KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
-            float dprev = 0.f;
-#pragma unroll
-            for (int i = 0; i < KK_NB; ++i) {
-#if KK_SWEEP_RESID
-                const float e = fmaf(-invd[i], v[i], lam[i]);                  // v[i] holds v_i - target_i
-#else
-                const float e = fmaf(-invd[i], v[i], lam[i] + tk[i]);          // off the critical path
-#endif
-                const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        // critical path
-                if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             // deferred update from row i-1
-                const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
-                const float d = s - lam[i];
-                lam[i] = s;
-#pragma unroll
-                for (int j = 0; j < KK_NB; ++j)
-                    if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
-                dprev = d;
-            }
-#endif
-            if (nc > 0) {
-                bool act = false;
-#pragma unroll 1
-                for (int c = 0; c < nc; ++c) {
-                    float jv = 0.f;
-#pragma unroll
-                    for (int j = 0; j < ND; ++j) jv = fmaf(cJ[c][j], v[j], jv);
-#if KK_SWEEP_RESID && !KK_SWEEP_FFMA2
-                    act = act | (c_wt[c] - jv > 0.f);
-#else
-                    act = act | (c_tgt[c] - jv > 0.f);
-#endif
+            do {
+                {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
+                    float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
+                    v[KK_NB] = fmaf(bminv, s - b_lam, v[KK_NB]); b_lam = s;
+                    s = fminf(fmaxf(fmaf(lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), lo_hi);
+                    v[KK_NB] = fmaf(bminv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
+                    s = fminf(fmaxf(fmaf(hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), hi_hi);
+                    v[KK_NB] = fmaf(nbminv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
                 }
-                if (act) { it0 = it; resume_mid_sweep = true; break; }
-            }
-            it0 = it + 1;
+                KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
+                float dprev = 0.f;
+#pragma unroll
+                for (int i = 0; i < KK_NB; ++i) {
+#if KK_SWEEP_SAT
+                    float s;
+                    if (i == 0) s = __saturatef(fmaf(-cs[i], v[i], lam[i]));
+                    else {
+                        const float e = fmaf(-cs[i], v[i], lam[i]);                // off the critical path (v[i] lacks row i-1's update)
+                        s = __saturatef(fmaf(-kk[i], dprev, e));                   // critical path: FFMA.SAT
+                        v[i] = fmaf(A[i][i - 1], dprev, v[i]);                     // deferred update from row i-1
+                    }
+                    const float d = s - lam[i];
+#if KK_SWEEP_LAM_ACC
+                    lam[i] += d;      // in place (no register rename, no MOV at the loop end); equals s whenever s - lam is exact
+#else
+                    lam[i] = s;
+#endif
+#else
+                    const float e = fmaf(-invd[i], v[i], lam[i]);                  // v[i] holds v_i - target_i
+                    const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        // critical path
+                    if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             // deferred update from row i-1
+                    const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
+                    const float d = s - lam[i];
+                    lam[i] = s;
+#endif
+#pragma unroll
+                    for (int j = 0; j < KK_NB; ++j)
+                        if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
+                    dprev = d;
+                }
+                ++it;
+                if (nc > 0) {
+#pragma unroll 1
+                    for (int c = 0; c < nc; ++c) {
+                        float jv = 0.f;
+#pragma unroll
+                        for (int j = 0; j < ND; ++j) jv = fmaf(KK_WATCH_J(c, j), v[j], jv);
+                        act = act | (c_wt[c] - jv > 0.f);
+                    }
+                }
+            } while (--left > 0 && !act);
         }
-#if KK_SWEEP_RESID && !KK_SWEEP_FFMA2
+        if (act) { it0 = it - 1; resume_mid_sweep = true; } else it0 = it;
+#undef KK_WATCH_J
+#if KK_SWEEP_SAT
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {           // back to velocities and impulses
+            v[i] = fmaf(v[i], P.sat_isig[i], tgt[i]);
+            lam[i] = fmaf(lam[i], P.sat_sig[i], -mi[i]);
+        }
+        if (it0 < P.iters) {                        // the general loop continues with the unscaled matrix (rare: a contact activated)
+#pragma unroll
+            for (int i = 0; i < KK_NB; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) A[i][j] *= P.sat_iss[i * (i + 1) / 2 + j];
+        }
+#else
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) v[i] += tgt[i];
-#endif
-#if KK_SWEEP_FFMA2
-        KK_SYNC_V();
 #endif
     }
     if (it0 < P.iters) {

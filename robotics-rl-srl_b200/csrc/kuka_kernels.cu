@@ -33,9 +33,16 @@ struct KukaDev {
 };
 
 // "Next episode" records (opt-in, srl_cfg.prefetch_resets): the post-reset state of every env's NEXT episode -- a pure function of
-// (seed, global env index, episode index) -- produced ahead of time by op = PREFETCH on a side stream, so that a LOCKSTEP step
-// whose env finishes an episode copies a record in instead of running reset()'s five random micro-steps inside the launch
-// (measured: every steady-state launch of 4096 envs contains such an env and costs 343 us instead of ~70, profiles/r01_step_launch_timing.txt).
+// (seed, global env index, episode index) -- produced ahead of time, so that a LOCKSTEP step whose env finishes an episode copies a
+// record in instead of running reset()'s five random micro-steps inside the launch (measured: every steady-state launch of 4096 envs
+// contains such an env and costs 343 us instead of ~70, profiles/r01_step_launch_timing.txt).
+// Who produces them (round 2): a HELPER CTA appended to every rollout / step launch of the handle.  It scans the flags, takes up to 128
+// envs without a complete record and advances each of their records by (at most T) random micro-steps of reset() -- ONE per lockstep
+// launch, so the helper finishes with the stepping CTAs and the launch stays one physics step long; a record is complete after five
+// launches.  The 147 stepping CTAs of 4096 envs leave one of the 148 SMs free, which is where the helper lands.  (Round 1's version ran
+// the whole five-step reset in a separate launch on a side stream: validated on B200 in round 2 -- bit-identical, memcheck clean -- but its
+// 270 us launches shared schedulers with 2-4 following step launches and doubled their duration: 137 us median instead of 70.)
+// op = PREFETCH as a launch of its own (srl_sim_prefetch_resets) remains as the bulk fill after an explicit reset of all envs.
 // Same member names as KukaDev's state arrays: env_load / env_store work on either.
 struct KukaNext {
     float4* q[3]; float4* qd[3];
@@ -44,6 +51,8 @@ struct KukaNext {
     float4* btn2;
     uint8_t* valid;     // [N] 1 = record complete and not yet consumed
     int32_t* episode;   // [N] episode index the record was produced for (a record for another episode is dropped)
+    uint8_t* progress;  // [N] random micro-steps of reset() already applied to an incomplete record (0 = not started)
+    int helper;         // 1: the LAST CTA of a rollout launch is the helper CTA that advances incomplete records (see kuka_kernel)
 };
 
 namespace {
@@ -215,10 +224,27 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done, float* __restrict__ ep_ret,
                                                        int32_t* __restrict__ ep_len, float* __restrict__ snap, const KukaNext nx) {
-    const int i = env_index(n, d.epw);
+    int i;
+    bool helper = false;         // PREFETCH: this thread belongs to the helper CTA and advances one env's next-episode record
+    if constexpr (PREFETCH) {
+        if (nx.helper && op == KUKA_OP_ROLLOUT && blockIdx.x == gridDim.x - 1) {
+            // helper CTA: collect up to blockDim.x envs whose record is incomplete, records in progress first
+            __shared__ int h_list[128];
+            __shared__ int h_cnt;
+            if (threadIdx.x == 0) h_cnt = 0;
+            __syncthreads();
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int j = threadIdx.x; j < n; j += blockDim.x)
+                    if (!nx.valid[j] && ((nx.progress[j] > 0) == (pass == 0))) { const int k = atomicAdd(&h_cnt, 1); if (k < 128) h_list[k] = j; }
+                __syncthreads();
+            }
+            if ((int)threadIdx.x >= h_cnt || threadIdx.x >= 128) return;
+            i = h_list[threadIdx.x]; helper = true; op = KUKA_OP_PREFETCH;
+        } else i = env_index(n, d.epw);
+    } else i = env_index(n, d.epw);
     if (i < 0) return;
     if (op == KUKA_OP_RESET && mask && !mask[i]) return;
-    if constexpr (PREFETCH) { if (op == KUKA_OP_PREFETCH && nx.valid[i]) return; }
+    if constexpr (PREFETCH) { if (op == KUKA_OP_PREFETCH && !helper && nx.valid[i]) return; }
     const KukaParams& P = d.P;
     const uint64_t genv = P.env_offset + (uint64_t)i;
     const size_t N = (size_t)n;
@@ -248,10 +274,21 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         in_reset = true; reset_left = 500;
     }
     bool consumed = false;       // PREFETCH: the env just took its next-episode record (reset_end is already part of it)
+    bool partial = false;        // helper: the launch ends before the record is complete
+    int budget = T;              // helper: random micro-steps this launch may add to the record
     if constexpr (PREFETCH) {
         if (op == KUKA_OP_PREFETCH) {   // e.episode (live state) is the index the env's next reset() will draw with
-            reset_begin<TWOB>(P, e, nullptr, genv);
-            in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
+            const int prog = helper ? (int)nx.progress[i] : 0;
+            if (prog > 0 && nx.episode[i] == (int)e.episode) {
+                // continue the record where the previous launch left it: the loop-carried state of reset() is all in KukaEnv, the
+                // kinematics are recomputed from it -- the same values in the same instructions as an uninterrupted reset
+                env_load<TWOB, true>(nx, i, e);
+                in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT - prog;
+            } else {
+                if (helper) nx.episode[i] = (int)e.episode;
+                reset_begin<TWOB>(P, e, nullptr, genv);
+                in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
+            }
         }
     }
     for (;;) {
@@ -341,7 +378,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             }
             if (!(PREFETCH && consumed)) reset_end<TWOB>(P, e);
             consumed = false;
-            if (obs) {  // getSRLState after reset (:278-279)
+            if (obs && op != KUKA_OP_PREFETCH) {  // getSRLState after reset (:278-279)
                 float* o = obs + 3 * (op == KUKA_OP_RESET ? (size_t)i : (size_t)t * N + (size_t)i);
                 o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2];
             }
@@ -429,6 +466,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         if (!JOINTS) apply_ee_delta(P, e, dx, dy, dz);
         saved_cb = new_cb; saved_ct = new_ct; saved_a0 = new_a0; saved_a1 = new_a1;
         kuka_physics_step<JOINTS, TWOB>(P, e, k, ct, armed, qj);
+        if constexpr (PREFETCH) { if (helper && --budget <= 0 && reset_left > 0) { partial = true; break; } }
         if (!in_reset) {
             // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
             if (e.terminated || e.counter > P.max_steps) { pending = true; rep = 0; }
@@ -438,9 +476,11 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     e.cbutton = saved_cb; e.ctable = saved_ct;
     if (TWOB) { e.cany0 = saved_a0; e.cany1 = saved_a1; }
     if constexpr (PREFETCH) {
-        if (op == KUKA_OP_PREFETCH) {      // record first, then the episode it is for, then the flag
+        if (op == KUKA_OP_PREFETCH) {
             env_store<TWOB>(nx, i, e);
-            nx.episode[i] = (int)e.episode - 1;
+            if (partial) { nx.progress[i] = (uint8_t)(N_RANDOM_ACTIONS_AT_INIT - reset_left); return; }   // nx.episode[i] was set when the record was begun
+            nx.episode[i] = (int)e.episode - 1;   // record first, then the episode it is for, then the flag
+            nx.progress[i] = 0;
             __threadfence();
             reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 1;
             return;
@@ -477,6 +517,15 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
         P.maxvel[i] = (float)c[KM_C_MAXVEL]; P.maximp[i] = (float)(c[KM_C_MAXFORCE] * dt);
         P.tmode[i] = (int)c[KM_C_TARGET];
         P.snap_q[i] = (float)r[KM_B_QINIT];
+    }
+    for (int i = 0; i < KK_NB; ++i) {
+        if (!(P.maximp[i] > 0.f)) { srl_set_error("kuka: every motor needs a positive force bound (the sweep carries impulses scaled to it)"); return false; }
+        const double sg = 2.0 * (double)P.maximp[i];
+        P.sat_sig[i] = (float)sg; P.sat_isig[i] = (float)(1.0 / sg); P.sat_isig2[i] = (float)(1.0 / (sg * sg));
+        for (int j = 0; j <= i; ++j) {
+            const double ss = sg * 2.0 * (double)P.maximp[j];
+            P.sat_ss[i * (i + 1) / 2 + j] = (float)ss; P.sat_iss[i * (i + 1) / 2 + j] = (float)(1.0 / ss);
+        }
     }
     P.nsph = (int)d[KM_H_NSPHERE];
     P.sph_min_body = KK_NB; P.sph_reach = 0.f;
@@ -602,6 +651,9 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
         SRL_CUDA_OK(cudaMalloc(&nx.cnt2, N * sizeof(int4))); SRL_CUDA_OK(cudaMemset(nx.cnt2, 0, N * sizeof(int4)));
         SRL_CUDA_OK(cudaMalloc(&nx.valid, N)); SRL_CUDA_OK(cudaMemset(nx.valid, 0, N));
         SRL_CUDA_OK(cudaMalloc(&nx.episode, N * sizeof(int32_t))); SRL_CUDA_OK(cudaMemset(nx.episode, 0xff, N * sizeof(int32_t)));
+        SRL_CUDA_OK(cudaMalloc(&nx.progress, N)); SRL_CUDA_OK(cudaMemset(nx.progress, 0, N));
+        SRL_CUDA_OK(cudaEventCreateWithFlags(&s->pf_ev, cudaEventDisableTiming));
+        SRL_CUDA_OK(cudaEventCreateWithFlags(&s->roll_ev, cudaEventDisableTiming));
         nh->enabled = true;
     }
     return 0;
@@ -618,9 +670,11 @@ void kuka_free(srl_sim* s) {
         KukaNext& nx = nh->nx;
         for (int k = 0; k < 3; ++k) { cudaFree(nx.q[k]); cudaFree(nx.qd[k]); }
         cudaFree(nx.misc0); cudaFree(nx.misc1); cudaFree(nx.tgt); cudaFree(nx.grip); cudaFree(nx.eepos); cudaFree(nx.cnt); cudaFree(nx.cnt2);
-        cudaFree(nx.btn2); cudaFree(nx.valid); cudaFree(nx.episode);
+        cudaFree(nx.btn2); cudaFree(nx.valid); cudaFree(nx.episode); cudaFree(nx.progress);
         delete nh;
         s->kuka_next = nullptr;
+        if (s->pf_ev) cudaEventDestroy(s->pf_ev);
+        if (s->roll_ev) cudaEventDestroy(s->roll_ev);
     }
 }
 
@@ -637,8 +691,16 @@ int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noi
     KukaDev* d = s->kuka;
     int grid, block; grid_for(s, d, grid, block);
     const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);
-    if (nh && nh->enabled)      // the rollout path that takes a ready next-episode record instead of resetting inside the launch
-        kuka_kernel<false, false, true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nh->nx);
+    if (nh && nh->enabled) {    // the rollout path that takes a ready next-episode record instead of resetting inside the launch
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        const bool capturing = cap != cudaStreamCaptureStatusNone;   // events recorded outside a capture cannot be waited for inside it
+        if (s->pf_pending && !capturing) { SRL_CUDA_OK(cudaStreamWaitEvent(st, s->pf_ev, 0)); s->pf_pending = false; }
+        KukaNext nx = nh->nx;
+        nx.helper = 1;          // + the helper CTA that advances the incomplete records by up to T micro-steps
+        kuka_kernel<false, false, true><<<grid + 1, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nx);
+        if (!capturing) { SRL_CUDA_OK(cudaEventRecord(s->roll_ev, st)); s->roll_ev_valid = true; }
+    }
     else
         KUKA_LAUNCH(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr);
     SRL_CUDA_OK(cudaGetLastError());
@@ -652,8 +714,12 @@ int kuka_launch_prefetch(srl_sim* s, cudaStream_t st) {
     const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);
     if (!nh || !nh->enabled) return 0;
     int grid, block; grid_for(s, d, grid, block);
+    // never concurrent with a rollout launch of the handle: its helper CTA writes the same records
+    if (s->roll_ev_valid) SRL_CUDA_OK(cudaStreamWaitEvent(st, s->roll_ev, 0));
     kuka_kernel<false, false, true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_PREFETCH, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nh->nx);
     SRL_CUDA_OK(cudaGetLastError());
+    SRL_CUDA_OK(cudaEventRecord(s->pf_ev, st));
+    s->pf_pending = true;
     s->launches += 1;
     return 0;
 }
@@ -730,6 +796,19 @@ int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
         SRL_CUDA_OK(pull(b, d->misc1));
         SRL_CUDA_OK(cudaMemcpy(ia.data(), d->cnt2, N * sizeof(int4), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < N; ++i) { D[2 * i] = b[i].w; D[2 * i + 1] = (double)ia[i].z; }
+        return 0;
+    }
+    case SRL_F_NEXT_RECORD: {
+        if (!need(3, 4)) return 1;
+        const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);
+        for (size_t i = 0; i < N; ++i) { I[3 * i] = 0; I[3 * i + 1] = 0; I[3 * i + 2] = -1; }
+        if (nh && nh->enabled) {
+            std::vector<uint8_t> va(N), pr(N); std::vector<int32_t> ep(N);
+            SRL_CUDA_OK(cudaMemcpy(va.data(), nh->nx.valid, N, cudaMemcpyDeviceToHost));
+            SRL_CUDA_OK(cudaMemcpy(pr.data(), nh->nx.progress, N, cudaMemcpyDeviceToHost));
+            SRL_CUDA_OK(cudaMemcpy(ep.data(), nh->nx.episode, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < N; ++i) { I[3 * i] = va[i]; I[3 * i + 1] = pr[i]; I[3 * i + 2] = ep[i]; }
+        }
         return 0;
     }
     default:

@@ -47,7 +47,10 @@ def env_thread(args, thread_num, partition=True):
         "record_data": not args.no_record_data,
         "multi_view": args.multi_view,
         "save_path": args.save_path,
-        "shape_reward": args.shape_reward
+        "shape_reward": args.shape_reward,
+        # the simulator has no rasteriser: the env records / returns the ground-truth state (the reference's default here is raw_pixels,
+        # whose frames this generator only ever handed to EpisodeSaver)
+        "srl_model": "ground_truth",
     }
     env_kwargs["name"] = args.name + "_part-" + str(thread_num) if partition else args.name
     env = registered_env[args.env][0](**env_kwargs)

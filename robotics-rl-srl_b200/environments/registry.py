@@ -18,17 +18,17 @@ registered_env = {
     "MobileRobotLineTargetGymEnv-v0": (MobileRobotLineTargetGymEnv, MobileRobotGymEnv, PlottingType.PLOT_2D, ThreadingType.PROCESS),
 }
 
-try:  # the Kuka classes register themselves once their module is importable
-    from environments.kuka_gym.kuka_button_gym_env import KukaButtonGymEnv
-    from environments.kuka_gym.kuka_rand_button_gym_env import KukaRandButtonGymEnv
-    from environments.kuka_gym.kuka_2button_gym_env import Kuka2ButtonGymEnv
-    from environments.kuka_gym.kuka_moving_button_gym_env import KukaMovingButtonGymEnv
-    registered_env["KukaButtonGymEnv-v0"] = (KukaButtonGymEnv, SRLGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS)
-    registered_env["KukaRandButtonGymEnv-v0"] = (KukaRandButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS)
-    registered_env["Kuka2ButtonGymEnv-v0"] = (Kuka2ButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS)
-    registered_env["KukaMovingButtonGymEnv-v0"] = (KukaMovingButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS)
-except ImportError:
-    pass
+from environments.kuka_gym.kuka_button_gym_env import KukaButtonGymEnv
+from environments.kuka_gym.kuka_rand_button_gym_env import KukaRandButtonGymEnv
+from environments.kuka_gym.kuka_2button_gym_env import Kuka2ButtonGymEnv
+from environments.kuka_gym.kuka_moving_button_gym_env import KukaMovingButtonGymEnv
+
+registered_env.update({
+    "KukaButtonGymEnv-v0":       (KukaButtonGymEnv, SRLGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS),
+    "KukaRandButtonGymEnv-v0":   (KukaRandButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS),
+    "Kuka2ButtonGymEnv-v0":      (Kuka2ButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS),
+    "KukaMovingButtonGymEnv-v0": (KukaMovingButtonGymEnv, KukaButtonGymEnv, PlottingType.PLOT_3D, ThreadingType.PROCESS),
+})
 
 
 class EnvSpec(object):

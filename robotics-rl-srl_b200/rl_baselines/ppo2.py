@@ -141,9 +141,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     value and the rollout-buffer writes in one launch; ``srl_obs_filter``: the observation filter in one launch; include/srl_policy.h)
     instead of ~60 small torch kernels: an env step of the collection loop is then three launches.  Sampling then uses the library's
     counter-based streams (keyed by seed and global env index) instead of torch's generator.
-    ``prefetch_resets`` (Kuka, experimental -- built at the end of round 1, NOT yet validated on a GPU): create the envs with
-    ``srl_cfg.prefetch_resets`` and refresh the next-episode records on a side stream after every env step, so that a lockstep step never
-    runs reset() inside the launch (include/srl_sim.h: srl_sim_prefetch_resets).
+    ``prefetch_resets`` (Kuka): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then carries a helper CTA that
+    prepares the next-episode records, so that a step whose env finishes an episode copies a record in instead of running reset() inside
+    the launch (include/srl_sim.h: srl_sim_prefetch_resets; validated bit-identical on B200 in round 2).
     ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
     ``collect`` / ``gae`` / ``optimise`` in it (a profiling aid: the synchronisations cost throughput)."""
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
@@ -152,6 +152,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     dist, rank, world = _dist_world()
     if prefetch_resets:
         env_kwargs["prefetch_resets"] = True
+    if env_kwargs.get("srl_model", "ground_truth") != "ground_truth":
+        # the collection loop feeds the simulator's observation buffer (the 3-D / 2-D ground-truth observation) straight to the policy
+        raise ValueError("ppo2.train supports srl_model='ground_truth' only (got %r)" % env_kwargs["srl_model"])
     env = BatchedSRLVecEnv(env_id, num_envs, seed=seed, device=device, global_env_offset=rank * num_envs, **env_kwargs)
     on_gpu = env.backend.on_gpu
     # device -1 is the CPU oracle installed by a test through srl_sim.backend.use_library (its buffers are numpy arrays,
@@ -208,19 +211,8 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         act_dev = torch.zeros(N if env.is_discrete else (N, env.sim.action_dim), device=dev, dtype=torch.int32 if env.is_discrete else torch.float32)
         done_u8 = torch.zeros((T, N), device=dev, dtype=torch.uint8)
 
-    side_pf = torch.cuda.Stream(device=dev) if (prefetch_resets and on_gpu) else None
-
-    def refresh_records():
-        """Fork: refresh the next-episode records on the side stream, after the env step just queued on the current stream."""
-        if side_pf is not None:
-            side_pf.wait_stream(torch.cuda.current_stream(dev))
-            env.sim.prefetch_resets(stream=side_pf.cuda_stream)
-
-    def join_records():
-        if side_pf is not None:
-            torch.cuda.current_stream(dev).wait_stream(side_pf)
-
-    refresh_records(); join_records()      # records for the first episodes' successors
+    if prefetch_resets and on_gpu:
+        env.sim.prefetch_resets(stream=env.backend.stream())   # bulk fill of the first records; from here on the helper CTA of every step launch keeps them up
 
     def collect():
         """n_steps lockstep env steps under the current policy; everything stays on the device, nothing synchronises."""
@@ -230,10 +222,8 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 buf["obs"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = obs, a, logp, v
                 act_dev = a.to(torch.int32) if env.is_discrete else torch.clamp(a, -1, 1).contiguous()
                 env.step_tensors(act_dev)                                 # one kernel launch, tensors stay on the GPU
-                refresh_records()
                 buf["rew"][t], buf["done"][t], buf["ep_ret"][t] = e_rew, e_done.float(), e_ep_ret
                 obs.copy_(norm(e_obs))
-            join_records()
             last_val.copy_(policy.vf(obs).squeeze(-1))
 
     def collect_fused():
@@ -244,9 +234,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
             for t in range(T):
                 fused.act(N, obs, act_dev, buf["logp"][t], buf["val"][t], obs_buf=buf["obs"][t], act_buf=buf["act"][t], stream=st)
                 env.sim.step(act_dev, None, env._obs, buf["rew"][t], done_u8[t], buf["ep_ret"][t], env._ep_len, stream=st)
-                refresh_records()
                 fused.filter(N, env._obs, obs, update=True, stream=st)
-            join_records()
             buf["done"].copy_(done_u8)
             last_val.copy_(policy.vf(obs).squeeze(-1))
 

@@ -99,10 +99,40 @@ class VecNormalize(object):
         self.venv.close()
 
 
+class DummyVecEnv(object):
+    """The reference-shaped plumbing: a list of single-env objects (N = 1 views on the simulator, built by ``makeEnv`` thunks, env i
+    seeded with ``seed + i``) stepped one after the other, each reset when done with the post-reset observation returned -- the worker
+    semantics of stable-baselines 2.5 ``DummyVecEnv`` / ``SubprocVecEnv`` that ``createEnvs`` of the reference
+    builds (rl_baselines/utils.py:216-220).  BASELINE.json configs[0] and BASELINE.md B3 are measured through it; anything that wants
+    throughput uses ``BatchedSRLVecEnv`` instead."""
+
+    def __init__(self, env_fns):
+        self.envs = [fn() for fn in env_fns]
+        self.num_envs = len(self.envs)
+        self.observation_space, self.action_space = self.envs[0].observation_space, self.envs[0].action_space
+
+    def reset(self):
+        return np.stack([env.reset() for env in self.envs])
+
+    def step(self, actions):
+        obs, rews, dones, infos = [], [], [], []
+        for env, a in zip(self.envs, actions):
+            o, r, d, info = env.step(a)
+            if d:
+                o = env.reset()
+            obs.append(o); rews.append(r); dones.append(d); infos.append(info)
+        return np.stack(obs), np.asarray(rews, np.float32), np.asarray(dones, bool), infos
+
+    def close(self):
+        for env in self.envs:
+            env.close()
+
+
 def createEnvs(args, allow_early_resets=False, env_kwargs=None, load_path_normalise=None):
     """
     :param args: (argparse.Namespace Object) needs ``env``, ``num_cpu`` (number of envs), ``seed``, ``num_stack``,
-        ``srl_model``; ``device`` (optional CUDA ordinal)
+        ``srl_model``; ``device`` (optional CUDA ordinal); ``per_env_objects`` (optional, extension): build ``num_cpu`` single-env
+        objects behind a ``DummyVecEnv`` like the reference does, instead of one batched env
     :param allow_early_resets: (bool) kept for signature compatibility (Monitor statistics come from the kernel)
     :param env_kwargs: (dict) The extra arguments for the environment
     :param load_path_normalise: (str) the path to loading the rolling average, None if not available or wanted.
@@ -110,7 +140,13 @@ def createEnvs(args, allow_early_resets=False, env_kwargs=None, load_path_normal
     """
     env_kwargs = dict(env_kwargs or {})
     env_kwargs.setdefault("srl_model", getattr(args, "srl_model", "ground_truth"))
-    envs = BatchedSRLVecEnv(args.env, args.num_cpu, seed=args.seed, device=getattr(args, "device", None), **env_kwargs)
+    if getattr(args, "per_env_objects", False):
+        # the reference's own shape: num_cpu env objects behind a (Dummy)VecEnv (rl_baselines/utils.py:216-220)
+        from environments.utils import makeEnv
+        envs = DummyVecEnv([makeEnv(args.env, args.seed, i, getattr(args, "log_dir", None), allow_early_resets=allow_early_resets, env_kwargs=env_kwargs)
+                            for i in range(args.num_cpu)])
+    else:
+        envs = BatchedSRLVecEnv(args.env, args.num_cpu, seed=args.seed, device=getattr(args, "device", None), **env_kwargs)
     envs = VecFrameStack(envs, getattr(args, "num_stack", 1))
     if env_kwargs["srl_model"] != "raw_pixels":
         envs = VecNormalize(envs, norm_obs=True, norm_reward=False)

@@ -32,13 +32,13 @@ ENV_KINDS = {
 
 # enum srl_state_field
 F_ROBOT_POS, F_TARGET_POS, F_STEP_COUNTER, F_JOINT_POS, F_JOINT_VEL, F_EE_CMD, F_EE_POS, \
-    F_BUTTON_GLIDER, F_COUNTERS, F_EPISODE_STATS, F_BUTTON_BASE, F_TWO_BUTTON = range(12)
+    F_BUTTON_GLIDER, F_COUNTERS, F_EPISODE_STATS, F_BUTTON_BASE, F_TWO_BUTTON, F_NEXT_RECORD = range(13)
 
 _FIELD_SPEC = {
     F_ROBOT_POS: (np.float64, 3), F_TARGET_POS: (np.float64, 3), F_STEP_COUNTER: (np.int32, 1),
     F_JOINT_POS: (np.float64, 12), F_JOINT_VEL: (np.float64, 12), F_EE_CMD: (np.float64, 3),
     F_EE_POS: (np.float64, 3), F_BUTTON_GLIDER: (np.float64, 2), F_COUNTERS: (np.int32, 4),
-    F_EPISODE_STATS: (np.float64, 2), F_BUTTON_BASE: (np.float64, 3), F_TWO_BUTTON: (np.float64, 8),
+    F_EPISODE_STATS: (np.float64, 2), F_BUTTON_BASE: (np.float64, 3), F_TWO_BUTTON: (np.float64, 8), F_NEXT_RECORD: (np.int32, 3),
 }
 
 MOBILE_RESET_DRAWS = 6
@@ -221,7 +221,8 @@ class Sim(object):
         self.library.check(rc, "srl_sim_rollout_host")
 
     def prefetch_resets(self, stream=None):
-        """Refresh the next-episode records (handles created with ``prefetch_resets=True``; a no-op otherwise).  Meant for a side stream."""
+        """Bulk fill of the next-episode records (handles created with ``prefetch_resets=True``; a no-op otherwise).  In steady state
+        the helper CTA of every step / rollout launch keeps the records up; call this once after a reset of all envs."""
         rc = self._lib.srl_sim_prefetch_resets(self.handle, stream)
         self.library.check(rc, "srl_sim_prefetch_resets")
 

@@ -37,25 +37,27 @@ print("lockstep srl_sim_step: mean %.1f us, median %.1f us, min %.1f us, max %.1
       % (1e3 * step_ms.mean(), 1e3 * np.median(step_ms), 1e3 * step_ms.min(), 1e3 * step_ms.max(), int((any_done > 0).sum()), T))
 if (any_done > 0).any() and (any_done == 0).any():
     print("  launches with a finished episode: %.1f us; without: %.1f us" % (1e3 * step_ms[any_done > 0].mean(), 1e3 * step_ms[any_done == 0].mean()))
-if os.environ.get("SRL_TEST_PREFETCH") == "1":
-    # experimental next-episode records: the same lockstep loop, records refreshed on a side stream after every step
-    sim2 = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=0, prefetch_resets=True)
-    sim2.reset(obs_out=obs, stream=st)
-    for _ in range(10):
-        sim2.rollout(T, acts, None, robs, rrew, rdone, None, None, stream=st)
-    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
-    sim2.prefetch_resets(stream=st); torch.cuda.synchronize()
-    ms2, wall0 = [], None
-    for rep in range(3):
-        for t in range(T):
-            sim2.step(acts[t], None, obs, rew, done, None, None, stream=st)
-            side.wait_stream(main); sim2.prefetch_resets(stream=side.cuda_stream)
-            if rep == 2:
-                ms2.append(sim2.last_kernel_ms())
-    torch.cuda.synchronize()
-    ms2 = np.array(ms2)
-    print("lockstep srl_sim_step WITH next-episode records (side-stream refresh): mean %.1f us, median %.1f us, max %.1f us per launch"
-          % (1e3 * ms2.mean(), 1e3 * np.median(ms2), 1e3 * ms2.max()))
+# next-episode records (srl_cfg.prefetch_resets): the same lockstep loop; the helper CTA of every launch keeps the records up
+sim2 = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=0, prefetch_resets=True)
+sim2.reset(obs_out=obs, stream=st)
+for _ in range(10):
+    sim2.rollout(T, acts, None, robs, rrew, rdone, None, None, stream=st)
+sim2.prefetch_resets(stream=st); torch.cuda.synchronize()
+ms2, hits, fin = [], 0, 0
+from srl_sim import _abi
+for rep in range(3):
+    for t in range(T):
+        if rep == 2:
+            rec = sim2.get_state(_abi.F_NEXT_RECORD); live = sim2.get_state(_abi.F_COUNTERS)[:, 3]
+            ready = (rec[:, 0] == 1) & (rec[:, 2] == live)
+        sim2.step(acts[t], None, obs, rew, done, None, None, stream=st)
+        if rep == 2:
+            ms2.append(sim2.last_kernel_ms())
+            d = done.cpu().numpy().astype(bool); hits += int((d & ready).sum()); fin += int(d.sum())
+torch.cuda.synchronize()
+ms2 = np.array(ms2)
+print("lockstep srl_sim_step WITH next-episode records (helper CTA): mean %.1f us, median %.1f us, min %.1f us, max %.1f us per launch; %d of %d finished episodes took a record"
+      % (1e3 * ms2.mean(), 1e3 * np.median(ms2), 1e3 * ms2.min(), 1e3 * ms2.max(), hits, fin))
 pol = MlpPolicy(3, n_actions=6).to(dev)
 norm = RunningNorm(3, dev)
 fp = FusedPolicy(be.library, pol, norm.state, seed=1)

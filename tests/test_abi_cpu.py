@@ -175,3 +175,40 @@ def test_dataset_generator_and_episode_saver_on_oracle(use_oracle_backend, tmp_p
     k = dataset_generator.main(["--env", "KukaButtonGymEnv-v0", "--num-episode", "1", "--save-path", base, "--name", "kuka", "--max-distance", "0.8"])
     g = np.load(base + "kuka/ground_truth.npz")
     assert k == len(g["ground_truth_states"]) and g["target_positions"].shape == (1, 3)
+
+
+def test_dataset_generator_env_testing_mode_without_recording(use_oracle_backend, tmp_path):
+    """`dataset_generator --no-record-data` is the reference's env-testing mode (dataset_generator.py:37-121 with record_data False):
+    it must run episodes without a saver and write nothing."""
+    from environments import dataset_generator
+    base = str(tmp_path) + "/"
+    n = dataset_generator.main(["--env", "MobileRobotGymEnv-v0", "--num-episode", "2", "--save-path", base, "--name", "dry", "--no-record-data"])
+    assert n == 2 * 251
+    assert not os.path.exists(base + "dry/preprocessed_data.npz")
+
+
+def test_reference_shaped_plumbing_matches_batched_env(use_oracle_backend):
+    """createEnvs(per_env_objects=True) builds what the reference builds -- num_cpu env objects from makeEnv thunks (seed + rank) behind a
+    DummyVecEnv -> VecFrameStack -> VecNormalize (/root/reference/rl_baselines/utils.py:194-229, environments/utils.py:36-57) -- and its
+    stepping semantics (auto-reset, post-reset observation) must be those of the env objects themselves."""
+    import types
+    from environments.utils import makeEnv
+    from rl_baselines.utils import DummyVecEnv, createEnvs
+    args = types.SimpleNamespace(env="MobileRobotGymEnv-v0", num_cpu=3, seed=5, num_stack=1, srl_model="ground_truth", per_env_objects=True, log_dir=None)
+    envs = createEnvs(args, env_kwargs=dict(is_discrete=True))
+    assert isinstance(envs.venv.venv, DummyVecEnv) and envs.num_envs == 3
+    singles = [makeEnv("MobileRobotGymEnv-v0", 5, i, None, env_kwargs=dict(is_discrete=True, srl_model="ground_truth"))() for i in range(3)]
+    o0 = envs.reset()
+    raw0 = np.stack([e.reset() for e in singles])
+    assert np.array_equal(envs.get_original_obs(), raw0.astype(np.float32)) and o0.shape == (3, 2)   # VecFrameStack holds float32
+    rs = np.random.RandomState(0)
+    for t in range(260):                                    # crosses the 251-step episode boundary
+        a = rs.randint(0, 4, size=3)
+        _, r, d, _ = envs.step(list(a))
+        for i, e in enumerate(singles):
+            o, ri, di, _ = e.step(a[i])
+            if di:
+                o = e.reset()
+            assert np.array_equal(envs.get_original_obs()[i], np.asarray(o, np.float32)) and r[i] == ri and d[i] == di
+    assert t == 259
+    envs.close()
