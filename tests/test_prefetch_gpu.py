@@ -97,7 +97,8 @@ def test_helper_cta_completes_a_record_in_five_lockstep_launches(cuda_backend):
             assert complete == 128 and sorted(in_progress.tolist()) == [0] * (n - 256) + [k - 5] * 128
         else:
             assert complete == 256
-    assert np.all(rec[rec[:, 0] == 1, 2] == 0)              # produced for the episode the envs are in (index 0 draws the next reset)
+    live_ep = sim.get_state(_abi.F_COUNTERS)[:, 3]
+    assert np.all(rec[rec[:, 0] == 1, 2] == live_ep[rec[:, 0] == 1])   # produced for the episode index the env's next reset() will draw with
     sim.close()
 
 
