@@ -87,8 +87,8 @@ typedef struct srl_cfg {
     float    max_distance;      /* Kuka safety-sphere radius (0.8); unused for MobileRobot     */
     float    timestep;          /* 0 = 1/240                                                   */
     uint32_t prefetch_resets;   /* Kuka, opt-in (0 = off): keep a ready post-reset state per env so that a lockstep
-                                   step never runs reset() inside the launch; the records are advanced by a helper CTA
-                                   appended to every step / rollout launch (bulk fill: srl_sim_prefetch_resets)        */
+                                   step never runs reset() inside the launch; the records are advanced by the idle slot
+                                   of every warp of every step / rollout launch (bulk fill: srl_sim_prefetch_resets)   */
     uint64_t global_env_offset; /* global index of local env 0 (multi-GPU sharding)            */
 } srl_cfg;
 
@@ -173,8 +173,10 @@ int srl_sim_rollout_host(srl_sim* sim, int T, const void* actions, const float* 
  * env index, episode index), so it can be produced ahead of time; a step whose env finishes an episode then copies the record in
  * instead of running reset()'s five random micro-steps inside the launch; if no record is ready it resets in the launch as
  * before -- results never depend on which of the two happened.  With the option on, EVERY srl_sim_step / srl_sim_rollout launch
- * carries one extra helper CTA that advances up to 128 incomplete records by one random micro-step per env step of the launch,
- * so no call is needed in steady state (and a captured CUDA graph of step launches just works).  This entry point is the BULK
+ * uses the first idle slot of each of its warps (a batch is spread over all warp schedulers, so a warp carries fewer envs than it has
+ * slots) to advance one incomplete record of that warp's envs by one random micro-step per env step of the launch -- the helper runs
+ * the same instructions as its warp, at no extra cost -- so no call is needed in steady state (and a captured CUDA graph of step
+ * launches just works).  This entry point is the BULK
  * fill: it completes the records of all envs that have none, in one launch of its own -- call it once after srl_sim_reset of all
  * envs if the first episodes are short.  Stream-ordered like every other call; when `stream` differs from the stream of the
  * handle's step launches the library orders the two with events (it never overlaps them).  No-op (returns 0) for handles

@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include "kuka_params.cuh"
 #include "philox.cuh"
+#include "kuka_coop.cuh"
 
 #define KK_DEV __device__ __forceinline__
 // Code-shape switches (measured on B200, see DESIGN.md "Kernel code shape"): per-body passes as rolled loops over
@@ -42,6 +43,15 @@
 // as r'_j = sigma_j (v_j - target_j) and M^-1 as sigma_i sigma_j A_ij (sigma = 2 max_imp), which keeps the matrix symmetric (78 registers).
 #ifndef KK_SWEEP_SAT
 #define KK_SWEEP_SAT 1
+#endif
+// a second copy of the sweep loop without the contact watch, taken when no lane of the warp has a contact row to watch
+#ifndef KK_SWEEP_TIGHT
+#define KK_SWEEP_TIGHT 1
+#endif
+// fold the previous row's contribution into the impulse update (shorter loop-carried path, one more FFMA per row) or not: with the FFMA.SAT
+// clamp the plain form is already issue-bound (B200, 4096 envs x 128 steps: 5.07 ms against 5.15 ms deferred; profiles/r02_ab_kuka_sweep.txt)
+#ifndef KK_SWEEP_DEFER
+#define KK_SWEEP_DEFER 0
 #endif
 // lam += d in place instead of lam = s (one FADD on the FMA pipe per row instead of a half-rate MOV at the loop end)
 #ifndef KK_SWEEP_LAM_ACC
@@ -662,17 +672,46 @@ KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
 // (computed by the caller with kuka_fk<true>); on return q, qd, qb, qdb are advanced by one time step.
 // JOINTS: use_inverse_kinematics = False (action_joints): the 7 arm set-points are given (`q_joints`), no IK (kuka.py:158-161).
 // TWOB: Kuka2ButtonGymEnv -- a second button glider (DoF KK_NB + 1) with the same motor / limit rows, right after the first.
-template <bool JOINTS, bool TWOB>
-KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed, const float* q_joints) {
+// COOP: the env is a group of 4 lanes (kuka_coop.cuh): kinematics, contact manifold, mass-matrix inverse, bias and contact rows come from
+// the group's scratch area `sc` (k / ct are unused); every lane of the group runs the row set-up and the sweeps on identical values.
+struct KkNoScratch { float dummy; KK_DEV float& operator[](int) const { return const_cast<float&>(dummy); } };
+template <bool JOINTS, bool TWOB, bool COOP = false, class SC = KkNoScratch>
+KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed, const float* q_joints,
+                              const SC& sc = SC(), int u = 0, unsigned gmask = 0u, int nc_coop = 0) {
     constexpr int ND = TWOB ? KK_NB + 2 : KK_NB + 1;
     // ---- applyAction: IK + motor set-points (kuka.py:142-187) ----
     float q_ik[7];
     if (JOINTS) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) q_ik[j] = q_joints[j];
+    } else if constexpr (COOP) {
+        KukaKin kk7;            // what the IK reads: axes and origins of the 7 arm joints, rotation of link 6 (static indices: registers)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            kk7.a[j] = mk3(sc[j * KC_BS + KB_A], sc[j * KC_BS + KB_A + 1], sc[j * KC_BS + KB_A + 2]);
+            kk7.p[j] = mk3(sc[j * KC_BS + KB_P], sc[j * KC_BS + KB_P + 1], sc[j * KC_BS + KB_P + 2]);
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) kk7.R6[t] = sc[6 * KC_BS + KB_R + t];
+        kuka_ik(P, e, kk7, q_ik);
     } else kuka_ik(P, e, k, q_ik);
     // ---- dynamics ----
     float A[KK_NB][KK_NB], bias[KK_NB];
+    if constexpr (COOP) {
+#if defined(__CUDACC__)
+        __syncwarp(gmask);      // every lane has read link 6's rotation: the wrench phase reuses its storage
+        kc_dynamics(sc, P, e.qd, u, gmask);
+#endif
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) {
+            bias[i] = sc[KC_OFF_BIAS + i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) A[i][j] = sc[KC_OFF_MA + i * KC_MS + j];
+        }
+        // Cholesky + M^-1 in registers, by every lane: dealt to the 4 lanes through shared memory it was three times slower (12 dependent
+        // pivot steps of load -> rsqrt -> scale -> store -> barrier; measured on B200, profiles/r02_kuka_coop_by_function.txt)
+        kuka_spd_inverse(A);
+    } else {
 #if KK_ROLL_DYN
     {
         float Mloc[KK_NB][KK_NB], bloc[KK_NB];  // thread-local (dynamically indexed by the rolled loops)
@@ -688,6 +727,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     kuka_dynamics(P, e, k, A, bias);
 #endif
     kuka_spd_inverse(A);
+    }
     float v[ND];
     {
         float rhs[KK_NB];
@@ -735,8 +775,22 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         lim_lam_lo[i] = 0.f; lim_lam_hi[i] = 0.f;
     }
     // ---- contact rows: J, W = M^-1 J^T, 1/D, target; two friction rows each (rare path, local memory) ----
-    const int nc = ct.n;
-    float cJ[3 * KK_MAXC][ND], cW[3 * KK_MAXC][ND], c_invd[3 * KK_MAXC], c_tgt[3 * KK_MAXC], c_lam[3 * KK_MAXC];
+    const int nc = COOP ? nc_coop : ct.n;
+    float cJ[COOP ? 1 : 3 * KK_MAXC][ND], cW[COOP ? 1 : 3 * KK_MAXC][ND], c_invd[COOP ? 1 : 3 * KK_MAXC], c_tgt[COOP ? 1 : 3 * KK_MAXC], c_lam[3 * KK_MAXC];
+#define KK_CJ(r, j) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + (j)] : cJ[COOP ? 0 : (r)][j])
+#define KK_CW(r, j) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 14 + (j)] : cW[COOP ? 0 : (r)][j])
+#define KK_CINVD(r) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 28] : c_invd[COOP ? 0 : (r)])
+#define KK_CTGT(r) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 29] : c_tgt[COOP ? 0 : (r)])
+    if constexpr (COOP) {
+        if (nc > 0) {           // rows dealt to the 4 lanes, through the scratch area
+#if defined(__CUDACC__)
+            __syncwarp(gmask);
+            kc_ph_rows<TWOB>(sc, P, A, nc, u);
+            __syncwarp(gmask);
+#endif
+            for (int r = 0; r < 3 * nc; ++r) c_lam[r] = 0.f;
+        }
+    } else
     if (nc > 0) {
         for (int r = 0; r < 3 * nc; ++r) {
             const int c = r < nc ? r : (r - nc) >> 1;
@@ -831,10 +885,10 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         for (int c = 0; c < nc; ++c) {
             float off = 0.f;
 #pragma unroll
-            for (int j = 0; j < KK_NB; ++j) { off = fmaf(cJ[c][j], tgt[j], off); cJw[c][j] = cJ[c][j] * P.sat_isig[j]; }
+            for (int j = 0; j < KK_NB; ++j) { off = fmaf(KK_CJ(c, j), tgt[j], off); cJw[c][j] = KK_CJ(c, j) * P.sat_isig[j]; }
 #pragma unroll
-            for (int j = KK_NB; j < ND; ++j) cJw[c][j] = cJ[c][j];
-            c_wt[c] = c_tgt[c] - off;
+            for (int j = KK_NB; j < ND; ++j) cJw[c][j] = KK_CJ(c, j);
+            c_wt[c] = KK_CTGT(c) - off;
         }
 #define KK_WATCH_J(c, j) cJw[c][j]
 #else
@@ -844,12 +898,12 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         for (int c = 0; c < nc; ++c) {
             float off = 0.f;
 #pragma unroll
-            for (int j = 0; j < KK_NB; ++j) off = fmaf(cJ[c][j], tgt[j], off);
-            c_wt[c] = c_tgt[c] - off;
+            for (int j = 0; j < KK_NB; ++j) off = fmaf(KK_CJ(c, j), tgt[j], off);
+            c_wt[c] = KK_CTGT(c) - off;
         }
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) v[i] -= tgt[i];
-#define KK_WATCH_J(c, j) cJ[c][j]
+#define KK_WATCH_J(c, j) KK_CJ(c, j)
 #endif
         // loop invariants of the button rows in vector registers (opaque copies: no uniform-register / constant-bank reloads inside the sweep)
         float bminv, nbminv, lo_hi, hi_hi, lo_t, hi_t;
@@ -860,64 +914,96 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         asm volatile("mov.f32 %0, %1;" : "=f"(lo_t) : "f"(bl_lo_t));
         asm volatile("mov.f32 %0, %1;" : "=f"(hi_t) : "f"(bl_hi_t));
         bool act = false;        // a watched contact row would activate in sweep `it - 1`
+        bool more = true;
         int it = 0;
+        // one sweep over the button rows and the 12 motor rows
+#if KK_SWEEP_SAT
+#if KK_SWEEP_DEFER
+#define KK_ROW(i)                                                                                                        \
+                    float s;                                                                                             \
+                    if (i == 0) s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                             \
+                    else {                                                                                               \
+                        const float e = fmaf(-cs[i], v[i], lam[i]);   /* off the critical path (v[i] lacks row i-1's update) */ \
+                        s = __saturatef(fmaf(-kk[i], dprev, e));      /* critical path: FFMA.SAT */                      \
+                        v[i] = fmaf(A[i][i - 1], dprev, v[i]);        /* deferred update from row i-1 */                 \
+                    }                                                                                                    \
+                    const float d = s - lam[i];                                                                          \
+                    if (KK_SWEEP_LAM_ACC) lam[i] += d; else lam[i] = s;   /* in place: no register rename, no MOV at the loop end; equals s whenever s - lam is exact */
+#define KK_ROW_SKIP(i, j) ((j) == (i) + 1)
+#else
+#define KK_ROW(i)                                                                                                        \
+                    const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                             \
+                    const float d = s - lam[i];                                                                          \
+                    if (KK_SWEEP_LAM_ACC) lam[i] += d; else lam[i] = s;
+#define KK_ROW_SKIP(i, j) false
+#endif
+#else
+#define KK_ROW(i)                                                                                                        \
+                    const float e = fmaf(-invd[i], v[i], lam[i]);                  /* v[i] holds v_i - target_i */       \
+                    const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        /* critical path */                   \
+                    if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             /* deferred update from row i-1 */    \
+                    const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);                                                   \
+                    const float d = s - lam[i];                                                                          \
+                    lam[i] = s;
+#define KK_ROW_SKIP(i, j) ((j) == (i) + 1)
+#endif
+#define KK_SWEEP_BODY()                                                                                                  \
+                {   /* button motor + the two limit rows (an independent 1-DoF chain, fills issue slots) */              \
+                    float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);                          \
+                    v[KK_NB] = fmaf(bminv, s - b_lam, v[KK_NB]); b_lam = s;                                              \
+                    s = fminf(fmaxf(fmaf(lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), lo_hi);                              \
+                    v[KK_NB] = fmaf(bminv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;                                      \
+                    s = fminf(fmaxf(fmaf(hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), hi_hi);                              \
+                    v[KK_NB] = fmaf(nbminv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;                                     \
+                }                                                                                                        \
+                KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()                                                                   \
+                float dprev = 0.f;                                                                                       \
+                _Pragma("unroll")                                                                                        \
+                for (int i = 0; i < KK_NB; ++i) {                                                                        \
+                    KK_ROW(i)                                                                                            \
+                    _Pragma("unroll")                                                                                    \
+                    for (int j = 0; j < KK_NB; ++j)                                                                      \
+                        if (!KK_ROW_SKIP(i, j)) v[j] = fmaf(KK_A(j, i), d, v[j]);   /* v[i+1] is updated by the next row when deferred */ \
+                    dprev = d;                                                                                           \
+                }
         if (P.iters > 0) {
             int left = P.iters;
             asm volatile("mov.u32 %0, %0;" : "+r"(left));
-            constexpr int sweep_unroll = KK_SWEEP_UNROLL;
-#pragma unroll sweep_unroll
-            do {
-                {   // button motor + the two limit rows (an independent 1-DoF chain, fills issue slots)
-                    float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);
-                    v[KK_NB] = fmaf(bminv, s - b_lam, v[KK_NB]); b_lam = s;
-                    s = fminf(fmaxf(fmaf(lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), lo_hi);
-                    v[KK_NB] = fmaf(bminv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
-                    s = fminf(fmaxf(fmaf(hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), hi_hi);
-                    v[KK_NB] = fmaf(nbminv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;
-                }
-                KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
-                float dprev = 0.f;
-#pragma unroll
-                for (int i = 0; i < KK_NB; ++i) {
-#if KK_SWEEP_SAT
-                    float s;
-                    if (i == 0) s = __saturatef(fmaf(-cs[i], v[i], lam[i]));
-                    else {
-                        const float e = fmaf(-cs[i], v[i], lam[i]);                // off the critical path (v[i] lacks row i-1's update)
-                        s = __saturatef(fmaf(-kk[i], dprev, e));                   // critical path: FFMA.SAT
-                        v[i] = fmaf(A[i][i - 1], dprev, v[i]);                     // deferred update from row i-1
-                    }
-                    const float d = s - lam[i];
-#if KK_SWEEP_LAM_ACC
-                    lam[i] += d;      // in place (no register rename, no MOV at the loop end); equals s whenever s - lam is exact
+#if defined(__CUDA_ARCH__) && KK_SWEEP_TIGHT
+            // 93 % of the warp-sweeps watch no contact in ANY lane (profiles/r02): those run a loop that is nothing but the rows and one
+            // back edge (the watch's reconvergence scaffolding cost ~40 cycles per sweep).  Warp-uniform choice: no divergence.
+            const bool quiet = __all_sync(__activemask(), nc == 0);
 #else
-                    lam[i] = s;
+            const bool quiet = false;
 #endif
-#else
-                    const float e = fmaf(-invd[i], v[i], lam[i]);                  // v[i] holds v_i - target_i
-                    const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        // critical path
-                    if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             // deferred update from row i-1
-                    const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);
-                    const float d = s - lam[i];
-                    lam[i] = s;
-#endif
-#pragma unroll
-                    for (int j = 0; j < KK_NB; ++j)
-                        if (j != i + 1) v[j] = fmaf(KK_A(j, i), d, v[j]);          // v[i+1] is updated by the next row
-                    dprev = d;
-                }
-                ++it;
-                if (nc > 0) {
+            if (quiet) {
 #pragma unroll 1
-                    for (int c = 0; c < nc; ++c) {
-                        float jv = 0.f;
+                do { KK_SWEEP_BODY() (void)dprev; } while (--left > 0);
+                it = P.iters;
+            } else {
+                constexpr int sweep_unroll = KK_SWEEP_UNROLL;
+#pragma unroll sweep_unroll
+                do {
+                    KK_SWEEP_BODY()
+                    (void)dprev;
+                    ++it;
+                    more = --left > 0;
+                    if (nc > 0) {
+#pragma unroll 1
+                        for (int c = 0; c < nc; ++c) {
+                            float jv = 0.f;
 #pragma unroll
-                        for (int j = 0; j < ND; ++j) jv = fmaf(KK_WATCH_J(c, j), v[j], jv);
-                        act = act | (c_wt[c] - jv > 0.f);
+                            for (int j = 0; j < ND; ++j) jv = fmaf(KK_WATCH_J(c, j), v[j], jv);
+                            act = act | (c_wt[c] - jv > 0.f);
+                        }
+                        if (act) more = false;
                     }
-                }
-            } while (--left > 0 && !act);
+                } while (more);
+            }
         }
+#undef KK_SWEEP_BODY
+#undef KK_ROW
+#undef KK_ROW_SKIP
         if (act) { it0 = it - 1; resume_mid_sweep = true; } else it0 = it;
 #undef KK_WATCH_J
 #if KK_SWEEP_SAT
@@ -991,13 +1077,13 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 }
                 float jv = 0.f;
 #pragma unroll
-                for (int j = 0; j < ND; ++j) jv = fmaf(cJ[r][j], v[j], jv);
-                const float s = fminf(fmaxf(fmaf(c_tgt[r] - jv, c_invd[r], c_lam[r]), lo), hi);
+                for (int j = 0; j < ND; ++j) jv = fmaf(KK_CJ(r, j), v[j], jv);
+                const float s = fminf(fmaxf(fmaf(KK_CTGT(r) - jv, KK_CINVD(r), c_lam[r]), lo), hi);
                 const float d = s - c_lam[r];
                 if (d == 0.f) continue;       // inactive (separating) contact: nothing to apply
                 c_lam[r] = s;
 #pragma unroll
-                for (int j = 0; j < ND; ++j) v[j] = fmaf(cW[r][j], d, v[j]);
+                for (int j = 0; j < ND; ++j) v[j] = fmaf(KK_CW(r, j), d, v[j]);
             }
         }
     }

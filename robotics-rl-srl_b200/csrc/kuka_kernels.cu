@@ -12,6 +12,7 @@
 // parameter block (constant bank, folded into FFMA operands).  HBM traffic is the SoA state once per launch
 // (float4 / int4 records, coalesced) plus action + noise in and obs + reward + done out per step.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -29,19 +30,22 @@ struct KukaDev {
     int4*   cnt2;    // episode, total_steps, ep_len, moving button: high word of the float64 target y / two buttons: n_contacts[1]
     float4* btn2;    // two buttons only: second glider q, qd, second button base x, y
     KukaParams P;
-    int epw;         // live lanes per warp
+    int epw;         // live env slots per warp (lanes, or groups of 4 lanes when coop)
+    int coop;        // 1: four lanes per env (kuka_coop.cuh), epw <= 8
 };
 
 // "Next episode" records (opt-in, srl_cfg.prefetch_resets): the post-reset state of every env's NEXT episode -- a pure function of
 // (seed, global env index, episode index) -- produced ahead of time, so that a LOCKSTEP step whose env finishes an episode copies a
 // record in instead of running reset()'s five random micro-steps inside the launch (measured: every steady-state launch of 4096 envs
 // contains such an env and costs 343 us instead of ~70, profiles/r01_step_launch_timing.txt).
-// Who produces them (round 2): a HELPER CTA appended to every rollout / step launch of the handle.  It scans the flags, takes up to 128
-// envs without a complete record and advances each of their records by (at most T) random micro-steps of reset() -- ONE per lockstep
-// launch, so the helper finishes with the stepping CTAs and the launch stays one physics step long; a record is complete after five
-// launches.  The 147 stepping CTAs of 4096 envs leave one of the 148 SMs free, which is where the helper lands.  (Round 1's version ran
-// the whole five-step reset in a separate launch on a side stream: validated on B200 in round 2 -- bit-identical, memcheck clean -- but its
-// 270 us launches shared schedulers with 2-4 following step launches and doubled their duration: 137 us median instead of 70.)
+// Who produces them (round 2): the first IDLE SLOT of every warp of every rollout / step launch.  A batch is spread over all warp schedulers, so
+// a warp carries fewer envs (7 of 8 groups of 4 lanes, or 7 of 32 lanes, at 4096 envs) than it has slots; the idle slot picks one env of its
+// own warp whose record is incomplete and advances that record by (at most T) random micro-steps of reset() -- ONE per lockstep launch, the
+// very instructions its warp is executing anyway, so the launch stays one physics step long and costs no extra issue slot; a record is
+// complete after five launches.  (Round 1's version ran the whole five-step reset in a separate launch on a side stream: validated on B200
+// in round 2 -- bit-identical, memcheck clean -- but its 270 us launches shared schedulers with 2-4 following step launches and doubled their
+// duration: 137 us median instead of 70.  A helper CTA on the 148th SM worked too -- 124 us -- but cannot serve enough records once an env
+// takes 4 lanes.)
 // op = PREFETCH as a launch of its own (srl_sim_prefetch_resets) remains as the bulk fill after an explicit reset of all envs.
 // Same member names as KukaDev's state arrays: env_load / env_store work on either.
 struct KukaNext {
@@ -196,14 +200,6 @@ KK_DEV void reset_end(const KukaParams& P, KukaEnv& e) {
     e.episode += 1;
 }
 
-// thread -> env mapping with `epw` live lanes per warp
-KK_DEV int env_index(int n, int epw) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (lane >= epw) return -1;
-    const int i = warp * epw + lane;
-    return i < n ? i : -1;
-}
-
 enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2, KUKA_OP_PREFETCH = 3 };
 
 // ONE kernel for reset, lockstep step and fused T-step rollout.  Every thread runs a single micro-step loop
@@ -217,31 +213,50 @@ enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2, KUKA_OP_PREFE
 //   op = PREFETCH (PREFETCH instantiation only): reset() of the env's NEXT episode into its `nx` record, for the envs whose record is
 //                 not valid -- the very instructions of the in-launch reset, so a record and an in-launch reset agree bit for bit
 // PREFETCH = false (the default instantiations): `nx` is ignored and the kernel is what it was before the feature existed.
-template <bool JOINTS, bool TWOB, bool PREFETCH = false>
+template <bool JOINTS, bool TWOB, bool PREFETCH = false, bool COOP = false>
 __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
                                                        const void* __restrict__ actions, const float* __restrict__ noise,
                                                        const uint8_t* __restrict__ mask, const double* __restrict__ draws,
                                                        float* __restrict__ obs, float* __restrict__ rew,
                                                        uint8_t* __restrict__ done, float* __restrict__ ep_ret,
                                                        int32_t* __restrict__ ep_len, float* __restrict__ snap, const KukaNext nx) {
-    int i;
-    bool helper = false;         // PREFETCH: this thread belongs to the helper CTA and advances one env's next-episode record
+    // Thread -> env.  One thread per env (COOP = false: lane l of a warp carries the warp's env l, `epw` live lanes), or a GROUP of 4 adjacent
+    // lanes per env (COOP = true: kuka_coop.cuh; group g = lane / 4 carries env g, `epw` <= 8 live groups): all 4 lanes hold identical copies of
+    // the env state and run the env logic and the sweeps redundantly; `u` = lane within the group deals out the once-per-step work.
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = COOP ? lane >> 2 : lane;            // env slot within the warp
+    const int u = COOP ? lane & 3 : 0;
+    const bool lead = !COOP || u == 0;                   // the lane of the group that talks to global memory
+    const unsigned gmask = COOP ? 0xFu << (lane & ~3) : 0u;
+    extern __shared__ float4 kc_smem[];
+    float* const kc_tab = reinterpret_cast<float*>(kc_smem);                                   // per-CTA model tables
+    KcScratch sc;                                                                              // this env's scratch area
+    sc.b = reinterpret_cast<float*>(kc_smem) + ((KC_CONST_WORDS + 31) / 32) * 32 + (8 * (threadIdx.x >> 5) + (lane >> 2)) * KC_ES;
+    if constexpr (COOP) {
+        kc_fill_const(d.P, kc_tab, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    int i = -1;
+    if (slot < d.epw) { i = warp * d.epw + slot; if (i >= n) i = -1; }
+    bool helper = false;         // PREFETCH: this thread (group) advances the next-episode record of one env of its warp
     if constexpr (PREFETCH) {
-        if (nx.helper && op == KUKA_OP_ROLLOUT && blockIdx.x == gridDim.x - 1) {
-            // helper CTA: collect up to blockDim.x envs whose record is incomplete, records in progress first
-            __shared__ int h_list[128];
-            __shared__ int h_cnt;
-            if (threadIdx.x == 0) h_cnt = 0;
-            __syncthreads();
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int j = threadIdx.x; j < n; j += blockDim.x)
-                    if (!nx.valid[j] && ((nx.progress[j] > 0) == (pass == 0))) { const int k = atomicAdd(&h_cnt, 1); if (k < 128) h_list[k] = j; }
-                __syncthreads();
+        // helper slot = the first idle slot of the warp: it runs the same micro-step loop as the warp's envs (SIMT: at no extra issue cost)
+        if (nx.helper && op == KUKA_OP_ROLLOUT && slot == d.epw && slot < (COOP ? 8 : 32)) {
+            int pick = -1;
+            if (lead) {          // first env of this warp whose record is incomplete, a record in progress first
+                int best = -1;
+                for (int k2 = 0; k2 < d.epw; ++k2) {
+                    const int j = warp * d.epw + k2;
+                    if (j < n && !reinterpret_cast<volatile const uint8_t*>(nx.valid)[j]) {
+                        const int pr = nx.progress[j];
+                        if (pr > best) { best = pr; pick = j; }
+                    }
+                }
             }
-            if ((int)threadIdx.x >= h_cnt || threadIdx.x >= 128) return;
-            i = h_list[threadIdx.x]; helper = true; op = KUKA_OP_PREFETCH;
-        } else i = env_index(n, d.epw);
-    } else i = env_index(n, d.epw);
+            if (COOP) pick = __shfl_sync(gmask, pick, lane & ~3);
+            if (pick >= 0) { i = pick; helper = true; op = KUKA_OP_PREFETCH; }
+        }
+    }
     if (i < 0) return;
     if (op == KUKA_OP_RESET && mask && !mask[i]) return;
     if constexpr (PREFETCH) { if (op == KUKA_OP_PREFETCH && !helper && nx.valid[i]) return; }
@@ -250,6 +265,12 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     const size_t N = (size_t)n;
     KukaEnv e; KukaKin k; KukaContacts ct;
     env_load<TWOB>(d, i, e);
+    int nc_reg = 0;              // COOP: contact rows of the current configuration (the manifold itself lives in the scratch area)
+    if constexpr (PREFETCH) {
+        // the helper slot has read the live state and the record flags of an env that another slot of this warp is about to step:
+        // nobody moves on before everybody has loaded
+        __syncwarp();
+    }
 
     int reset_left = 0;          // > 0: inside reset(), this many random micro-steps to go
     bool in_reset = false;       // reset() in progress (finalised when reset_left reaches 0)
@@ -285,14 +306,28 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 env_load<TWOB, true>(nx, i, e);
                 in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT - prog;
             } else {
-                if (helper) nx.episode[i] = (int)e.episode;
+                if (helper && lead) nx.episode[i] = (int)e.episode;
                 reset_begin<TWOB>(P, e, nullptr, genv);
                 in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
             }
         }
     }
     for (;;) {
-        kuka_fk<true, TWOB>(P, e, k, ct);  // link states of the configuration just reached + collision detection for the next step
+        // link states of the configuration just reached + collision detection for the next step
+        if constexpr (COOP) {
+            KcKinIn kin;
+#pragma unroll
+            for (int j = 0; j < KK_NB; ++j) kin.q[j] = e.q[j];
+            kin.qb = e.qb; kin.qb2 = e.qb2; kin.bbx = e.bbx; kin.bby = e.bby; kin.bbz = e.bbz; kin.bb2x = e.bb2x; kin.bb2y = e.bb2y;
+            __syncwarp(gmask);   // the group is done with the rows / matrices of the previous micro-step (the candidates reuse that storage)
+            const bool near = kc_kinematics<TWOB>(sc, kc_tab, P, kin, u, gmask);
+            e.grip[0] = sc[8 * KC_BS + KB_C]; e.grip[1] = sc[8 * KC_BS + KB_C + 1]; e.grip[2] = sc[8 * KC_BS + KB_C + 2];   // getLinkState(kuka, 8)[0]: COM of link 8
+            e.eepos[0] = sc[6 * KC_BS + KB_P]; e.eepos[1] = sc[6 * KC_BS + KB_P + 1]; e.eepos[2] = sc[6 * KC_BS + KB_P + 2];
+            const int fl = near ? (int)sc[KC_OFF_LINK + 6] : 0;
+            e.cbutton = fl & 1; e.ctable = (fl >> 1) & 1;
+            if (TWOB) { e.cany0 = (fl >> 2) & 1; e.cany1 = (fl >> 3) & 1; }
+            nc_reg = near ? (int)sc[KC_OFF_LINK + 7] : 0;
+        } else kuka_fk<true, TWOB>(P, e, k, ct);
         const int new_cb = e.cbutton, new_ct = e.ctable, new_a0 = TWOB ? e.cany0 : 0, new_a1 = TWOB ? e.cany1 : 0;
         if (pending) {
             // ---- _reward() (:428-463): manifold of the step that just ran, link states after it ----
@@ -335,25 +370,32 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             }
             const bool is_done = e.terminated || e.counter > P.max_steps;  // _termination() (:422-426)
             e.ep_ret += reward; e.ep_len += 1;
-            if (rew) rew[off] = reward;
-            if (done) done[off] = is_done ? 1 : 0;
-            if (is_done) {
+            if (rew && lead) rew[off] = reward;
+            if (done && lead) done[off] = is_done ? 1 : 0;
+            if (is_done && lead) {
                 if (ep_ret) ep_ret[off] = e.ep_ret;
                 if (ep_len) ep_len[off] = e.ep_len;
             }
             if (is_done && P.auto_reset) {   // SubprocVecEnv worker: reset and return the post-reset observation
                 if constexpr (PREFETCH) {
-                    if (op == KUKA_OP_ROLLOUT && reinterpret_cast<volatile const uint8_t*>(nx.valid)[i]) {
-                        __threadfence();     // the record was written before the flag (message passing with op = PREFETCH)
-                        const bool match = reinterpret_cast<volatile const int32_t*>(nx.episode)[i] == (int)e.episode;
-                        if (match) {
+                    if (op == KUKA_OP_ROLLOUT) {
+                        // 0: no record, 1: a complete record for another episode (explicit reset in between: dropped), 2: the record of this episode.
+                        // Read by the group's lead lane and broadcast: the 4 lanes must take the same branch whatever the helper is doing meanwhile
+                        int rec = 0;
+                        if (lead && reinterpret_cast<volatile const uint8_t*>(nx.valid)[i]) {
+                            __threadfence();     // the record was written before the flag (message passing with op = PREFETCH)
+                            rec = reinterpret_cast<volatile const int32_t*>(nx.episode)[i] == (int)e.episode ? 2 : 1;
+                        }
+                        if (COOP) rec = __shfl_sync(gmask, rec, lane & ~3);
+                        if (rec == 2) {
                             const uint32_t total_steps = e.total_steps;         // the only field that runs across episodes
                             env_load<TWOB, true>(nx, i, e);
                             e.total_steps = total_steps;
                             __threadfence();   // the record is read before the flag is cleared: a PREFETCH thread that sees 0 may overwrite it
+                            if (COOP) __syncwarp(gmask);
                         }
-                        reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 0;   // consumed, or produced for another episode (explicit reset in between): refreshed by the next PREFETCH
-                        if (match) {
+                        if (rec && lead) reinterpret_cast<volatile uint8_t*>(nx.valid)[i] = 0;   // consumed or stale: to be produced again
+                        if (rec == 2) {
                             saved_cb = e.cbutton; saved_ct = e.ctable;           // what the in-launch reset leaves behind: the manifold flags of its last micro-step
                             if (TWOB) { saved_a0 = e.cany0; saved_a1 = e.cany1; }
                             consumed = true; in_reset = true; reset_left = 0;
@@ -366,19 +408,21 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                 in_reset = true; reset_left = N_RANDOM_ACTIONS_AT_INIT;
                 continue;                      // the snapshot configuration needs its own kinematics
             }
-            if (obs) { float* o = obs + 3 * off; o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2]; }
+            if (obs && lead) { float* o = obs + 3 * off; o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2]; }
             ++t;
         }
         if (in_reset && reset_left == 0) {
             in_reset = false;
             if (op == KUKA_OP_SETTLE) {
-                for (int j = 0; j < KK_NB; ++j) { snap[j] = e.q[j]; snap[KK_NB + j] = e.qd[j]; }
-                snap[24] = e.ee[0]; snap[25] = e.ee[1]; snap[26] = e.ee[2]; snap[27] = e.qb; snap[28] = e.qdb;
+                if (lead) {
+                    for (int j = 0; j < KK_NB; ++j) { snap[j] = e.q[j]; snap[KK_NB + j] = e.qd[j]; }
+                    snap[24] = e.ee[0]; snap[25] = e.ee[1]; snap[26] = e.ee[2]; snap[27] = e.qb; snap[28] = e.qdb;
+                }
                 return;
             }
             if (!(PREFETCH && consumed)) reset_end<TWOB>(P, e);
             consumed = false;
-            if (obs && op != KUKA_OP_PREFETCH) {  // getSRLState after reset (:278-279)
+            if (obs && lead && op != KUKA_OP_PREFETCH) {  // getSRLState after reset (:278-279)
                 float* o = obs + 3 * (op == KUKA_OP_RESET ? (size_t)i : (size_t)t * N + (size_t)i);
                 o[0] = e.grip[0] - e.tgt[0]; o[1] = e.grip[1] - e.tgt[1]; o[2] = e.grip[2] - e.tgt[2];
             }
@@ -465,7 +509,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         // ---- applyAction + stepSimulation ----
         if (!JOINTS) apply_ee_delta(P, e, dx, dy, dz);
         saved_cb = new_cb; saved_ct = new_ct; saved_a0 = new_a0; saved_a1 = new_a1;
-        kuka_physics_step<JOINTS, TWOB>(P, e, k, ct, armed, qj);
+        kuka_physics_step<JOINTS, TWOB, COOP>(P, e, k, ct, armed, qj, sc, u, gmask, nc_reg);
         if constexpr (PREFETCH) { if (helper && --budget <= 0 && reset_left > 0) { partial = true; break; } }
         if (!in_reset) {
             // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
@@ -477,6 +521,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     if (TWOB) { e.cany0 = saved_a0; e.cany1 = saved_a1; }
     if constexpr (PREFETCH) {
         if (op == KUKA_OP_PREFETCH) {
+            if (!lead) return;
             env_store<TWOB>(nx, i, e);
             if (partial) { nx.progress[i] = (uint8_t)(N_RANDOM_ACTIONS_AT_INIT - reset_left); return; }   // nx.episode[i] was set when the record was begun
             nx.episode[i] = (int)e.episode - 1;   // record first, then the episode it is for, then the flag
@@ -486,7 +531,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             return;
         }
     }
-    env_store<TWOB>(d, i, e);
+    if (lead) env_store<TWOB>(d, i, e);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -581,14 +626,38 @@ bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P
     return true;
 }
 
-// one instantiation per (action_joints, two_buttons): the default kernel pays nothing for the variants
-#define KUKA_LAUNCH(d, grid, block, st, ...)                                                                            \
-    do {                                                                                                                \
-        if ((d)->P.two_buttons) {                                                                                       \
-            if ((d)->P.action_joints) kuka_kernel<true, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});    \
-            else kuka_kernel<false, true><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});                        \
-        } else if ((d)->P.action_joints) kuka_kernel<true, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{}); \
-        else kuka_kernel<false, false><<<grid, block, 0, st>>>(*(d), __VA_ARGS__, KukaNext{});                           \
+// one instantiation per (action_joints, two_buttons, four-lanes-per-env): the default kernel pays nothing for the variants
+#define KUKA_SMEM_BYTES ((size_t)(((KC_CONST_WORDS + 31) / 32) * 32 + 32 * KC_ES) * sizeof(float))   /* 4 warps x 8 env slots */
+template <bool J, bool T2, bool PF, bool CO>
+cudaError_t kuka_launch_inst(const KukaDev* d, int grid, int block, cudaStream_t st, int n, int op, int T, const void* actions, const float* noise,
+                             const uint8_t* mask, const double* draws, float* obs, float* rew, uint8_t* done, float* ep_ret, int32_t* ep_len,
+                             float* snap, const KukaNext& nx) {
+    const size_t smem = CO ? KUKA_SMEM_BYTES : 0;
+    static bool attr_set = false;
+    if (CO && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kuka_kernel<J, T2, PF, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kuka_kernel<J, T2, PF, CO><<<grid, block, smem, st>>>(*d, n, op, T, actions, noise, mask, draws, obs, rew, done, ep_ret, ep_len, snap, nx);
+    return cudaGetLastError();
+}
+#define KUKA_LAUNCH(d, grid, block, st, ...)                                                                             \
+    do {                                                                                                                 \
+        const KukaNext nx0 = KukaNext{};                                                                                 \
+        cudaError_t le;                                                                                                  \
+        const int jt = ((d)->P.action_joints ? 1 : 0) | ((d)->P.two_buttons ? 2 : 0) | ((d)->coop ? 4 : 0);              \
+        switch (jt) {                                                                                                    \
+        case 0: le = kuka_launch_inst<false, false, false, false>(d, grid, block, st, __VA_ARGS__, nx0); break;          \
+        case 1: le = kuka_launch_inst<true, false, false, false>(d, grid, block, st, __VA_ARGS__, nx0); break;           \
+        case 2: le = kuka_launch_inst<false, true, false, false>(d, grid, block, st, __VA_ARGS__, nx0); break;           \
+        case 3: le = kuka_launch_inst<true, true, false, false>(d, grid, block, st, __VA_ARGS__, nx0); break;            \
+        case 4: le = kuka_launch_inst<false, false, false, true>(d, grid, block, st, __VA_ARGS__, nx0); break;           \
+        case 5: le = kuka_launch_inst<true, false, false, true>(d, grid, block, st, __VA_ARGS__, nx0); break;            \
+        case 6: le = kuka_launch_inst<false, true, false, true>(d, grid, block, st, __VA_ARGS__, nx0); break;            \
+        default: le = kuka_launch_inst<true, true, false, true>(d, grid, block, st, __VA_ARGS__, nx0); break;            \
+        }                                                                                                                \
+        SRL_CUDA_OK(le);                                                                                                 \
     } while (0)
 
 // Host-side owner of the next-episode records of one handle (srl_sim::kuka_next); the kernel gets the pointer block by value.
@@ -626,6 +695,9 @@ int kuka_alloc(srl_sim* s, const void* blob, size_t bytes) {
     if (epw < 1) epw = 1;
     if (epw > 32) epw = 32;
     d->epw = epw;
+    // four lanes per env while a warp carries at most 8 envs (the whole batch still fits one warp per scheduler); SRL_KUKA_COOP=0 / 1 overrides
+    d->coop = epw <= 8 ? 1 : 0;
+    if (const char* co = getenv("SRL_KUKA_COOP")) d->coop = (atoi(co) != 0 && epw <= 8) ? 1 : 0;
     // the 500 settle steps of reset(), once
     float* snap = nullptr;
     SRL_CUDA_OK(cudaMalloc(&snap, 32 * sizeof(float)));
@@ -697,8 +769,9 @@ int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noi
         const bool capturing = cap != cudaStreamCaptureStatusNone;   // events recorded outside a capture cannot be waited for inside it
         if (s->pf_pending && !capturing) { SRL_CUDA_OK(cudaStreamWaitEvent(st, s->pf_ev, 0)); s->pf_pending = false; }
         KukaNext nx = nh->nx;
-        nx.helper = 1;          // + the helper CTA that advances the incomplete records by up to T micro-steps
-        kuka_kernel<false, false, true><<<grid + 1, block, 0, st>>>(*d, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nx);
+        nx.helper = 1;          // the first idle slot of every warp advances one incomplete record of its warp's envs by up to T micro-steps
+        if (d->coop) SRL_CUDA_OK((kuka_launch_inst<false, false, true, true>(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nx)));
+        else SRL_CUDA_OK((kuka_launch_inst<false, false, true, false>(d, grid, block, st, s->n, KUKA_OP_ROLLOUT, T, actions, noise, nullptr, nullptr, obs, rew, done, ep_ret, ep_len, nullptr, nx)));
         if (!capturing) { SRL_CUDA_OK(cudaEventRecord(s->roll_ev, st)); s->roll_ev_valid = true; }
     }
     else
@@ -716,8 +789,8 @@ int kuka_launch_prefetch(srl_sim* s, cudaStream_t st) {
     int grid, block; grid_for(s, d, grid, block);
     // never concurrent with a rollout launch of the handle: its helper CTA writes the same records
     if (s->roll_ev_valid) SRL_CUDA_OK(cudaStreamWaitEvent(st, s->roll_ev, 0));
-    kuka_kernel<false, false, true><<<grid, block, 0, st>>>(*d, s->n, KUKA_OP_PREFETCH, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nh->nx);
-    SRL_CUDA_OK(cudaGetLastError());
+    if (d->coop) SRL_CUDA_OK((kuka_launch_inst<false, false, true, true>(d, grid, block, st, s->n, KUKA_OP_PREFETCH, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nh->nx)));
+    else SRL_CUDA_OK((kuka_launch_inst<false, false, true, false>(d, grid, block, st, s->n, KUKA_OP_PREFETCH, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nh->nx)));
     SRL_CUDA_OK(cudaEventRecord(s->pf_ev, st));
     s->pf_pending = true;
     s->launches += 1;

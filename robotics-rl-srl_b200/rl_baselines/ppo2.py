@@ -141,7 +141,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     value and the rollout-buffer writes in one launch; ``srl_obs_filter``: the observation filter in one launch; include/srl_policy.h)
     instead of ~60 small torch kernels: an env step of the collection loop is then three launches.  Sampling then uses the library's
     counter-based streams (keyed by seed and global env index) instead of torch's generator.
-    ``prefetch_resets`` (Kuka): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then carries a helper CTA that
+    ``prefetch_resets`` (Kuka): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then uses the idle slot of each warp as a helper that
     prepares the next-episode records, so that a step whose env finishes an episode copies a record in instead of running reset() inside
     the launch (include/srl_sim.h: srl_sim_prefetch_resets; validated bit-identical on B200 in round 2).
     ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
@@ -212,7 +212,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         done_u8 = torch.zeros((T, N), device=dev, dtype=torch.uint8)
 
     if prefetch_resets and on_gpu:
-        env.sim.prefetch_resets(stream=env.backend.stream())   # bulk fill of the first records; from here on the helper CTA of every step launch keeps them up
+        env.sim.prefetch_resets(stream=env.backend.stream())   # bulk fill of the first records; from here on the helper slots of every step launch keep them up
 
     def collect():
         """n_steps lockstep env steps under the current policy; everything stays on the device, nothing synchronises."""

@@ -222,7 +222,7 @@ class Sim(object):
 
     def prefetch_resets(self, stream=None):
         """Bulk fill of the next-episode records (handles created with ``prefetch_resets=True``; a no-op otherwise).  In steady state
-        the helper CTA of every step / rollout launch keeps the records up; call this once after a reset of all envs."""
+        the helper slots of every step / rollout launch keep the records up; call this once after a reset of all envs."""
         rc = self._lib.srl_sim_prefetch_resets(self.handle, stream)
         self.library.check(rc, "srl_sim_prefetch_resets")
 

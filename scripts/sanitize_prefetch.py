@@ -1,4 +1,4 @@
-"""Lockstep Kuka stepping with next-episode records (helper CTA in every step launch + an occasional bulk fill from a side stream), small
+"""Lockstep Kuka stepping with next-episode records (helper slots in every step launch + an occasional bulk fill from a side stream), small
 enough for compute-sanitizer (memcheck / racecheck): short episodes so that every env consumes several records."""
 import os, sys
 import numpy as np

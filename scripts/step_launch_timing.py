@@ -37,7 +37,7 @@ print("lockstep srl_sim_step: mean %.1f us, median %.1f us, min %.1f us, max %.1
       % (1e3 * step_ms.mean(), 1e3 * np.median(step_ms), 1e3 * step_ms.min(), 1e3 * step_ms.max(), int((any_done > 0).sum()), T))
 if (any_done > 0).any() and (any_done == 0).any():
     print("  launches with a finished episode: %.1f us; without: %.1f us" % (1e3 * step_ms[any_done > 0].mean(), 1e3 * step_ms[any_done == 0].mean()))
-# next-episode records (srl_cfg.prefetch_resets): the same lockstep loop; the helper CTA of every launch keeps the records up
+# next-episode records (srl_cfg.prefetch_resets): the same lockstep loop; the helper slots of every launch keep the records up
 sim2 = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=0, prefetch_resets=True)
 sim2.reset(obs_out=obs, stream=st)
 for _ in range(10):
@@ -56,7 +56,7 @@ for rep in range(3):
             d = done.cpu().numpy().astype(bool); hits += int((d & ready).sum()); fin += int(d.sum())
 torch.cuda.synchronize()
 ms2 = np.array(ms2)
-print("lockstep srl_sim_step WITH next-episode records (helper CTA): mean %.1f us, median %.1f us, min %.1f us, max %.1f us per launch; %d of %d finished episodes took a record"
+print("lockstep srl_sim_step WITH next-episode records (helper slots): mean %.1f us, median %.1f us, min %.1f us, max %.1f us per launch; %d of %d finished episodes took a record"
       % (1e3 * ms2.mean(), 1e3 * np.median(ms2), 1e3 * ms2.min(), 1e3 * ms2.max(), hits, fin))
 pol = MlpPolicy(3, n_actions=6).to(dev)
 norm = RunningNorm(3, dev)

@@ -203,16 +203,29 @@ def test_cuda_matches_committed_golden(cuda_backend):
 
 
 def test_step_equals_rollout_and_lane_packing_invariance(cuda_backend):
-    """Lockstep step() x T == fused rollout(T), and the result does not depend on envs_per_warp (bit-exact)."""
+    """Lockstep step() x T == fused rollout(T), and the result does not depend on how the envs are packed into warps (bit-exact) -- within
+    each of the two layouts the kernel has: four lanes per env (up to 8 envs per warp, the default for batches that fit one warp per
+    scheduler) and one thread per env (more envs per warp).  ACROSS the two layouts the once-per-step arithmetic is associated differently,
+    so they agree to the float32 tolerances of the oracle comparison, flags included on this seed."""
     n, T = 40, 90
     rs = np.random.RandomState(4)
     acts = rs.randint(0, 6, size=(T, n)).astype(np.int32); noise = rs.normal(0, 0.01, size=(T, n)).astype(np.float32)
     base = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40)
     assert base["done"].sum() >= 2 * n
-    for kw in (dict(stepwise=True), dict(envs_per_warp=1), dict(envs_per_warp=7), dict(envs_per_warp=32), dict(chunk=13)):
+    keys = ("obs0", "obs", "rew", "done", "ep_ret", "ep_len", "q", "qd", "grip", "counters")
+    for kw in (dict(stepwise=True), dict(envs_per_warp=1), dict(envs_per_warp=7), dict(envs_per_warp=8), dict(chunk=13)):
         other = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40, **kw)
-        for k in ("obs0", "obs", "rew", "done", "ep_ret", "ep_len", "q", "qd", "grip", "counters"):
+        for k in keys:
             assert np.array_equal(base[k], other[k]), (kw, k)
+    wide = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40, envs_per_warp=32)      # one thread per env
+    for kw in (dict(envs_per_warp=9), dict(envs_per_warp=20, stepwise=True)):
+        other = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, seed=2, max_steps=40, **kw)
+        for k in keys:
+            assert np.array_equal(wide[k], other[k]), (kw, k)
+    for k in ("rew", "done", "ep_len", "counters"):
+        assert np.array_equal(base[k], wide[k]), k
+    for k, tol in (("obs0", POS_TOL), ("obs", POS_TOL), ("grip", POS_TOL), ("q", Q_TOL), ("qd", QD_TOL)):
+        assert np.abs(base[k] - wide[k]).max() < tol, k
     assert base["launches"] == 3                                        # settle (create) + reset + ONE fused rollout
 
 

@@ -1,6 +1,6 @@
 """
 Next-episode records for the lockstep Kuka step (srl_cfg.prefetch_resets, include/srl_sim.h): with the option on, every step / rollout
-launch carries a helper CTA that advances incomplete records by one random micro-step of reset() per env step, and a step whose env
+launch uses the first idle slot of every warp to advance one incomplete record of that warp's envs by one random micro-step of reset() per env step, and a step whose env
 finishes an episode copies a complete record in instead of running reset() inside the launch.  A record is produced by the very
 instructions of the in-launch reset, so whatever mix of record hits and in-launch resets a run sees, it must be BIT-IDENTICAL to the
 default path.  Reference semantics: the reset() a SubprocVecEnv worker runs between two steps
@@ -19,7 +19,7 @@ STATE_FIELDS = (_abi.F_JOINT_POS, _abi.F_JOINT_VEL, _abi.F_EE_CMD, _abi.F_TARGET
 
 
 def _lockstep(be, kind, n, T, acts, mode, **cfg):
-    """mode: off | helper (records only ever produced by the helper CTAs) | bulk_first (one bulk fill after reset, then helper CTAs) |
+    """mode: off | helper (records only ever produced by the helper slots) | bulk_first (one bulk fill after reset, then helper slots) |
     bulk_side (a bulk fill on a SIDE stream after every step: the library orders it against the step launches)."""
     import torch
     sim = be.make_sim(kind, n, model_blob=load_kuka_scene().blob, prefetch_resets=mode != "off", **cfg)
@@ -68,42 +68,37 @@ def test_lockstep_steps_with_next_episode_records_are_bit_identical(cuda_backend
             assert np.array_equal(base_state[f], state[f]), (mode, f)
         found, finished = np.sum(hits, axis=0)
         print("%s %s: %d of %d finished episodes found a complete record" % (kind, mode, found, finished))
-        # the mechanism must actually serve records (31-step episodes leave 26 launches of slack after the 5 a record needs; the helper
-        # serves 128 envs at a time, so 200 envs all finishing on the same step cannot all hit in helper-only mode)
-        assert found >= (0.9 if mode != "helper" else 0.3) * finished, (mode, found, finished)
+        # the mechanism must actually serve records (200 envs = one env per warp: its helper slot needs 5 of the 31 launches of an episode)
+        assert found >= 0.9 * finished, (mode, found, finished)
 
 
-def test_helper_cta_completes_a_record_in_five_lockstep_launches(cuda_backend):
-    """One helper CTA advances up to 128 records by ONE micro-step per lockstep launch: after k < 5 launches the first 128 incomplete
-    records carry progress k, after 5 they are complete and the next 128 envs are being served."""
+@pytest.mark.parametrize("epw", [1, 3, 7])
+def test_helper_slot_completes_a_record_in_five_lockstep_launches(cuda_backend, epw):
+    """The first idle slot of every warp advances ONE record of its warp's envs by one micro-step per lockstep launch: with `epw` envs per
+    warp, after k launches warp w has completed k // 5 records and the next one carries progress k % 5."""
     be = cuda_backend
-    n = 300
-    sim = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=1, prefetch_resets=True)
+    n = 40 * epw
+    sim = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=1, prefetch_resets=True, envs_per_warp=epw)
     st = be.stream()
     sim.reset(stream=st)
     a = be.from_host(np.zeros((n,), np.int32))
     obs = be.zeros((n, 3), np.float32); rew = be.zeros((n,), np.float32); done = be.zeros((n,), np.uint8)
     rec = sim.get_state(_abi.F_NEXT_RECORD)
     assert rec[:, 0].sum() == 0 and rec[:, 1].sum() == 0
-    for k in range(1, 11):
+    for k in range(1, 5 * epw + 3):
         sim.step(a, None, obs, rew, done, None, None, stream=st)
-        rec = sim.get_state(_abi.F_NEXT_RECORD)
-        complete, in_progress = int(rec[:, 0].sum()), rec[:, 1][rec[:, 0] == 0]
-        if k < 5:
-            assert complete == 0 and sorted(in_progress.tolist()) == [0] * (n - 128) + [k] * 128
-        elif k == 5:
-            assert complete == 128 and in_progress.sum() == 0
-        elif k < 10:
-            assert complete == 128 and sorted(in_progress.tolist()) == [0] * (n - 256) + [k - 5] * 128
-        else:
-            assert complete == 256
+        rec = sim.get_state(_abi.F_NEXT_RECORD).reshape(40, epw, 3)
+        complete, progress = rec[:, :, 0].sum(axis=1), rec[:, :, 1].sum(axis=1)
+        assert np.all(complete == min(k // 5, epw)), (k, complete)
+        assert np.all(progress == (k % 5 if k // 5 < epw else 0)), (k, progress)
     live_ep = sim.get_state(_abi.F_COUNTERS)[:, 3]
-    assert np.all(rec[rec[:, 0] == 1, 2] == live_ep[rec[:, 0] == 1])   # produced for the episode index the env's next reset() will draw with
+    rec = rec.reshape(n, 3)
+    assert np.all(rec[:, 0] == 1) and np.all(rec[:, 2] == live_ep)     # produced for the episode index the env's next reset() will draw with
     sim.close()
 
 
 def test_fused_rollout_and_explicit_resets_with_records(cuda_backend):
-    """The records also serve the fused T-step rollout (same kernel; its helper CTA completes a record within one launch), and an explicit
+    """The records also serve the fused T-step rollout (same kernel; the helper slots complete a record within one launch), and an explicit
     srl_sim_reset between two rollouts leaves records for an episode index the env no longer has: they must be dropped, not used."""
     import torch
     n, T = 96, 120
@@ -129,7 +124,7 @@ def test_fused_rollout_and_explicit_resets_with_records(cuda_backend):
 
 
 def test_records_inside_a_captured_cuda_graph(cuda_backend):
-    """Config 3's collection loop is a captured CUDA graph of lockstep launches: the helper CTA is part of the step kernel, so the records
+    """Config 3's collection loop is a captured CUDA graph of lockstep launches: the helper slots are part of the step kernel, so the records
     need no extra launches, streams or events inside the graph.  Replays must match eager stepping without records bit for bit."""
     import torch
     be = cuda_backend
