@@ -155,12 +155,15 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     if env_kwargs.get("srl_model", "ground_truth") != "ground_truth":
         # the collection loop feeds the simulator's observation buffer (the 3-D / 2-D ground-truth observation) straight to the policy
         raise ValueError("ppo2.train supports srl_model='ground_truth' only (got %r)" % env_kwargs["srl_model"])
-    env = BatchedSRLVecEnv(env_id, num_envs, seed=seed, device=device, global_env_offset=rank * num_envs, **env_kwargs)
+    import types
+    from rl_baselines.utils import createTensorEnvs, save_obs_rms
+    env = createTensorEnvs(types.SimpleNamespace(env=env_id, num_cpu=num_envs, seed=seed, device=device), env_kwargs=env_kwargs,
+                           global_env_offset=rank * num_envs)
     on_gpu = env.backend.on_gpu
     # device -1 is the CPU oracle installed by a test through srl_sim.backend.use_library (its buffers are numpy arrays,
     # shared with torch below); the product backend is always a CUDA device
     dev = env.backend.torch_device if on_gpu else torch.device("cpu")
-    e_obs, e_rew, e_done, e_ep_ret = [x if on_gpu else torch.from_numpy(x) for x in (env._obs, env._rew, env._done, env._ep_ret)]
+    e_obs, e_rew, e_done, e_ep_ret, e_ep_len = [x if on_gpu else torch.from_numpy(x) for x in (env._obs, env._rew, env._done, env._ep_ret, env._ep_len)]
     D = env.observation_space.shape[0]
     if env.is_discrete:
         policy = MlpPolicy(D, n_actions=env.action_space.n).to(dev)
@@ -200,7 +203,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     buf = dict(obs=torch.empty((T, N, D), device=dev), act=torch.empty((T, N) if env.is_discrete else (T, N, env.sim.action_dim), device=dev,
                                                                        dtype=torch.int64 if env.is_discrete else torch.float32),
                logp=torch.empty((T, N), device=dev), val=torch.empty((T, N), device=dev), rew=torch.empty((T, N), device=dev),
-               done=torch.empty((T, N), device=dev), ep_ret=torch.empty((T, N), device=dev))
+               done=torch.empty((T, N), device=dev), ep_ret=torch.empty((T, N), device=dev), ep_len=torch.zeros((T, N), device=dev, dtype=torch.int32))
     last_val = torch.empty(N, device=dev)
     fused = None
     if fused_act:
@@ -222,7 +225,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 buf["obs"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = obs, a, logp, v
                 act_dev = a.to(torch.int32) if env.is_discrete else torch.clamp(a, -1, 1).contiguous()
                 env.step_tensors(act_dev)                                 # one kernel launch, tensors stay on the GPU
-                buf["rew"][t], buf["done"][t], buf["ep_ret"][t] = e_rew, e_done.float(), e_ep_ret
+                buf["rew"][t], buf["done"][t], buf["ep_ret"][t], buf["ep_len"][t] = e_rew, e_done.float(), e_ep_ret, e_ep_len
                 obs.copy_(norm(e_obs))
             last_val.copy_(policy.vf(obs).squeeze(-1))
 
@@ -233,7 +236,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
             st = env.backend.stream()
             for t in range(T):
                 fused.act(N, obs, act_dev, buf["logp"][t], buf["val"][t], obs_buf=buf["obs"][t], act_buf=buf["act"][t], stream=st)
-                env.sim.step(act_dev, None, env._obs, buf["rew"][t], done_u8[t], buf["ep_ret"][t], env._ep_len, stream=st)
+                env.sim.step(act_dev, None, env._obs, buf["rew"][t], done_u8[t], buf["ep_ret"][t], buf["ep_len"][t], stream=st)
                 fused.filter(N, env._obs, obs, update=True, stream=st)
             buf["done"].copy_(done_u8)
             last_val.copy_(policy.vf(obs).squeeze(-1))
@@ -302,6 +305,23 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     mb_graph, mb_warm = None, 0        # the minibatch step is captured after three eager warm-up steps (real ones) on a side stream
 
     history, ep_returns = [], []
+    # Monitor log (environments/utils.py:53-54 wraps every env in bench.Monitor; rl_baselines/visualize.py:59-107 reads the files back): one
+    # `<rank>.monitor.csv` per process with the episodes of all its envs, return and length straight from the kernel's episode statistics
+    monitor = None
+    if log_dir:
+        from srl_sim.monitor import MonitorWriter, compute_mean_reward
+        os.makedirs(log_dir, exist_ok=True)
+        monitor = MonitorWriter(os.path.join(log_dir, str(rank)), env_id=env_id)
+    # best-model callback of the reference (rl_baselines/train.py:132-159): every SAVE_INTERVAL callback calls (20 PPO2 updates of 8 envs x
+    # 128 steps there; scaled to this batch) the mean return of the last N_EPISODES_EVAL episodes of the monitor logs is computed, and when it
+    # beats the best so far (and MIN_EPISODES_BEFORE_SAVE episodes exist) the observation filter and the model are saved
+    N_EPISODES_EVAL, MIN_EPISODES_BEFORE_SAVE = 100, 100
+    save_interval = max(1, 20 * 8 * 128 // (N * T * world))
+    best_mean_reward, n_saved = -10000.0, 0
+
+    def save_model(path):
+        torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean.clone(), obs_var=norm.var.clone(), obs_count=norm.count.clone()), path)
+        save_obs_rms(log_dir, norm.mean.detach().cpu().numpy(), norm.var.detach().cpu().numpy(), float(norm.count))
 
     def tick(name=None, since=0.0):
         if phase_times is None:
@@ -329,7 +349,15 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         if dist is not None:                   # one all-reduce of 2 D + 1 doubles per rollout
             merge_running_moments(norm, prior, dist.all_reduce, world)
         t_ph = tick("collect", t_ph)
-        ep_returns.extend(buf["ep_ret"][buf["done"].bool()].tolist())
+        dmask = buf["done"].bool()
+        new_rets = buf["ep_ret"][dmask].tolist()
+        ep_returns.extend(new_rets)
+        if monitor is not None and new_rets:
+            t_now = time.time() - monitor.t_start
+            t_idx = dmask.nonzero()[:, 0].float()                          # step index of each finished episode within the rollout
+            t_prev = getattr(monitor, "_t_prev", 0.0)
+            monitor.write_episodes(new_rets, buf["ep_len"][dmask].tolist(), (t_prev + (t_now - t_prev) * (t_idx + 1.0) / T).tolist())
+            monitor._t_prev = t_now
         if gae_graph is not None:
             gae_graph.replay()
         else:
@@ -371,10 +399,35 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
         else:
             mean_ret = float(np.mean(window)) if window else float("nan")
         history.append((steps, mean_ret, fps))
+        if log_dir and update % save_interval == 0:
+            if dist is not None:
+                dist.barrier()             # every rank's monitor file holds this update's episodes
+            if rank == 0:
+                if dist is None:           # one process: the in-memory list is the monitor file (same episodes, same order)
+                    ok, n_episodes = len(ep_returns) > 0, len(ep_returns)
+                    eval_reward = float(np.mean(ep_returns[-N_EPISODES_EVAL:])) if ok else 0.0
+                else:
+                    ok, eval_reward, n_episodes = compute_mean_reward(log_dir, N_EPISODES_EVAL)
+                if ok and verbose:
+                    print("Best mean reward: {:.2f} - Last mean reward per episode: {:.2f}".format(best_mean_reward, eval_reward))
+                if ok and eval_reward > best_mean_reward and n_episodes >= MIN_EPISODES_BEFORE_SAVE:
+                    best_mean_reward = eval_reward
+                    if verbose:
+                        print("Saving new best model")
+                    save_model(os.path.join(log_dir, "ppo2_model.pt"))
+                    n_saved += 1
         if verbose and rank == 0:
             print("update %d/%d  steps %d  mean episode return %.3f  episodes %d  fps %.0f" % (update, n_updates, steps, mean_ret, len(ep_returns), fps))
+    if monitor is not None:
+        monitor.close()
     if log_dir and rank == 0:
-        torch.save(dict(policy=policy.state_dict(), obs_mean=norm.mean.clone(), obs_var=norm.var.clone()), os.path.join(log_dir, "ppo2_model.pt"))
+        save_model(os.path.join(log_dir, "ppo2_model_final.pt"))
+        if n_saved == 0:                   # a run too short for the callback to fire (fewer than MIN_EPISODES_BEFORE_SAVE episodes): keep the last model
+            save_model(os.path.join(log_dir, "ppo2_model.pt"))
+        with open(os.path.join(log_dir, "best_model.json"), "w") as f:
+            json.dump(dict(best_mean_reward=best_mean_reward if n_saved else None, saves=n_saved, n_episodes_eval=N_EPISODES_EVAL,
+                           min_episodes_before_save=MIN_EPISODES_BEFORE_SAVE, save_interval_updates=save_interval), f)
     env.close()
+    train.best_mean_reward, train.n_saved = best_mean_reward, n_saved
     train.last_policy, train.last_norm = policy, norm      # for callers that want the trained objects (tests, enjoy)
     return history

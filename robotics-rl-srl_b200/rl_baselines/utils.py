@@ -153,3 +153,25 @@ def createEnvs(args, allow_early_resets=False, env_kwargs=None, load_path_normal
         if load_path_normalise is not None:
             envs.load_running_average(load_path_normalise)
     return envs
+
+
+def createTensorEnvs(args, env_kwargs=None, global_env_offset=0):
+    """
+    The device-resident sibling of ``createEnvs`` for trainers that keep the whole collection loop on the GPU (rl_baselines/ppo2.py): the
+    same arguments pick the same envs (``args.env``, ``args.num_cpu`` envs seeded ``args.seed + global index``, ``env_kwargs``), but the
+    result is the bare ``BatchedSRLVecEnv`` whose ``step_tensors`` / ``sim.step`` read and write CUDA tensors -- no host round trip, hence
+    no host-side ``VecFrameStack`` / ``VecNormalize`` wrappers: the trainer runs the observation filter on the device and saves it in the
+    ``VecNormalize`` file format (``save_obs_rms``) so that ``createEnvs(..., load_path_normalise=...)`` can load it back.
+    """
+    env_kwargs = dict(env_kwargs or {})
+    env_kwargs.setdefault("srl_model", getattr(args, "srl_model", "ground_truth"))
+    return BatchedSRLVecEnv(args.env, args.num_cpu, seed=args.seed, device=getattr(args, "device", None), global_env_offset=global_env_offset, **env_kwargs)
+
+
+def save_obs_rms(path, mean, var, count):
+    """Write ``<path>/obs_rms.pkl`` -- what ``VecNormalize.save_running_average`` writes (rl_baselines/train.py:145-151 calls it when the
+    model improves) -- from the moments of a device-side filter."""
+    rms = RunningMeanStd(np.asarray(mean).shape)
+    rms.mean, rms.var, rms.count = np.asarray(mean, np.float64).copy(), np.asarray(var, np.float64).copy(), float(count)
+    with open("{}/obs_rms.pkl".format(path), "wb") as f:
+        pickle.dump(rms, f)

@@ -34,10 +34,45 @@ class MonitorWriter(object):
         self.f.flush()
         return info
 
+    def write_episodes(self, ep_rets, ep_lens, times):
+        """Many rows at once (the batched trainer finishes ~1000 episodes per update): `times` are seconds since t_start."""
+        self.f.write("".join("%s,%d,%s\n" % (round(float(r), 6), int(l), round(float(t), 6)) for r, l, t in zip(ep_rets, ep_lens, times)))
+        self.f.flush()
+
     def close(self):
         if self.f is not None:
             self.f.close()
             self.f = None
+
+
+def load_monitor_csv(log_folder):
+    """What the reference's ``loadCsv`` (rl_baselines/visualize.py:59-107, non-ES branch) makes of a log folder: every ``*.monitor.csv`` is
+    read (two header lines, then ``r,l,t`` rows), the episodes of all files are merged in order of their time stamp, and the result is
+    ``([[timesteps before the episode, episode return], ...], total timesteps)``."""
+    import glob
+    rows = []
+    for path in glob.glob(os.path.join(log_folder, "*.monitor.csv")):
+        with open(path) as f:
+            f.readline(); f.readline()
+            for line in f:
+                r, l, t = line.split(",")
+                rows.append((float(t), int(l), float(r)))
+    rows.sort(key=lambda x: x[0])
+    result, timesteps = [], 0
+    for _, l, r in rows:
+        result.append([timesteps, r])
+        timesteps += l
+    return result, timesteps
+
+
+def compute_mean_reward(log_folder, n_episodes):
+    """``computeMeanReward`` of the reference (rl_baselines/utils.py:123-147): mean return of the last ``n_episodes`` episodes of a log
+    folder, ``(ok, mean, episodes available)``; not ok while there is no finished episode."""
+    result, _ = load_monitor_csv(log_folder)
+    if not result:
+        return False, 0.0, 0
+    y = [r for _, r in result]
+    return True, float(sum(y[-n_episodes:]) / len(y[-n_episodes:])), len(y)
 
 
 class Monitor(object):

@@ -353,18 +353,24 @@ def test_reference_class_logic_golden_through_cuda(tag, cuda_lib):
     replay_ref_logic_case(tag, POS_TOL, max_steps={"two_disc": 690}.get(tag))
 
 
-def _parity_until_first_flag_shift(c, o, max_shifted_envs):
+def _parity_until_first_flag_shift(c, o, max_shifted_envs, max_drift_envs=0, drift_tol=POS_TOL, stats=None):
     """fp32 vs fp64 can move a contact ONSET by one step when the sphere-shape distance lands within float32 rounding
     (~3e-6 m, against ~1.2 mm of approach per step) of the 0.02 m manifold margin.  After such a shift the episode ends one
     step earlier/later and the env legitimately sees different actions, so each env is compared up to its first flag
     difference, which must be exactly such a one-step shift (of a button contact, reward 1, or of a table contact, reward -1 and done);
-    only a few envs may have one."""
+    only a few envs may have one.  `max_drift_envs` envs may exceed POS_TOL (but not `drift_tol`) before their first flag difference: with
+    force_down off and the large workspace box an arm can spend hundreds of steps stretched out towards an unreachable command without an
+    episode boundary, where float32 and float64 separate by a few micrometres per step (measured: 2 of 4096 envs pass 1 mm after ~500
+    such steps, in the one-thread-per-env kernel of round 1 as well)."""
     T, n = o["rew"].shape
-    shifted = 0
+    shifted, drifted, worst = 0, 0, 0.0
     for i in range(n):
         bad = np.nonzero((c["rew"][:, i] != o["rew"][:, i]) | (c["done"][:, i] != o["done"][:, i]))[0]
         t_end = T if len(bad) == 0 else int(bad[0])
-        assert np.abs(c["obs"][:t_end, i] - o["obs"][:t_end, i]).max(initial=0.0) < POS_TOL
+        dmax = float(np.abs(c["obs"][:t_end, i] - o["obs"][:t_end, i]).max(initial=0.0))
+        worst = max(worst, dmax)
+        assert dmax < drift_tol, (i, dmax)
+        drifted += dmax >= POS_TOL
         if len(bad):
             shifted += 1
             t = t_end
@@ -377,6 +383,9 @@ def _parity_until_first_flag_shift(c, o, max_shifted_envs):
                 assert early["rew"][t + 1, i] == 1.0
                 assert np.abs(c["obs"][t, i] - o["obs"][t, i]).max() < POS_TOL
     assert shifted <= max_shifted_envs, shifted
+    assert drifted <= max_drift_envs, drifted
+    if stats is not None:
+        stats.update(drifted=drifted, worst=worst)
     return shifted
 
 
@@ -393,17 +402,34 @@ def test_moving_button_kind_vs_oracle(cuda_backend, oracle_backend):
     assert o["done"].sum() >= n // 2 and np.abs(o["target"][:, 1]).max() <= 0.3011
 
 
-def test_config2_full_batch_4096_envs_vs_oracle(cuda_backend, oracle_lib):
-    """BASELINE config 2 at FULL size: all 4096 envs x 1000 steps, CUDA vs the oracle (sharded over the host threads).
-    Flags must agree except for one-step contact-onset shifts (see _parity_until_first_flag_shift) in a small fraction of
-    envs; positions agree to 1e-3 m up to that point."""
+# BASELINE.json configs at FULL batch: (env id, steps, action kind, cfg, noise std, bound on the envs that may see a one-step contact-onset
+# shift = 2 x the count measured on B200 with this kernel (profiles/r02_parity_full_batch.txt), floor 8)
+FULL_BATCH_CASES = {
+    # measured on B200, round 2 (four lanes per env): 10 / 26 / 2 / see profiles/r02_parity_full_batch.txt
+    "config2": ("KukaButtonGymEnv-v0", 1000, "discrete", dict(seed=0, is_discrete=True, random_target=False, force_down=True, action_repeat=1, max_distance=0.8), 0.01, 20),
+    "config5": ("KukaRandButtonGymEnv-v0", 2000, "continuous", dict(seed=0, is_discrete=False, random_target=True, force_down=True, action_repeat=1, max_distance=0.8), 1e-4, 52),
+    "action_repeat3": ("KukaButtonGymEnv-v0", 400, "discrete", dict(seed=0, is_discrete=True, random_target=False, force_down=True, action_repeat=3, max_distance=0.8), 0.01, 8),
+    "no_force_down": ("KukaButtonGymEnv-v0", 600, "discrete", dict(seed=0, is_discrete=True, random_target=True, force_down=False, action_repeat=1, max_distance=0.8), 0.01, 40),
+}
+FULL_BATCH_DRIFT = {"no_force_down": (6, 6e-3)}     # envs allowed past POS_TOL before their first flag difference, and how far (3 x measured: 2 envs, 3.4 mm)
+
+
+@pytest.mark.parametrize("case", sorted(FULL_BATCH_CASES))
+def test_full_batch_4096_envs_vs_oracle(cuda_backend, oracle_lib, case):
+    """BASELINE configs 2 and 5 (and the action_repeat / force_down variants) at FULL size: all 4096 envs, CUDA (float32) vs the oracle
+    (float64, sharded over the host threads).  Reward / done flags must agree except for one-step contact-onset shifts (see
+    _parity_until_first_flag_shift) in a small, bounded number of envs; positions agree to 1e-3 m up to that point.  The shift statistics
+    are printed (pytest -s / the tail of a failing run) and recorded in profiles/r02_parity_full_batch.txt."""
     import threading
     from srl_sim.backend import Backend
-    n, T = 4096, 1000
-    acts = np.random.default_rng(0).integers(0, 6, (T, n), dtype=np.int32)
-    noise = np.random.default_rng(1).normal(0, 0.01, (T, n)).astype(np.float32)
-    cfg = dict(seed=0, is_discrete=True, random_target=False, force_down=True, action_repeat=1, max_distance=0.8)
-    c = _run(cuda_backend, "KukaButtonGymEnv-v0", n, T, acts, noise, **cfg)
+    env_id, T, kind, cfg, noise_std, bound = FULL_BATCH_CASES[case]
+    n = 4096
+    if kind == "discrete":
+        acts = np.random.default_rng(0).integers(0, 6, (T, n), dtype=np.int32)
+    else:
+        acts = np.random.default_rng(0).uniform(-1, 1, (T, n, 3)).astype(np.float32)
+    noise = np.random.default_rng(1).normal(0, noise_std, (T, n)).astype(np.float32)
+    c = _run(cuda_backend, env_id, n, T, acts, noise, **cfg)
     threads = max(1, min(16, os.cpu_count() or 1))
     bounds = np.linspace(0, n, threads + 1).astype(int)
     parts = [None] * threads
@@ -411,15 +437,18 @@ def test_config2_full_batch_4096_envs_vs_oracle(cuda_backend, oracle_lib):
 
     def work(k):
         lo, hi = int(bounds[k]), int(bounds[k + 1])
-        parts[k] = _run(be, "KukaButtonGymEnv-v0", hi - lo, T, np.ascontiguousarray(acts[:, lo:hi]), np.ascontiguousarray(noise[:, lo:hi]),
+        parts[k] = _run(be, env_id, hi - lo, T, np.ascontiguousarray(acts[:, lo:hi]), np.ascontiguousarray(noise[:, lo:hi]),
                         global_env_offset=lo, **cfg)
     ths = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
     [t.start() for t in ths]; [t.join() for t in ths]
     o = {k: np.concatenate([p[k] for p in parts], axis=1 if parts[0][k].ndim >= 2 and k in ("obs", "rew", "done", "ep_ret", "ep_len") else 0)
          for k in ("obs0", "obs", "rew", "done")}
     assert np.abs(c["obs0"] - o["obs0"]).max() < POS_TOL
-    shifted = _parity_until_first_flag_shift(c, o, max_shifted_envs=n // 20)
+    drift_envs, drift_tol = FULL_BATCH_DRIFT.get(case, (0, POS_TOL))
+    st = {}
+    shifted = _parity_until_first_flag_shift(c, o, max_shifted_envs=bound, max_drift_envs=drift_envs, drift_tol=drift_tol, stats=st)
     same = (c["rew"] == o["rew"]) & (c["done"] == o["done"])
-    print("config 2 full batch: %d of %d envs with a one-step contact-onset shift; %.4f%% of (env, step) flags identical; episodes %d"
-          % (shifted, n, 100.0 * same.mean(), int(o["done"].sum())))
-    assert o["done"].sum() >= 2 * n
+    print("FULL-BATCH PARITY %s: %d of %d envs with a one-step contact-onset shift (bound %d); %.4f%% of the %d (env, step) flags identical; episodes %d; "
+          "largest |obs| difference before an env's first flag difference %.2e m, %d envs above 1e-3 m"
+          % (case, shifted, n, bound, 100.0 * same.mean(), same.size, int(o["done"].sum()), st["worst"], st["drifted"]))
+    assert o["done"].sum() >= n

@@ -131,3 +131,39 @@ def test_ppo2_with_fused_policy_step_runs_on_other_action_spaces(cuda_lib, env_i
     from rl_baselines.ppo2 import train
     hist = train(env_id, 64, 64 * 128 * 2, seed=3, env_kwargs=kw, verbose=0, fused_act=True)
     assert len(hist) == 2 and hist[-1][0] == 64 * 128 * 2
+
+
+def test_policy_act_kernel_against_an_independent_float64_numpy_model(cuda_lib):
+    """An independent checker (the CPU checker is csrc/policy_core.h compiled for the host): the two 64-64 tanh towers in
+    float64 numpy from the module's weights.  Value, log-probability OF THE ACTION THE KERNEL SAMPLED and -- over many launches -- the
+    sampling frequencies must follow it."""
+    pol = _policy(3, True, 6, seed=11).cuda()
+    fused, _ = _fused(cuda_lib, pol, 3, seed=3)
+    n = 4096
+    obs = torch.randn(n, 3, device="cuda") * 1.2
+    act_env = torch.zeros(n, dtype=torch.int32, device="cuda"); logp = torch.zeros(n, device="cuda"); val = torch.zeros(n, device="cuda")
+
+    def tower(seq, x):
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        h = x
+        for k, m in enumerate(lin):
+            h = h @ m.weight.detach().cpu().numpy().astype(np.float64).T + m.bias.detach().cpu().numpy().astype(np.float64)
+            if k < len(lin) - 1:
+                h = np.tanh(h)
+        return h
+    x = obs.cpu().numpy().astype(np.float64)
+    logits = tower(pol.pi, x)
+    logsm = logits - np.log(np.exp(logits - logits.max(1, keepdims=True)).sum(1, keepdims=True)) - logits.max(1, keepdims=True)
+    value = tower(pol.vf, x)[:, 0]
+    counts = np.zeros((n, 6))
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(200):
+        fused.act(n, obs, act_env, logp, val, stream=st)
+        torch.cuda.synchronize()
+        a = act_env.cpu().numpy()
+        assert np.abs(val.cpu().numpy() - value).max() < 2e-5
+        assert np.abs(logp.cpu().numpy() - logsm[np.arange(n), a]).max() < 2e-5
+        counts[np.arange(n), a] += 1
+    # 4096 x 200 draws: the pooled frequencies follow the mean softmax to a few standard errors
+    emp, exp = counts.sum(0) / counts.sum(), np.exp(logsm).mean(0)
+    assert np.abs(emp - exp).max() < 5 * np.sqrt(0.25 / counts.sum()) + 1e-4, (emp, exp)

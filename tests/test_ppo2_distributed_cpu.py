@@ -130,3 +130,46 @@ def test_train_entry_point_flags_on_the_oracle_backend(use_oracle_backend, tmp_p
     assert args["n_steps"] == 16 and args["noptepochs"] == 2 and args["num_cpu"] == 8 and args["seed"] == 4
     assert json.load(open(os.path.join(run, "env_globals.json")))["random_target"] is True
     assert os.path.isfile(os.path.join(run, "ppo2_model.pt"))
+
+
+def test_monitor_log_best_model_callback_and_obs_filter_file(use_oracle_backend, tmp_path):
+    """SURVEY 8(f).1 pieces of the trainer, on the oracle backend: a per-process `<rank>.monitor.csv` in the bench.Monitor format that the
+    reference's loadCsv reads (/root/reference/rl_baselines/visualize.py:59-107), the best-model callback
+    (/root/reference/rl_baselines/train.py:132-159: mean of the last 100 episodes, saved when it improves and 100 episodes exist) and the
+    observation filter in VecNormalize's file format, loadable through createEnvs(load_path_normalise=...)."""
+    import json
+    import types
+    import torch
+    from rl_baselines.ppo2 import train
+    from rl_baselines.utils import createEnvs
+    from srl_sim.monitor import load_monitor_csv
+    n, updates = 64, 10
+    hist = train("MobileRobotGymEnv-v0", n, n * 128 * updates, seed=3, env_kwargs=dict(is_discrete=True, shape_reward=True), log_dir=str(tmp_path),
+                 verbose=0, cuda_graph=False, device=None)
+    assert len(hist) == updates
+    # ---- monitor file: header, r,l,t rows; every MobileRobot episode lasts 251 steps; loadCsv's view of it ----
+    lines = open(str(tmp_path / "0.monitor.csv")).read().split("\n")
+    assert json.loads(lines[0][1:])["env_id"] == "MobileRobotGymEnv-v0" and lines[1] == "r,l,t"
+    result, timesteps = load_monitor_csv(str(tmp_path))
+    n_ep = n * (128 * updates // 251)
+    assert len(result) == n_ep and timesteps == 251 * n_ep
+    assert [r[0] for r in result[:3]] == [0, 251, 502]
+    rows = [l.split(",") for l in lines[2:] if l]
+    assert all(int(r[1]) == 251 for r in rows) and all(float(a[2]) <= float(b[2]) for a, b in zip(rows, rows[1:]))
+    # ---- best-model callback ----
+    meta = json.load(open(str(tmp_path / "best_model.json")))
+    assert meta["saves"] >= 1 and meta["min_episodes_before_save"] == 100
+    best = torch.load(str(tmp_path / "ppo2_model.pt"))
+    final = torch.load(str(tmp_path / "ppo2_model_final.pt"))
+    assert set(best) == set(final) == {"policy", "obs_mean", "obs_var", "obs_count"}
+    assert abs(meta["best_mean_reward"] - train.best_mean_reward) < 1e-9
+    y = [r[1] for r in result]
+    assert meta["best_mean_reward"] <= max(np.mean(y[max(0, k - 100):k]) for k in range(100, len(y) + 1)) + 1e-6
+    # ---- observation filter through the reference's load path ----
+    args = types.SimpleNamespace(env="MobileRobotGymEnv-v0", num_cpu=2, seed=0, num_stack=1, srl_model="ground_truth")
+    envs = createEnvs(args, env_kwargs=dict(is_discrete=True), load_path_normalise=str(tmp_path))
+    assert np.allclose(envs.obs_rms.mean, final["obs_mean"].cpu().numpy()) or np.allclose(envs.obs_rms.mean, best["obs_mean"].cpu().numpy())
+    assert envs.obs_rms.count > 64 * 128
+    envs.close()
+    with pytest.raises(ValueError):
+        train("MobileRobotGymEnv-v0", 4, 4 * 128, env_kwargs=dict(srl_model="joints"), verbose=0, cuda_graph=False, device=None)

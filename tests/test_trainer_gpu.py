@@ -1,6 +1,8 @@
 """Consumers of the hot path on the GPU: the PPO2 restatement learns on the batched simulator, and the
 reference-shaped entry point `python -m rl_baselines.train` runs for every registered env id (tests/test_pipeline.py:95-111
 of the reference asserts exactly that: exit code 0 after 1600 steps with --num-cpu 4)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -30,6 +32,35 @@ def test_train_entry_point_runs_for_every_env(env_id, cuda_lib, tmp_path):
     assert len(hist) >= 1
     fps = main(["--algo", "random_agent", "--env", env_id, "--num-cpu", "4", "--num-timesteps", "400"])
     assert fps > 0
+
+
+def test_train_logs_reload_and_enjoy(cuda_lib, tmp_path):
+    """SURVEY 8(f).1 end to end on the GPU: rl_baselines.ppo2.train on the device-resident VecEnv (built by createTensorEnvs, records for
+    the lockstep step on) writes args.json / env_globals.json, a bench.Monitor-format `0.monitor.csv` fed by the kernel's episode
+    statistics, the best model + observation filter whenever the mean of the last 100 episodes improves
+    (/root/reference/rl_baselines/train.py:132-159); the log is parsed the way the reference's loadCsv does
+    (/root/reference/rl_baselines/visualize.py:59-107) and replay.enjoy_baselines replays the BEST model."""
+    import json
+    import torch
+    from srl_sim import backend
+    backend.use_library(None, None)
+    from rl_baselines.ppo2 import train
+    from srl_sim.monitor import load_monitor_csv
+    n, updates = 512, 8
+    hist = train("KukaButtonGymEnv-v0", n, n * 128 * updates, seed=1, env_kwargs=dict(is_discrete=True, max_steps=60), log_dir=str(tmp_path), verbose=0,
+                 prefetch_resets=True, fused_act=True)
+    assert len(hist) == updates
+    result, timesteps = load_monitor_csv(str(tmp_path))
+    assert len(result) >= n * updates and result[0][0] == 0 and 0 < timesteps <= n * 128 * updates     # 61-step episodes at most
+    rows = [l.split(",") for l in open(str(tmp_path / "0.monitor.csv")).read().split("\n")[2:] if l]
+    assert all(1 <= int(r[1]) <= 61 for r in rows) and all(float(r[0]) == int(float(r[0])) for r in rows)   # sparse reward: integer returns
+    meta = json.load(open(str(tmp_path / "best_model.json")))
+    assert meta["saves"] >= 1
+    best = torch.load(str(tmp_path / "ppo2_model.pt"))
+    assert {"policy", "obs_mean", "obs_var", "obs_count"} <= set(best) and os.path.isfile(str(tmp_path / "obs_rms.pkl"))
+    from replay.enjoy_baselines import main
+    n_done, mean_reward = main(["--log-dir", str(tmp_path), "--num-cpu", "16", "--num-timesteps", "1100"])
+    assert n_done >= 16 and np.isfinite(mean_reward)
 
 
 def test_enjoy_replays_a_trained_agent(cuda_lib, tmp_path):
