@@ -246,11 +246,17 @@ def roofline_block(workload, spec, n, T, launch_s, clocks, lib_path, sms):
                      "peak_source": "theoretical: SMs x 128 lanes x 2 x SM clock (MEASURED_PEAKS.json has no fp32 figure)"},
             "hbm": hbm,
             "note": "issue-bound fp32 kernel (150 strictly sequential PGS sweeps per env step), not HBM-bound; frac = warp instructions issued / "
-                    "issue slots, lane_util = live threads per warp instruction / 32, useful_lane_frac = frac x lane_util"}
+                    "issue slots, lane_util = live threads per warp instruction / 32, distinct_lane_util discounts the lanes that repeat another lane's work (4 lanes per env run the sweeps redundantly), useful_lane_frac = frac x distinct_lane_util"}
     if prof:
         ach = prof["warp_inst_per_launch"] / launch_s / 1e9
-        roof.update({"achieved": ach, "frac": ach / issue_peak, "lane_util": prof["threads_per_warp_inst"] / 32.0,
-                     "useful_lane_frac": ach / issue_peak * prof["threads_per_warp_inst"] / 32.0,
+        lane_util = prof["threads_per_warp_inst"] / 32.0
+        # an env is a group of 4 lanes; in the sweeps (hot_loop_inst_share of the instructions) the 4 lanes compute the SAME values, so only a
+        # quarter of those live lanes does distinct work; in the once-per-step code the 4 lanes split the work
+        hot = prof.get("hot_loop_inst_share")
+        lanes_per_env = 4.0 if "<0, 0, 0, 1>" in prof.get("kernel", "") or "ELb1EEE" in prof.get("kernel", "") else 1.0
+        distinct = lane_util * ((hot / lanes_per_env + (1.0 - hot)) if hot is not None else 1.0 / lanes_per_env)
+        roof.update({"achieved": ach, "frac": ach / issue_peak, "lane_util": lane_util, "distinct_lane_util": distinct,
+                     "useful_lane_frac": ach / issue_peak * distinct, "lanes_per_env": lanes_per_env, "sweep_inst_share": hot,
                      "warp_inst_per_launch": prof["warp_inst_per_launch"]})
     return roof
 

@@ -48,6 +48,10 @@
 #ifndef KK_SWEEP_TIGHT
 #define KK_SWEEP_TIGHT 1
 #endif
+// sweeps per iteration of the tight loop
+#ifndef KK_TIGHT_UNROLL
+#define KK_TIGHT_UNROLL 1
+#endif
 // fold the previous row's contribution into the impulse update (shorter loop-carried path, one more FFMA per row) or not: with the FFMA.SAT
 // clamp the plain form is already issue-bound (B200, 4096 envs x 128 steps: 5.07 ms against 5.15 ms deferred; profiles/r02_ab_kuka_sweep.txt)
 #ifndef KK_SWEEP_DEFER
@@ -977,7 +981,8 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             const bool quiet = false;
 #endif
             if (quiet) {
-#pragma unroll 1
+                constexpr int tight_unroll = KK_TIGHT_UNROLL;
+#pragma unroll tight_unroll
                 do { KK_SWEEP_BODY() (void)dprev; } while (--left > 0);
                 it = P.iters;
             } else {

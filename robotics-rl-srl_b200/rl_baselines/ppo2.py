@@ -131,17 +131,18 @@ def allreduce_mean_gradients(params, dist, world):
 
 
 def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True,
-          phase_times=None, fused_act=False, prefetch_resets=False, episode_window=40):
+          phase_times=None, fused_act=None, prefetch_resets=None, episode_window=40):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
     ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
     launch per step, buffer writes -- a few dozen small kernels per env step) is captured ONCE into a CUDA graph and replayed
     per update, so a rollout costs one graph launch instead of ~n_steps x 50 kernel launches from Python.
-    ``fused_act``: run the per-step policy work through the library's own kernels (``srl_policy_act``: both towers, sample, log-prob,
+    ``fused_act`` (default: on whenever the envs live on a GPU; measured 1.3x end to end with the records on, profiles/r02_step_launch_timing.txt):
+    run the per-step policy work through the library's own kernels (``srl_policy_act``: both towers, sample, log-prob,
     value and the rollout-buffer writes in one launch; ``srl_obs_filter``: the observation filter in one launch; include/srl_policy.h)
     instead of ~60 small torch kernels: an env step of the collection loop is then three launches.  Sampling then uses the library's
     counter-based streams (keyed by seed and global env index) instead of torch's generator.
-    ``prefetch_resets`` (Kuka): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then uses the idle slot of each warp as a helper that
+    ``prefetch_resets`` (default: on whenever the envs live on a GPU; a no-op for the kinds without records): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then uses the idle slot of each warp as a helper that
     prepares the next-episode records, so that a step whose env finishes an episode copies a record in instead of running reset() inside
     the launch (include/srl_sim.h: srl_sim_prefetch_resets; validated bit-identical on B200 in round 2).
     ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
@@ -150,6 +151,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     torch.manual_seed(seed)
     env_kwargs = dict(env_kwargs or {})
     dist, rank, world = _dist_world()
+    if prefetch_resets is None:
+        from srl_sim.backend import default_backend
+        prefetch_resets = default_backend(device).on_gpu
     if prefetch_resets:
         env_kwargs["prefetch_resets"] = True
     if env_kwargs.get("srl_model", "ground_truth") != "ground_truth":
@@ -206,6 +210,8 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                done=torch.empty((T, N), device=dev), ep_ret=torch.empty((T, N), device=dev), ep_len=torch.zeros((T, N), device=dev, dtype=torch.int32))
     last_val = torch.empty(N, device=dev)
     fused = None
+    if fused_act is None:
+        fused_act = on_gpu
     if fused_act:
         if not on_gpu:
             raise ValueError("fused_act=True needs the CUDA library (there is no CPU fallback)")

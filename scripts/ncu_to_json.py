@@ -43,6 +43,17 @@ doc = {
     "note": "one launch, ncu --set full --clock-control none; per-launch times under ncu are cold-cache and serialised -- bench.py uses only the "
             "instruction / byte COUNTS of this capture, with its own live launch time",
 }
+# share of the warp instructions executed in the hottest loop (the PGS sweep for Kuka): instructions executed >= 100x the median count
+try:
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(io.StringIO(src)))
+    shdr = srows[1]; iex = shdr.index("Instructions Executed")
+    ex = [int(r[iex]) for r in srows[2:] if len(r) > iex and r[iex].isdigit()]
+    pos = sorted(e for e in ex if e > 0)
+    med = pos[len(pos) // 2]
+    doc["hot_loop_inst_share"] = sum(e for e in ex if e >= 100 * med) / float(sum(ex))
+except Exception as exn:
+    doc["hot_loop_inst_share"] = None
 with open(out, "w") as f:
     json.dump(doc, f, indent=1)
 print(json.dumps(doc))

