@@ -75,3 +75,39 @@ def test_enjoy_replays_a_trained_agent(cuda_lib, tmp_path):
     assert n_done == 16 and np.isfinite(mean_reward)       # every MobileRobot episode lasts 251 steps
     n_done, _ = main(["--log-dir", str(tmp_path), "--num-cpu", "4", "--num-timesteps", "260", "--deterministic", "--shape-reward"])
     assert n_done == 4
+
+
+def test_dataset_generator_and_record_data_on_the_cuda_backend(cuda_lib, tmp_path):
+    """SURVEY 8(f).3 on the product path: `python -m environments.dataset_generator` drives single-env objects (N = 1 views on the CUDA
+    simulator) with record_data=True, EpisodeSaver writes the two npz schemas (/root/reference/state_representation/episode_saver.py:139-162);
+    the recorded MobileRobot states must be the ones the oracle backend records for the same seeds (bit-exact: the env has no physics), and a
+    recorded Kuka episode must be consistent with itself (positions within the fp32 tolerance of the oracle's recording)."""
+    from srl_sim import backend
+    from srl_sim._abi import SimLibrary
+    from conftest import ORACLE_LIB
+    from environments import dataset_generator
+    out = {}
+    for tag, lib, dev in (("cuda", None, None), ("oracle", SimLibrary(ORACLE_LIB), -1)):
+        backend.use_library(lib, dev)
+        try:
+            base = str(tmp_path / tag) + "/"
+            os.makedirs(base, exist_ok=True)
+            n = dataset_generator.main(["--env", "MobileRobotGymEnv-v0", "--num-episode", "3", "--save-path", base, "--seed", "5", "-r", "--name", "mob", "--num-cpu", "1"])
+            k = dataset_generator.main(["--env", "KukaButtonGymEnv-v0", "--num-episode", "1", "--save-path", base, "--seed", "2", "--name", "kuka", "--max-distance", "0.8"])
+            out[tag] = (n, k, dict(np.load(base + "mob/preprocessed_data.npz")), dict(np.load(base + "mob/ground_truth.npz")),
+                        dict(np.load(base + "kuka/preprocessed_data.npz")), dict(np.load(base + "kuka/ground_truth.npz")))
+        finally:
+            backend.use_library(None, None)
+    (n_c, k_c, pre_c, gt_c, kpre_c, kgt_c), (n_o, k_o, pre_o, gt_o, kpre_o, kgt_o) = out["cuda"], out["oracle"]
+    assert n_c == n_o == 3 * 251
+    for key in ("rewards", "actions", "episode_starts"):
+        assert np.array_equal(pre_c[key], pre_o[key]), key
+    for key in ("target_positions", "ground_truth_states"):
+        assert np.array_equal(gt_c[key], gt_o[key]), key
+    assert list(gt_c["images_path"]) == list(gt_o["images_path"]) and gt_c["images_path"][251] == "mob/record_001/frame000000"
+    # Kuka: same seeds and actions; float32 kernel vs float64 oracle
+    m = min(k_c, k_o)
+    assert m > 10 and abs(k_c - k_o) <= 1
+    assert np.array_equal(kpre_c["actions"][:m - 1], kpre_o["actions"][:m - 1])
+    assert np.abs(kgt_c["ground_truth_states"][:m - 1] - kgt_o["ground_truth_states"][:m - 1]).max() < 1e-3
+    assert kgt_c["target_positions"].shape == (1, 3) and np.abs(kgt_c["target_positions"] - kgt_o["target_positions"]).max() < 1e-5
