@@ -183,25 +183,31 @@ def model_blob(workload):
 
 
 # ------------------------------------------------------------------- committed ncu captures, keyed by SASS hash ----
-KERNEL_PATTERN = {"kuka": "kuka_kernelILb0ELb0ELb0E", "mobile": "mobile_rollout_kernelILi4ELb1ELb0ELb0ELb1E"}
+KERNEL_PATTERN = {"kuka": "kuka_kernelILb0ELb0ELb0ELb1E", "mobile": "mobile_rollout_kernelILi4ELb1ELb0ELb0ELb1E"}   # 4096 Kuka envs run the four-lanes-per-env instantiation
 
 
 def kernel_sass_sha16(lib_path, workload):
-    """sha256 (16 hex digits) of the SASS of the workload's dominant kernel as shipped in `lib_path` (cuobjdump -sass, the text of that
-    one function with addresses / encodings).  The ncu-derived constants of the roofline block are only valid for this exact code."""
+    """sha256 (16 hex digits) of the INSTRUCTION STREAM of the workload's dominant kernel as shipped in `lib_path`: `cuobjdump -sass`, the
+    opcode + operand text of that one function, without addresses, encodings or the mangled name (which move when unrelated code is added
+    to the translation unit while the kernel's code stays the same).  The ncu-derived constants of the roofline block are only valid for
+    this exact code."""
+    import re
     try:
         out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True, timeout=120).stdout
     except Exception:
         return None
-    pat, keep, lines = KERNEL_PATTERN[workload], False, []
+    pat, keep, ins = KERNEL_PATTERN[workload], False, []
     for ln in out.splitlines():
         if "Function :" in ln:
             keep = pat in ln
+            continue
         if keep:
-            lines.append(ln.rstrip())
-    if not lines:
+            m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(.*?);", ln)
+            if m:
+                ins.append(re.sub(r"\s+", " ", m.group(1)).strip())
+    if not ins:
         return None
-    return hashlib.sha256("\n".join(lines).encode()).hexdigest()[:16]
+    return hashlib.sha256("\n".join(ins).encode()).hexdigest()[:16]
 
 
 def load_profile(workload, lib_path):

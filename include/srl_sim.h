@@ -184,6 +184,19 @@ int srl_sim_rollout_host(srl_sim* sim, int T, const void* actions, const float* 
  * (kuka_button_gym_env.py:214-281 via rl_baselines/utils.py:216-220). */
 int srl_sim_prefetch_resets(srl_sim* sim, void* stream);
 
+/* Image observations (`srl_model = "raw_pixels"`): what the reference obtains per env from PyBullet's TinyRenderer in render(mode='rgb_array')
+ * (environments/kuka_gym/kuka_button_gym_env.py:370-420, environments/mobile_robot/mobile_robot_env.py:287-334).  The camera is given the way
+ * the reference gives it to computeViewMatrixFromYawPitchRoll (upAxisIndex = 2) / computeProjectionMatrixFOV; rows run top to bottom like
+ * getCameraImage's.  One frame of `width` x `height` RGB bytes per env: rgb_out is u8[N, height, width, 3] (device pointer for the CUDA
+ * library).  The scene is drawn from analytic primitives (the pybullet_data meshes and textures are not available): same camera and
+ * layout as the reference, not TinyRenderer's pixels -- see csrc/render_core.h. */
+typedef struct srl_camera {
+    float target[3];            /* cameraTargetPosition                                         */
+    float distance, yaw, pitch, roll;   /* degrees                                              */
+    float fov;                  /* vertical field of view in degrees; aspect = width / height   */
+} srl_camera;
+int srl_sim_render(srl_sim* sim, const srl_camera* camera, int width, int height, uint8_t* rgb_out, void* stream);
+
 /* Debug / single-env accessors (host arrays, synchronising; not on the hot path).  Derived link-state fields
  * (SRL_F_ROBOT_POS, SRL_F_EE_POS) reflect the last step or reset; they are not recomputed by set_state. */
 int srl_sim_get_state(srl_sim* sim, int field, void* dst, size_t bytes);

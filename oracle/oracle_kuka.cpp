@@ -28,6 +28,7 @@
 #include <string.h>
 #include <vector>
 #include "oracle_sim.h"
+#include "../robotics-rl-srl_b200/csrc/render_core.h"
 #include "philox.h"
 #include "../robotics-rl-srl_b200/csrc/kuka_model.h"
 
@@ -980,6 +981,35 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
         if (s->auto_reset) oracle_kuka_reset_env(s, i, NULL);
     }
     if (obs) oracle_kuka_obs(s, i, obs + 3 * (size_t)i);
+}
+
+/* Scene primitives of env i for the CPU checker of the image path (csrc/render_core.h holds the list builder both sides share): joint
+ * frames and gripper collision spheres from this file's own float64 forward kinematics. */
+int oracle_kuka_scene(const srl_sim* s, int i, void* prims_out) {
+    const KukaWorld& w = *s->kuka;
+    const KModel& m = w.m;
+    const KEnv& e = w.envs[i];
+    Kin k;
+    forward_kinematics(m, e.q, k);
+    float jp[NB * 3], sph[KM_MAX_SPHERES * 4];
+    for (int b = 0; b < NB; ++b) { jp[3 * b] = (float)k.p[b].x; jp[3 * b + 1] = (float)k.p[b].y; jp[3 * b + 2] = (float)k.p[b].z; }
+    int ns = 0;
+    for (int t = 0; t < m.nsphere; ++t) {
+        const KSphere& sp = m.sph[t];
+        if (sp.body < 7) continue;
+        const V3 c = k.p[sp.body] + k.R[sp.body] * sp.c;
+        sph[4 * ns] = (float)c.x; sph[4 * ns + 1] = (float)c.y; sph[4 * ns + 2] = (float)c.z; sph[4 * ns + 3] = (float)sp.r;
+        ++ns;
+    }
+    SrlKukaSceneConst K;
+    for (int a = 0; a < 3; ++a) K.base[a] = (float)m.sc[KM_SC_BASE_POS + a];
+    K.table_z = (float)m.sc[KM_SC_TABLE_TOP_Z]; K.txmin = (float)m.sc[KM_SC_TABLE_XMIN]; K.txmax = (float)m.sc[KM_SC_TABLE_XMAX];
+    K.tymin = (float)m.sc[KM_SC_TABLE_YMIN]; K.tymax = (float)m.sc[KM_SC_TABLE_YMAX];
+    K.glider_z = (float)m.sc[KM_SC_GLIDER_Z]; K.disc_r = (float)m.sc[KM_SC_DISC_RADIUS]; K.disc_z0 = (float)m.sc[KM_SC_DISC_Z0]; K.disc_z1 = (float)m.sc[KM_SC_DISC_Z1];
+    K.stack_r = (float)m.sc[KM_SC_STACK_RADIUS]; K.stack_top = (float)m.sc[KM_SC_STACK_TOP];
+    K.two_buttons = e.nbuttons == 2;
+    return srl_kuka_scene(K, jp, sph, ns, (float)e.button_base[0], (float)e.button_base[1], (float)e.button_base[2], (float)e.qb,
+                          (float)e.button2_base[0], (float)e.button2_base[1], (float)m.sc[KM_SC_BUTTON_BASE + 2], (float)e.qb2, static_cast<SrlPrim*>(prims_out));
 }
 
 int oracle_kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {

@@ -60,5 +60,6 @@ void oracle_kuka_step_env(srl_sim* s, int i, const void* actions, const float* n
                           float* obs, float* rew, uint8_t* done, float* ep_ret, int32_t* ep_len);
 int  oracle_kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes);
 int  oracle_kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes);
+int  oracle_kuka_scene(const srl_sim* s, int i, void* prims_out /* SrlPrim[SRL_MAX_PRIMS], csrc/render_core.h */);
 
 #endif

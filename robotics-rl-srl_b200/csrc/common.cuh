@@ -58,6 +58,8 @@ struct srl_sim {
     cudaEvent_t host_ev[2 * SRL_HOST_MAX_CHUNKS];
     bool host_pipe_ready;
     int host_chunks;    // SRL_HOST_CHUNKS override (0 = by bytes moved)
+    float* render_prims; // [N][SRL_MAX_PRIMS][16] scene primitives of the last srl_sim_render (allocated on first use)
+    int* render_counts;
     bool host_zero_copy; // single-chunk rollouts store obs / reward / done straight into pinned, device-mapped host buffers (opt-in: SRL_HOST_ZEROCOPY=1)
 };
 
@@ -73,6 +75,10 @@ int mobile_launch_rollout(srl_sim* s, int T, const void* actions, const float* n
 int mobile_get_state(srl_sim* s, int field, void* dst, size_t bytes);
 int mobile_set_state(srl_sim* s, int field, const void* src, size_t bytes);
 
+// ---- image observations (render_kernels.cu) ------------------------------------------------
+int render_launch(srl_sim* s, const srl_camera* cam, int width, int height, uint8_t* rgb, cudaStream_t st);
+void render_free(srl_sim* s);
+
 // ---- launchers (kuka_kernels.cu) ---------------------------------------------------------
 int kuka_alloc(srl_sim* s, const void* blob, size_t bytes);
 void kuka_free(srl_sim* s);
@@ -80,5 +86,6 @@ int kuka_launch_reset(srl_sim* s, const uint8_t* mask, const double* draws, floa
 int kuka_launch_rollout(srl_sim* s, int T, const void* actions, const float* noise, float* obs, float* rew,
                         uint8_t* done, float* ep_ret, int32_t* ep_len, cudaStream_t st);
 int kuka_launch_prefetch(srl_sim* s, cudaStream_t st);
+int kuka_render_prims(srl_sim* s, float* prims, int* counts, cudaStream_t st);   // [N][SRL_MAX_PRIMS][16] primitive list of every env's scene
 int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes);
 int kuka_set_state(srl_sim* s, int field, const void* src, size_t bytes);

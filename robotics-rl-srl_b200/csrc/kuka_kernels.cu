@@ -17,6 +17,7 @@
 #include <vector>
 #include "common.cuh"
 #include "kuka_device.cuh"
+#include "render_core.h"
 
 struct KukaDev {
     float4* q[3];    // [N] joint positions  (12 floats as 3 x float4)
@@ -534,6 +535,59 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     if (lead) env_store<TWOB>(d, i, e);
 }
 
+// Scene primitives of every env for srl_sim_render (render_core.h): one thread per env recomputes the joint frames of the stored
+// configuration (the link states in HBM are only the two the env logic reads) and lists the primitives.
+template <bool TWOB>
+__global__ void kuka_prims_kernel(const __grid_constant__ KukaDev d, int n, float* __restrict__ prims, int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KukaParams& P = d.P;
+    KukaEnv e; KukaKin k; KukaContacts ct;
+    env_load<TWOB>(d, i, e);
+    // world rotations are needed for the sphere centres: rerun the chain with the rotations kept (12 bodies, negligible next to the ray-casting)
+    float Rb[KK_NB][9]; f3 pb[KK_NB];
+    {
+        float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, R7[9]; f3 p = mk3(P.base[0], P.base[1], P.base[2]), p7 = p;
+        for (int t = 0; t < 9; ++t) R7[t] = R[t];
+        for (int b = 0; b < KK_NB; ++b) {
+            if (b == 10) { for (int t = 0; t < 9; ++t) R[t] = R7[t]; p = p7; }
+            const float ox = P.org[b][0], oy = P.org[b][1], oz = P.org[b][2];
+            p = mk3(p.x + R[0] * ox + R[1] * oy + R[2] * oz, p.y + R[3] * ox + R[4] * oy + R[5] * oz, p.z + R[6] * ox + R[7] * oy + R[8] * oz);
+            float sn, cs; sincosf(e.q[b], &sn, &cs);
+            const float t = 1.f - cs, ax = P.axis[b][0], ay = P.axis[b][1], az = P.axis[b][2];
+            const float Q[9] = {cs + t * ax * ax, t * ax * ay - sn * az, t * ax * az + sn * ay, t * ax * ay + sn * az, cs + t * ay * ay, t * ay * az - sn * ax,
+                                t * ax * az - sn * ay, t * ay * az + sn * ax, cs + t * az * az};
+            float B[9], Rn[9];
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) B[3 * r + c] = P.rot[b][3 * r] * Q[c] + P.rot[b][3 * r + 1] * Q[3 + c] + P.rot[b][3 * r + 2] * Q[6 + c];
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rn[3 * r + c] = R[3 * r] * B[c] + R[3 * r + 1] * B[3 + c] + R[3 * r + 2] * B[6 + c];
+            for (int t2 = 0; t2 < 9; ++t2) { R[t2] = Rn[t2]; Rb[b][t2] = Rn[t2]; }
+            pb[b] = p;
+            if (b == 7) { for (int t2 = 0; t2 < 9; ++t2) R7[t2] = R[t2]; p7 = p; }
+        }
+    }
+    float jp[KK_NB * 3], sph[KM_MAX_SPHERES * 4];
+    for (int b = 0; b < KK_NB; ++b) { jp[3 * b] = pb[b].x; jp[3 * b + 1] = pb[b].y; jp[3 * b + 2] = pb[b].z; }
+    int ns = 0;
+    for (int sidx = 0; sidx < P.nsph; ++sidx) {
+        const int b = P.sph_body[sidx];
+        if (b < 7) continue;          // the arm links are drawn as capsules; the gripper bodies by their collision spheres
+        const float* R = Rb[b];
+        sph[4 * ns] = pb[b].x + R[0] * P.sph_c[sidx][0] + R[1] * P.sph_c[sidx][1] + R[2] * P.sph_c[sidx][2];
+        sph[4 * ns + 1] = pb[b].y + R[3] * P.sph_c[sidx][0] + R[4] * P.sph_c[sidx][1] + R[5] * P.sph_c[sidx][2];
+        sph[4 * ns + 2] = pb[b].z + R[6] * P.sph_c[sidx][0] + R[7] * P.sph_c[sidx][1] + R[8] * P.sph_c[sidx][2];
+        sph[4 * ns + 3] = P.sph_r[sidx];
+        ++ns;
+    }
+    SrlKukaSceneConst K;
+    K.base[0] = P.base[0]; K.base[1] = P.base[1]; K.base[2] = P.base[2];
+    K.table_z = P.table_z; K.txmin = P.txmin; K.txmax = P.txmax; K.tymin = P.tymin; K.tymax = P.tymax;
+    K.glider_z = P.glider_z; K.disc_r = P.disc_r; K.disc_z0 = P.disc_z0; K.disc_z1 = P.disc_z1; K.stack_r = P.stack_r; K.stack_top = P.stack_top;
+    K.two_buttons = TWOB ? 1 : 0;
+    SrlPrim* out = reinterpret_cast<SrlPrim*>(prims + (size_t)i * SRL_MAX_PRIMS * SRL_PRIM_WORDS);
+    counts[i] = srl_kuka_scene(K, jp, sph, ns, e.bbx, e.bby, e.bbz, e.qb, e.bb2x, e.bb2y, P.btn_base[2], e.qb2, out);
+    (void)k; (void)ct;
+}
+
 // ---- host side -------------------------------------------------------------------------------
 bool fill_params(const void* blob, size_t bytes, const srl_sim* s, KukaParams& P) {
     const double* d = (const double*)blob;
@@ -794,6 +848,15 @@ int kuka_launch_prefetch(srl_sim* s, cudaStream_t st) {
     SRL_CUDA_OK(cudaEventRecord(s->pf_ev, st));
     s->pf_pending = true;
     s->launches += 1;
+    return 0;
+}
+
+int kuka_render_prims(srl_sim* s, float* prims, int* counts, cudaStream_t st) {
+    KukaDev* d = s->kuka;
+    const int grid = (s->n + 63) / 64;
+    if (d->P.two_buttons) kuka_prims_kernel<true><<<grid, 64, 0, st>>>(*d, s->n, prims, counts);
+    else kuka_prims_kernel<false><<<grid, 64, 0, st>>>(*d, s->n, prims, counts);
+    SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -144,6 +144,7 @@ void srl_sim_destroy(srl_sim* s) {
     DeviceGuard guard(s->device);
     cudaDeviceSynchronize();
     if (srl_is_mobile(s->kind)) mobile_free(s); else kuka_free(s);
+    render_free(s);
     for (int k = 0; k < 5; ++k) if (s->stage[k]) cudaFree(s->stage[k]);
     for (int k = 0; k < 3; ++k) if (s->host_st[k]) cudaStreamDestroy(s->host_st[k]);
     for (int k = 0; k < 2 * SRL_HOST_MAX_CHUNKS; ++k) if (s->host_ev[k]) cudaEventDestroy(s->host_ev[k]);
@@ -267,6 +268,14 @@ int srl_sim_rollout_host(srl_sim* s, int T, const void* actions, const float* no
     SRL_CUDA_OK(cudaStreamSynchronize(st_run));   // the state update is complete even when no output was requested
     SRL_CUDA_OK(cudaStreamSynchronize(st_out));
     return 0;
+}
+
+int srl_sim_render(srl_sim* s, const srl_camera* camera, int width, int height, uint8_t* rgb_out, void* stream) {
+    if (!s || !camera || !rgb_out) { srl_set_error("render: null argument"); return 1; }
+    if (width <= 0 || height <= 0 || width > 4096 || height > 4096) { srl_set_error("render: bad image size %d x %d", width, height); return 1; }
+    if (!(camera->distance > 0.f) || !(camera->fov > 0.f && camera->fov < 180.f)) { srl_set_error("render: bad camera (distance %g, fov %g)", camera->distance, camera->fov); return 1; }
+    DeviceGuard guard(s->device);
+    return render_launch(s, camera, width, height, rgb_out, (cudaStream_t)stream);
 }
 
 int srl_sim_get_state(srl_sim* s, int field, void* dst, size_t bytes) {

@@ -138,7 +138,7 @@ class KukaButtonGymEnv(SRLGymEnv):
             self.state_dim = self.getGroundTruthDim() + self.getJointsDim()
 
         if self.srl_model == "raw_pixels":
-            self.observation_space = spaces.Box(low=0, high=255, shape=(self._height, self._width, 3), dtype=np.uint8)
+            self.observation_space = spaces.Box(low=0, high=255, shape=(self._height, self._width, 6 if multi_view else 3), dtype=np.uint8)
         else:
             self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.state_dim,), dtype=np.float32)
 
@@ -203,11 +203,6 @@ class KukaButtonGymEnv(SRLGymEnv):
         self.n_contacts, self.n_steps_outside, self.terminated = int(c[0]), int(c[1]), bool(c[2])
         self._env_step_counter = int(self._sim.get_state(_abi.F_STEP_COUNTER)[0, 0])
 
-    def _require_state_obs(self):
-        if self.srl_model == "raw_pixels" and self.saver is None:   # a recording run never looks at the image observation
-            raise NotImplementedError("image observations (raw_pixels) are out of scope of the batched simulator; "
-                                      "use srl_model='ground_truth'")
-
     def _draw_button_placement(self):
         """np_random draws that place the button (:227-231) -> (x, y) handed to the kernel."""
         x_pos, y_pos = 0.5, 0
@@ -239,28 +234,31 @@ class KukaButtonGymEnv(SRLGymEnv):
         return draws + [0.0]
 
     def reset(self):
-        self._require_state_obs()
         draws = self._backend.from_host(np.asarray([self._reset_draws()], dtype=np.float64))
         self._sim.reset(mask=None, reset_draws=draws, obs_out=self._obs_buf, stream=self._backend.stream())
         self._pull_state()
         if self.saver is not None:   # (:275-276)
-            self.saver.reset(None, self.getTargetPos(), self.getGroundTruth())
+            self.saver.reset(self._frame_for_saver(), self.getTargetPos(), self.getGroundTruth())
         return self._state_or_image()
 
+    def _frame_for_saver(self):
+        """The frame EpisodeSaver stores next to the state (:275-276, :362-363): rendered when images are what the env observes."""
+        if self.srl_model == "raw_pixels":
+            return self.getExtendedObservation()
+        return None
+
     def _state_or_image(self):
-        """What reset() / step() return (:278-281, :365-368): the SRL state, or -- raw_pixels -- the image, which only a
-        recording run (that ignores it) can get here: an empty placeholder."""
+        """What reset() / step() return (:278-281, :365-368): the SRL state, or -- raw_pixels -- the rendered frame."""
         if self.srl_model != "raw_pixels":
             return self.getSRLState(self._observation)
-        return np.array(self._observation)
+        return np.array(self.getExtendedObservation())
 
     def getExtendedObservation(self):
-        """Image observation of the reference (:287-291); not rendered by the simulator."""
-        self._require_state_obs()
+        """Image observation of the reference (:287-291): the frame of the fixed camera (two cameras with multi_view)."""
+        self._observation = self.render("rgb_array")
         return self._observation
 
     def step(self, action):
-        self._require_state_obs()
         be = self._backend
         noise = 0.0
         if action is None:
@@ -285,13 +283,15 @@ class KukaButtonGymEnv(SRLGymEnv):
         self._pull_state()
         reward = rew if self._shape_reward else int(rew)
         if self.saver is not None:   # (:362-363)
-            self.saver.step(None, self.action, reward, done, self.getGroundTruth())
+            self.saver.step(self._frame_for_saver(), self.action, reward, done, self.getGroundTruth())
         return self._state_or_image(), reward, done, {}
 
     def render(self, mode='human', close=False):
         if mode != "rgb_array":
             return np.array([])
-        raise NotImplementedError("the batched simulator does not rasterise images (SURVEY section 8(f), item 4)")
+        from srl_sim.render import KUKA_CAMERA, KUKA_CAMERA_2, render_batch
+        cams = [KUKA_CAMERA, KUKA_CAMERA_2] if self.multi_view else [KUKA_CAMERA]      # (:385-418)
+        return self._backend.to_host(render_batch(self._sim, self._backend, cams, self._width, self._height))[0].copy()
 
     def close(self):
         if getattr(self, "_sim", None) is not None:

@@ -17,6 +17,7 @@ class MobileRobot1DGymEnv(MobileRobotGymEnv):
 
     def __init__(self, name="mobile_robot_1D", **kwargs):
         super(MobileRobot1DGymEnv, self).__init__(name=name, **kwargs)
+        self.camera_target_pos = (2, 0, 0)        # (:33)
 
     def _make_action_space(self):
         if self._is_discrete:

@@ -55,7 +55,7 @@ class MobileRobotGymEnv(SRLGymEnv):
     :param state_dim: (int) When learning states
     :param env_rank: (int) the number ID of the environment
     :param srl_pipe: (Queue, [Queue]) contains the input and output of the SRL model
-    :param fpv: (bool) first person view camera (image path, out of scope)
+    :param fpv: (bool) first person view camera: a second frame stacked on the channels of the image observation
     :param device: (int) CUDA device ordinal (extension; default 0)
     """
     _ENV_ID = "MobileRobotGymEnv-v0"
@@ -93,6 +93,7 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.has_bumped = False
         self.collision_margin = 0.1
         self.fpv = fpv
+        self.camera_target_pos = (2, 2, 0)        # (:84); the 1-D variant looks at (2, 0, 0)
         self.srl_model = srl_model
 
         if record_data:   # (:109-111)
@@ -104,7 +105,7 @@ class MobileRobotGymEnv(SRLGymEnv):
         if self.srl_model == "ground_truth":
             self.state_dim = self.getGroundTruthDim()
         if self.srl_model == "raw_pixels":
-            self.observation_space = spaces.Box(low=0, high=255, shape=(self._height, self._width, 3), dtype=np.uint8)
+            self.observation_space = spaces.Box(low=0, high=255, shape=(self._height, self._width, 6 if fpv else 3), dtype=np.uint8)
         else:
             self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.state_dim,), dtype=np.float32)
 
@@ -154,13 +155,7 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.robot_pos = self._sim.get_state(_abi.F_ROBOT_POS)[0].copy()
         self.target_pos = self._sim.get_state(_abi.F_TARGET_POS)[0].copy()
 
-    def _require_state_obs(self):
-        if self.srl_model == "raw_pixels" and self.saver is None:   # a recording run never looks at the image observation
-            raise NotImplementedError("image observations (raw_pixels) are out of scope of the batched simulator; "
-                                      "use srl_model='ground_truth'")
-
     def reset(self):
-        self._require_state_obs()
         self.terminated = False
         draws = self._backend.from_host(np.asarray([self._reset_draws()], dtype=np.float64))
         self._sim.reset(mask=None, reset_draws=draws, obs_out=self._obs_buf, stream=self._backend.stream())
@@ -168,17 +163,20 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.has_bumped = False
         self._pull_state()
         if self.saver is not None:   # (:216-217)
-            self.saver.reset(None, self.getTargetPos(), self.getGroundTruth())
+            self.saver.reset(self._frame_for_saver(), self.getTargetPos(), self.getGroundTruth())
         return self._state_or_image()
+
+    def _frame_for_saver(self):
+        return self.getObservation() if self.srl_model == "raw_pixels" else None
 
     def _state_or_image(self):
         if self.srl_model != "raw_pixels":
             return self.getSRLState(self._observation)
-        return np.array(self._observation)
+        return np.array(self.getObservation())
 
     def getObservation(self):
-        """Image observation of the reference (:228-233); not rendered by the simulator."""
-        self._require_state_obs()
+        """Image observation of the reference (:228-233): the frame of the fixed top-down camera (+ the first-person frame with fpv)."""
+        self._observation = self.render("rgb_array")
         return self._observation
 
     def _encode_action(self, action):
@@ -187,7 +185,6 @@ class MobileRobotGymEnv(SRLGymEnv):
         return np.asarray(action, dtype=np.float32).reshape(1, -1)
 
     def step(self, action):
-        self._require_state_obs()
         # dv = DELTA_POS + np_random.normal(0.0, scale=NOISE_STD): the draw is consumed like in the reference
         noise = self.np_random.normal(0.0, scale=NOISE_STD)
         be = self._backend
@@ -202,13 +199,17 @@ class MobileRobotGymEnv(SRLGymEnv):
         self.has_bumped = bool(self._sim.get_state(_abi.F_COUNTERS)[0, 1])
         reward = rew if self._shape_reward else int(rew)
         if self.saver is not None:   # (:274-275)
-            self.saver.step(None, action, reward, done, self.getGroundTruth())
+            self.saver.step(self._frame_for_saver(), action, reward, done, self.getGroundTruth())
         return self._state_or_image(), reward, done, {}
 
     def render(self, mode='human', close=False):
         if mode != "rgb_array":
             return np.array([])
-        raise NotImplementedError("the batched simulator does not rasterise images (SURVEY section 8(f), item 4)")
+        from srl_sim.render import MOBILE_CAMERA, mobile_fpv_camera, render_batch
+        cams = [dict(MOBILE_CAMERA, target=self.camera_target_pos)]
+        if self.fpv:      # first-person camera stacked on the channels (:316-332)
+            cams.append(mobile_fpv_camera(self.robot_pos))
+        return self._backend.to_host(render_batch(self._sim, self._backend, cams, RENDER_WIDTH, RENDER_HEIGHT))[0].copy()
 
     def close(self):
         if getattr(self, "_sim", None) is not None:

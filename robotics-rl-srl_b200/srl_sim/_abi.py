@@ -79,6 +79,7 @@ _EXPORTS = [
     ("srl_sim_rollout", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("srl_sim_rollout_host", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("srl_sim_prefetch_resets", c_int, [c_void_p, c_void_p]),
+    ("srl_sim_render", c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     ("srl_sim_get_state", c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     ("srl_sim_set_state", c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     ("srl_sim_launch_count", c_uint64, [c_void_p]),
@@ -225,6 +226,11 @@ class Sim(object):
         the helper slots of every step / rollout launch keep the records up; call this once after a reset of all envs."""
         rc = self._lib.srl_sim_prefetch_resets(self.handle, stream)
         self.library.check(rc, "srl_sim_prefetch_resets")
+
+    def render(self, cam, width, height, rgb_out, stream=None):
+        """One ``width`` x ``height`` RGB frame per env into ``rgb_out`` (u8[N, H, W, 3]); ``cam`` is an ``srl_sim.render.SrlCamera``."""
+        rc = self._lib.srl_sim_render(self.handle, ctypes.byref(cam), int(width), int(height), _ptr(rgb_out), stream)
+        self.library.check(rc, "srl_sim_render")
 
     # -- state access ------------------------------------------------------------------------
     def get_state(self, field):

@@ -46,9 +46,19 @@ class BatchedSRLVecEnv(object):
             raise KeyError("unknown env id %r" % env_id)
         srl_model = env_kwargs.pop("srl_model", "ground_truth")
         kuka_state_models = ("joints", "joints_position") if env_id.startswith("Kuka") else ()
-        if srl_model != "ground_truth" and srl_model not in kuka_state_models:
-            raise NotImplementedError("BatchedSRLVecEnv provides the state observations ground_truth%s (got srl_model=%r)"
+        if srl_model not in ("ground_truth", "raw_pixels") and srl_model not in kuka_state_models:
+            raise NotImplementedError("BatchedSRLVecEnv provides ground_truth%s states and raw_pixels frames (got srl_model=%r; learned SRL models are out of scope)"
                                       % ("".join(" / " + m for m in kuka_state_models), srl_model))
+        # raw_pixels: one rendered frame per env and camera (srl_sim/render.py; multi_view / fpv stack a second camera on the channels)
+        self._cams = None
+        if srl_model == "raw_pixels":
+            from . import render as _render
+            if env_id.startswith("Kuka"):
+                self._cams = [_render.KUKA_CAMERA] + ([_render.KUKA_CAMERA_2] if env_kwargs.get("multi_view", False) else [])
+            else:
+                self._cams = [dict(_render.MOBILE_CAMERA, target=(2, 0, 0) if env_id == "MobileRobot1DGymEnv-v0" else (2, 2, 0))]
+                if env_kwargs.get("fpv", False):
+                    raise NotImplementedError("fpv frames follow each robot: use the single-env classes (one camera per env)")
         self.srl_model = srl_model
         self.env_id = env_id
         self.num_envs = int(num_envs)
@@ -76,8 +86,12 @@ class BatchedSRLVecEnv(object):
         if srl_model in ("joints", "joints_position"):
             from .model import KUKA_INIT_JOINT_POSITIONS
             self._joints = np.tile(np.asarray(KUKA_INIT_JOINT_POSITIONS, np.float32), (self.num_envs, 1))
-        out_dim = {"ground_truth": D, "joints": 14, "joints_position": D + 14}[srl_model]
-        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(out_dim,), dtype=np.float32)
+        if srl_model == "raw_pixels":
+            from .render import RENDER_HEIGHT, RENDER_WIDTH
+            self.observation_space = spaces.Box(low=0, high=255, shape=(RENDER_HEIGHT, RENDER_WIDTH, 3 * len(self._cams)), dtype=np.uint8)
+        else:
+            out_dim = {"ground_truth": D, "joints": 14, "joints_position": D + 14}[srl_model]
+            self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(out_dim,), dtype=np.float32)
         self._monitor = None
         if log_dir is not None:
             from .monitor import MonitorWriter
@@ -99,8 +113,16 @@ class BatchedSRLVecEnv(object):
         self.closed = False
 
     # ---- VecEnv API (numpy) --------------------------------------------------------------------------
+    def render_tensors(self):
+        """The current frame of every env, ``uint8 [N, H, W, 3 * cameras]`` in the backend's memory (a CUDA tensor on a GPU)."""
+        from .render import KUKA_CAMERA, MOBILE_CAMERA, render_batch
+        cams = self._cams or ([KUKA_CAMERA] if self.env_id.startswith("Kuka") else [MOBILE_CAMERA])
+        return render_batch(self.sim, self.backend, cams)
+
     def _state(self, obs):
-        """ground-truth observation [N, D] -> the configured state (getSRLState)."""
+        """ground-truth observation [N, D] -> the configured state (getSRLState), or the rendered frames (raw_pixels)."""
+        if self.srl_model == "raw_pixels":
+            return self.backend.to_host(self.render_tensors()).copy()
         if self._joints is None:
             return obs
         return self._joints.copy() if self.srl_model == "joints" else np.concatenate([obs, self._joints], axis=1)
@@ -149,7 +171,8 @@ class BatchedSRLVecEnv(object):
         raise NotImplementedError("the batch is seeded at construction (counter-based streams keyed by env index)")
 
     def get_images(self):
-        raise NotImplementedError("image observations are out of scope of the batched simulator")
+        """VecEnv.get_images: one RGB frame per env (numpy)."""
+        return list(self.backend.to_host(self.render_tensors()))
 
     def render(self, mode="human"):
         raise NotImplementedError("image observations are out of scope of the batched simulator")

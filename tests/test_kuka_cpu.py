@@ -269,8 +269,9 @@ def test_single_env_classes_on_oracle(use_oracle_backend):
     assert jt.action_space.shape == (7,)
     o, r, d, _ = jt.step(jt.action_space.sample())
     assert o.shape == (3,) and r in (-1, 0, 1) and not d
-    with pytest.raises(NotImplementedError):
-        registered_env["KukaButtonGymEnv-v0"][0]().reset()             # default raw_pixels: no rasteriser
+    px = registered_env["KukaButtonGymEnv-v0"][0]()                      # the reference's default observation: raw_pixels (tests/test_render_cpu.py)
+    px.seed(0)
+    assert px.reset().shape == (224, 224, 3)
 
 
 # ---- env-level logic pinned against the REFERENCE classes ---------------------------------------------------
