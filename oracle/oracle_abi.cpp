@@ -220,8 +220,9 @@ int srl_sim_render(srl_sim* s, const srl_camera* cam, int width, int height, uin
     if (!s || !cam || !rgb_out) { oracle_set_error("render: null argument"); return 1; }
     if (width <= 0 || height <= 0) { oracle_set_error("render: bad image size"); return 1; }
     SrlCam c;
-    srl_camera_setup(cam->target, cam->distance, cam->yaw, cam->pitch, cam->roll, cam->fov, (float)width / (float)height, c);
+    srl_camera_setup(cam->target, cam->distance, cam->yaw, cam->pitch, cam->roll, cam->fov, width, height, c);
     std::vector<SrlPrim> prims(SRL_MAX_PRIMS);
+    std::vector<SrlPrep> prep(SRL_MAX_PRIMS);
     for (int i = 0; i < s->n; ++i) {
         int np;
         if (is_mobile(s->kind)) {
@@ -229,9 +230,11 @@ int srl_sim_render(srl_sim* s, const srl_camera* cam, int width, int height, uin
             const int rk = s->kind == SRL_ENV_MOBILE_2TARGET ? 1 : s->kind == SRL_ENV_MOBILE_LINE_TARGET ? 2 : s->kind == SRL_ENV_MOBILE_1D ? 3 : 0;
             np = srl_mobile_scene(rk, (float)e.pos[0], (float)e.pos[1], (float)e.target[0][0], (float)e.target[0][1], (float)e.target[1][0], (float)e.target[1][1], prims.data());
         } else np = oracle_kuka_scene(s, i, prims.data());
+        for (int k = 0; k < np; ++k) srl_prepare(c.eye, prims[k], prep[k]);
         uint8_t* frame = rgb_out + (size_t)i * height * width * 3;
         for (int y = 0; y < height; ++y)
-            for (int x = 0; x < width; ++x) srl_render_pixel(c, prims.data(), np, x, y, width, height, frame + ((size_t)y * width + x) * 3);
+            for (int x = 0; x < width; ++x)
+                srl_render_pixel(c, prep.data(), prims.data(), srl_prim_mask_all(np), x, y, frame + ((size_t)y * width + x) * 3);
     }
     return 0;
 }

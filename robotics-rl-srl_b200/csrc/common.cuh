@@ -59,6 +59,7 @@ struct srl_sim {
     bool host_pipe_ready;
     int host_chunks;    // SRL_HOST_CHUNKS override (0 = by bytes moved)
     float* render_prims; // [N][SRL_MAX_PRIMS][16] scene primitives of the last srl_sim_render (allocated on first use)
+    float* render_prep;  // same shape: their per-camera prepared forms (render_core.h SrlPrep)
     int* render_counts;
     bool host_zero_copy; // single-chunk rollouts store obs / reward / done straight into pinned, device-mapped host buffers (opt-in: SRL_HOST_ZEROCOPY=1)
 };

@@ -32,7 +32,8 @@ enum { SRL_PRIM_PLANE = 0, SRL_PRIM_SPHERE = 1, SRL_PRIM_CAPSULE = 2, SRL_PRIM_C
 //   BOX     a0..2 centre, a3..5 half extents, a6 cos, a7 sin  (rotated about z)
 struct SrlPrim { float type, a[11], r, g, b, pad; };
 
-struct SrlCam { float eye[3], fwd[3], right[3], up[3], tan_half_fov, aspect; };
+// pixel (x, y) (row 0 = top) looks along fwd + u right + v up with u = ub + su (x + 0.5), v = vb - sv (y + 0.5)
+struct SrlCam { float eye[3], fwd[3], right[3], up[3], ub, su, vb, sv; };
 
 SRL_RHD void srl_prim_set(SrlPrim& p, int type, float r, float g, float b) {
     p.type = (float)type; p.r = r; p.g = g; p.b = b; p.pad = 0.f;
@@ -63,7 +64,7 @@ SRL_RHD void srl_prim_plane(SrlPrim& p, float z, float checker, float r, float g
 
 // ---- camera: pybullet's computeViewMatrixFromYawPitchRoll (upAxisIndex = 2) + computeProjectionMatrixFOV, as eye + basis (RECALLED from
 //      PhysicsClientC_API.cpp: eye = target + Rz(yaw) Ry(roll) Rx(pitch) (0, -distance, 0), up = the same rotation of (0, 0, 1)) ----
-SRL_RHD void srl_camera_setup(const float* target, float distance, float yaw_deg, float pitch_deg, float roll_deg, float fov_deg, float aspect, SrlCam& c) {
+SRL_RHD void srl_camera_setup(const float* target, float distance, float yaw_deg, float pitch_deg, float roll_deg, float fov_deg, int W, int H, SrlCam& c) {
     const float d2r = 0.01745329251994329547f;
     const float cy = cosf(yaw_deg * d2r), sy = sinf(yaw_deg * d2r), cp = cosf(pitch_deg * d2r), sp = sinf(pitch_deg * d2r);
     const float cr = cosf(roll_deg * d2r), sr = sinf(roll_deg * d2r);
@@ -87,132 +88,184 @@ SRL_RHD void srl_camera_setup(const float* target, float distance, float yaw_deg
     c.up[0] = c.right[1] * c.fwd[2] - c.right[2] * c.fwd[1];
     c.up[1] = c.right[2] * c.fwd[0] - c.right[0] * c.fwd[2];
     c.up[2] = c.right[0] * c.fwd[1] - c.right[1] * c.fwd[0];
-    c.tan_half_fov = tanf(0.5f * fov_deg * d2r);
-    c.aspect = aspect;
+    const float th = tanf(0.5f * fov_deg * d2r), aspect = (float)W / (float)H;      // computeProjectionMatrixFOV: vertical fov, aspect = width / height
+    c.ub = -th * aspect; c.su = 2.f * th * aspect / (float)W;
+    c.vb = th; c.sv = 2.f * th / (float)H;
 }
 
-// ---- ray / primitive intersections: nearest t > tmin, outward normal ----
-SRL_RHD bool srl_hit_sphere(const float* o, const float* d, const float* c, float r, float& t, float* n) {
-    const float ox = o[0] - c[0], oy = o[1] - c[1], oz = o[2] - c[2];
-    const float b = ox * d[0] + oy * d[1] + oz * d[2], cc = ox * ox + oy * oy + oz * oz - r * r;
+// ---- per-camera prepared form of a primitive: everything of the intersection arithmetic that does not depend on the pixel ----------------
+//   PLANE   g0 = z - eye_z
+//   SPHERE  g0..2 = eye - centre, g3 = |eye - centre|^2 - r^2
+//   CAPSULE g0..2 = ba = end1 - end0, g3..5 = oa = eye - end0, g6 = ba.ba, g7 = ba.oa, g8 = ba.ba oa.oa - (ba.oa)^2 - r^2 ba.ba,
+//           g9 = oa.oa - r^2, g10 = |eye - end1|^2 - r^2                (a zero-length capsule is prepared as the SPHERE it is)
+//   CYL     g0, g1 = eye.xy - centre.xy, g2 = g0^2 + g1^2 - r^2, g3 = z0 - eye_z, g4 = z1 - eye_z, g5 = r^2
+//   BOX     g0..2 = eye - centre in the box frame, g3..5 = half extents, g6 = cos, g7 = sin
+// u0..v1: the screen-space bound the CUDA tile test reads (filled by the caller; the CPU checker does not cull).
+struct SrlPrep { float type, g[11], u0, u1, v0, v1; };
+
+SRL_RHD void srl_prepare(const float* eye, const SrlPrim& p, SrlPrep& q) {
+    const int type = (int)p.type;
+    q.type = p.type;
+    for (int i = 0; i < 11; ++i) q.g[i] = 0.f;
+    q.u0 = -1e30f; q.u1 = 1e30f; q.v0 = -1e30f; q.v1 = 1e30f;
+    if (type == SRL_PRIM_PLANE) q.g[0] = p.a[0] - eye[2];
+    else if (type == SRL_PRIM_SPHERE) {
+        const float ox = eye[0] - p.a[0], oy = eye[1] - p.a[1], oz = eye[2] - p.a[2];
+        q.g[0] = ox; q.g[1] = oy; q.g[2] = oz; q.g[3] = ox * ox + oy * oy + oz * oz - p.a[3] * p.a[3];
+    } else if (type == SRL_PRIM_CAPSULE) {
+        const float r = p.a[6];
+        const float ba[3] = {p.a[3] - p.a[0], p.a[4] - p.a[1], p.a[5] - p.a[2]}, oa[3] = {eye[0] - p.a[0], eye[1] - p.a[1], eye[2] - p.a[2]};
+        const float ob[3] = {eye[0] - p.a[3], eye[1] - p.a[4], eye[2] - p.a[5]};
+        const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2], baoa = ba[0] * oa[0] + ba[1] * oa[1] + ba[2] * oa[2];
+        const float oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
+        if (baba < 1e-12f) {
+            q.type = (float)SRL_PRIM_SPHERE;
+            q.g[0] = oa[0]; q.g[1] = oa[1]; q.g[2] = oa[2]; q.g[3] = oaoa - r * r;
+        } else {
+            for (int i = 0; i < 3; ++i) { q.g[i] = ba[i]; q.g[3 + i] = oa[i]; }
+            q.g[6] = baba; q.g[7] = baoa; q.g[8] = baba * oaoa - baoa * baoa - r * r * baba;
+            q.g[9] = oaoa - r * r; q.g[10] = ob[0] * ob[0] + ob[1] * ob[1] + ob[2] * ob[2] - r * r;
+        }
+    } else if (type == SRL_PRIM_CYL) {
+        const float ox = eye[0] - p.a[0], oy = eye[1] - p.a[1];
+        q.g[0] = ox; q.g[1] = oy; q.g[2] = ox * ox + oy * oy - p.a[4] * p.a[4]; q.g[3] = p.a[2] - eye[2]; q.g[4] = p.a[3] - eye[2]; q.g[5] = p.a[4] * p.a[4];
+    } else {
+        const float cs = p.a[6], sn = p.a[7], px = eye[0] - p.a[0], py = eye[1] - p.a[1];
+        q.g[0] = cs * px + sn * py; q.g[1] = -sn * px + cs * py; q.g[2] = eye[2] - p.a[2];
+        q.g[3] = p.a[3]; q.g[4] = p.a[4]; q.g[5] = p.a[5]; q.g[6] = cs; q.g[7] = sn;
+    }
+}
+
+// ---- ray (eye, unit d) against a prepared primitive: the nearest t > 1e-4, or false ----
+SRL_RHD bool srl_sphere_t(float b, float cc, float& t) {          // b = (eye - c).d, cc = |eye - c|^2 - r^2
     const float h = b * b - cc;
     if (h < 0.f) return false;
-    const float tt = -b - sqrtf(h);
-    if (tt <= 1e-4f) return false;
-    t = tt;
-    n[0] = (ox + tt * d[0]) / r; n[1] = (oy + tt * d[1]) / r; n[2] = (oz + tt * d[2]) / r;
-    return true;
+    t = -b - sqrtf(h);
+    return t > 1e-4f;
 }
-SRL_RHD bool srl_hit_capsule(const float* o, const float* d, const float* pa, const float* pb, float r, float& t, float* n) {
-    // closed form for a capped-by-spheres cylinder (the segment pa-pb swept by a sphere of radius r)
-    const float ba[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, oa[3] = {o[0] - pa[0], o[1] - pa[1], o[2] - pa[2]};
-    const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2];
-    if (baba < 1e-12f) return srl_hit_sphere(o, d, pa, r, t, n);
-    const float bard = ba[0] * d[0] + ba[1] * d[1] + ba[2] * d[2], baoa = ba[0] * oa[0] + ba[1] * oa[1] + ba[2] * oa[2];
-    const float rdoa = d[0] * oa[0] + d[1] * oa[1] + d[2] * oa[2], oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
-    const float a = baba - bard * bard;
-    float b = baba * rdoa - baoa * bard, c = baba * oaoa - baoa * baoa - r * r * baba;
-    float h = b * b - a * c;
-    float tt = -1.f;
-    if (h >= 0.f && a > 1e-12f) {
-        const float t0 = (-b - sqrtf(h)) / a;
-        const float y = baoa + t0 * bard;
-        if (y > 0.f && y < baba && t0 > 1e-4f) {      // body
-            tt = t0;
-            const float k = y / baba;
-            n[0] = (oa[0] + t0 * d[0] - ba[0] * k) / r; n[1] = (oa[1] + t0 * d[1] - ba[1] * k) / r; n[2] = (oa[2] + t0 * d[2] - ba[2] * k) / r;
+SRL_RHD bool srl_hit_t(const SrlPrep& q, const float* d, float& t) {
+    const int type = (int)q.type;
+    const float* g = q.g;
+    if (type == SRL_PRIM_PLANE) {
+        if (!(d[2] < -1e-6f)) return false;
+        t = g[0] / d[2];
+        return t > 1e-4f;
+    }
+    if (type == SRL_PRIM_SPHERE) return srl_sphere_t(g[0] * d[0] + g[1] * d[1] + g[2] * d[2], g[3], t);
+    if (type == SRL_PRIM_CAPSULE) {
+        // the segment end0-end1 swept by a sphere: the open cylinder between the ends first, else the nearer of the two end spheres
+        const float bard = g[0] * d[0] + g[1] * d[1] + g[2] * d[2], rdoa = g[3] * d[0] + g[4] * d[1] + g[5] * d[2];
+        const float a = g[6] - bard * bard, b = g[6] * rdoa - g[7] * bard;
+        const float h = b * b - a * g[8];
+        if (h >= 0.f && a > 1e-12f) {
+            const float t0 = (-b - sqrtf(h)) / a;
+            const float y = g[7] + t0 * bard;
+            if (y > 0.f && y < g[6] && t0 > 1e-4f) { t = t0; return true; }
         }
+        float t1 = 0.f, t2 = 0.f;
+        const bool h1 = srl_sphere_t(rdoa, g[9], t1), h2 = srl_sphere_t(rdoa - bard, g[10], t2);
+        if (h1 && (!h2 || t1 <= t2)) { t = t1; return true; }
+        if (h2) { t = t2; return true; }
+        return false;
     }
-    if (tt < 0.f) {                                    // caps: the nearer of the two end spheres
-        float t1, n1[3], t2, n2[3];
-        const bool h1 = srl_hit_sphere(o, d, pa, r, t1, n1), h2 = srl_hit_sphere(o, d, pb, r, t2, n2);
-        if (h1 && (!h2 || t1 <= t2)) { tt = t1; n[0] = n1[0]; n[1] = n1[1]; n[2] = n1[2]; }
-        else if (h2) { tt = t2; n[0] = n2[0]; n[1] = n2[1]; n[2] = n2[2]; }
-        else return false;
-    }
-    t = tt;
-    return true;
-}
-SRL_RHD bool srl_hit_cyl(const float* o, const float* d, float cx, float cy, float z0, float z1, float r, float& t, float* n) {
-    float best = 1e30f;
-    const float ox = o[0] - cx, oy = o[1] - cy;
-    const float a = d[0] * d[0] + d[1] * d[1];
-    if (a > 1e-12f) {                                  // side
-        const float b = ox * d[0] + oy * d[1], c = ox * ox + oy * oy - r * r;
-        const float h = b * b - a * c;
-        if (h >= 0.f) {
-            const float tt = (-b - sqrtf(h)) / a;
-            const float z = o[2] + tt * d[2];
-            if (tt > 1e-4f && z >= z0 && z <= z1) { best = tt; n[0] = (ox + tt * d[0]) / r; n[1] = (oy + tt * d[1]) / r; n[2] = 0.f; }
+    if (type == SRL_PRIM_CYL) {
+        float best = 1e30f;
+        const float a = d[0] * d[0] + d[1] * d[1];
+        if (a > 1e-12f) {                                  // side
+            const float b = g[0] * d[0] + g[1] * d[1];
+            const float h = b * b - a * g[2];
+            if (h >= 0.f) {
+                const float tt = (-b - sqrtf(h)) / a;
+                const float z = tt * d[2];
+                if (tt > 1e-4f && z >= g[3] && z <= g[4]) best = tt;
+            }
         }
+        if (fabsf(d[2]) > 1e-12f) {                        // the cap facing the ray
+            const float tt = (d[2] < 0.f ? g[4] : g[3]) / d[2];
+            const float x = g[0] + tt * d[0], y = g[1] + tt * d[1];
+            if (tt > 1e-4f && tt < best && x * x + y * y <= g[5]) best = tt;
+        }
+        if (best > 1e29f) return false;
+        t = best;
+        return true;
     }
-    if (fabsf(d[2]) > 1e-12f) {                        // caps
-        const float zc = d[2] < 0.f ? z1 : z0;
-        const float tt = (zc - o[2]) / d[2];
-        const float x = ox + tt * d[0], y = oy + tt * d[1];
-        if (tt > 1e-4f && tt < best && x * x + y * y <= r * r) { best = tt; n[0] = 0.f; n[1] = 0.f; n[2] = d[2] < 0.f ? 1.f : -1.f; }
-    }
-    if (best > 1e29f) return false;
-    t = best;
-    return true;
-}
-SRL_RHD bool srl_hit_box(const float* o, const float* d, const float* a, float& t, float* n) {
-    // into the box frame (rotation about z by the box's yaw)
-    const float cs = a[6], sn = a[7];
-    const float px = o[0] - a[0], py = o[1] - a[1], pz = o[2] - a[2];
-    const float lo[3] = {cs * px + sn * py, -sn * px + cs * py, pz}, ld[3] = {cs * d[0] + sn * d[1], -sn * d[0] + cs * d[1], d[2]};
-    float tn = -1e30f, tf = 1e30f; int axis = 0; float sign = 1.f;
+    // box: slabs in the box frame
+    const float ld[3] = {g[6] * d[0] + g[7] * d[1], -g[7] * d[0] + g[6] * d[1], d[2]};
+    float tn = -1e30f, tf = 1e30f;
     for (int k = 0; k < 3; ++k) {
-        if (fabsf(ld[k]) < 1e-12f) { if (fabsf(lo[k]) > a[3 + k]) return false; continue; }
+        if (fabsf(ld[k]) < 1e-12f) { if (fabsf(g[k]) > g[3 + k]) return false; continue; }
         const float inv = 1.f / ld[k];
-        float t0 = (-a[3 + k] - lo[k]) * inv, t1 = (a[3 + k] - lo[k]) * inv;
-        float sg = -1.f;
-        if (t0 > t1) { const float tmp = t0; t0 = t1; t1 = tmp; sg = 1.f; }
-        if (t0 > tn) { tn = t0; axis = k; sign = sg; }
+        float t0 = (-g[3 + k] - g[k]) * inv, t1 = (g[3 + k] - g[k]) * inv;
+        if (t0 > t1) { const float tmp = t0; t0 = t1; t1 = tmp; }
+        if (t0 > tn) tn = t0;
         if (t1 < tf) tf = t1;
     }
     if (tn > tf || tn <= 1e-4f) return false;
     t = tn;
-    const float ln[3] = {axis == 0 ? sign : 0.f, axis == 1 ? sign : 0.f, axis == 2 ? sign : 0.f};
-    n[0] = cs * ln[0] - sn * ln[1]; n[1] = sn * ln[0] + cs * ln[1]; n[2] = ln[2];
     return true;
 }
 
-// One pixel: nearest hit over the primitive list, ambient + Lambert shading, 8-bit RGB.  Row 0 is the TOP of the image (getCameraImage).
-SRL_RHD void srl_render_pixel(const SrlCam& c, const SrlPrim* prims, int np, int x, int y, int W, int H, uint8_t* rgb) {
-    const float u = (2.f * ((float)x + 0.5f) / (float)W - 1.f) * c.tan_half_fov * c.aspect;
-    const float v = (1.f - 2.f * ((float)y + 0.5f) / (float)H) * c.tan_half_fov;
+// Outward unit normal of primitive p at the surface point P.
+SRL_RHD void srl_normal_at(const SrlPrim& p, const float* P, float* n) {
+    const int type = (int)p.type;
+    n[0] = 0.f; n[1] = 0.f; n[2] = 1.f;
+    if (type == SRL_PRIM_SPHERE) { for (int i = 0; i < 3; ++i) n[i] = (P[i] - p.a[i]) / p.a[3]; }
+    else if (type == SRL_PRIM_CAPSULE) {
+        const float ba[3] = {p.a[3] - p.a[0], p.a[4] - p.a[1], p.a[5] - p.a[2]}, w[3] = {P[0] - p.a[0], P[1] - p.a[1], P[2] - p.a[2]};
+        const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2];
+        float k = baba < 1e-12f ? 0.f : (w[0] * ba[0] + w[1] * ba[1] + w[2] * ba[2]) / baba;
+        k = k < 0.f ? 0.f : k > 1.f ? 1.f : k;
+        for (int i = 0; i < 3; ++i) n[i] = (w[i] - k * ba[i]) / p.a[6];
+    } else if (type == SRL_PRIM_CYL) {
+        const float rx = P[0] - p.a[0], ry = P[1] - p.a[1], r = p.a[4];
+        if (rx * rx + ry * ry < 0.9999f * r * r) n[2] = P[2] > 0.5f * (p.a[2] + p.a[3]) ? 1.f : -1.f;      // on a cap
+        else { n[0] = rx / r; n[1] = ry / r; n[2] = 0.f; }
+    } else if (type == SRL_PRIM_BOX) {
+        const float cs = p.a[6], sn = p.a[7], px = P[0] - p.a[0], py = P[1] - p.a[1];
+        const float l[3] = {cs * px + sn * py, -sn * px + cs * py, P[2] - p.a[2]};
+        int axis = 0; float out = fabsf(l[0]) - p.a[3];                   // the face the point lies on: the axis whose slab it is closest to leaving
+        for (int k = 1; k < 3; ++k) { const float o = fabsf(l[k]) - p.a[3 + k]; if (o > out) { out = o; axis = k; } }
+        const float sg = l[axis] < 0.f ? -1.f : 1.f;
+        const float ln[3] = {axis == 0 ? sg : 0.f, axis == 1 ? sg : 0.f, axis == 2 ? sg : 0.f};
+        n[0] = cs * ln[0] - sn * ln[1]; n[1] = sn * ln[0] + cs * ln[1]; n[2] = ln[2];
+    }
+}
+
+// One pixel: nearest hit over the primitives whose bit is set in `mask` (in list order), ambient + Lambert shading, 8-bit RGB.  Row 0 is the
+// TOP of the image (getCameraImage).  The CUDA kernel passes the subset whose screen bound reaches the pixel's neighbourhood; the CPU checker
+// passes all of them.  `prep[k]` is srl_prepare(c.eye, prims[k]).
+SRL_RHD unsigned long long srl_prim_mask_all(int np) { return np >= 64 ? ~0ull : ((1ull << np) - 1ull); }
+SRL_RHD void srl_render_pixel(const SrlCam& c, const SrlPrep* prep, const SrlPrim* prims, unsigned long long mask, int x, int y, uint8_t* rgb) {
+    const float u = c.ub + c.su * ((float)x + 0.5f);
+    const float v = c.vb - c.sv * ((float)y + 0.5f);
     float d[3] = {c.fwd[0] + u * c.right[0] + v * c.up[0], c.fwd[1] + u * c.right[1] + v * c.up[1], c.fwd[2] + u * c.right[2] + v * c.up[2]};
     const float dl = 1.f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     d[0] *= dl; d[1] *= dl; d[2] *= dl;
-    float best = 1e30f, bn[3] = {0.f, 0.f, 1.f}, col[3] = {0.84f, 0.89f, 0.95f};   // background (above the horizon)
-    bool hit = false;
-    for (int k = 0; k < np; ++k) {
-        const SrlPrim& p = prims[k];
-        const int type = (int)p.type;
-        float t = 0.f, n[3] = {0.f, 0.f, 1.f};
-        bool h = false;
-        float cr = p.r, cg = p.g, cb = p.b;
-        if (type == SRL_PRIM_PLANE) {
-            if (d[2] < -1e-6f) {
-                t = (p.a[0] - c.eye[2]) / d[2];
-                h = t > 1e-4f;
-                if (h && p.a[1] > 0.f) {
-                    const float px = c.eye[0] + t * d[0], py = c.eye[1] + t * d[1];
-                    const int ix = (int)floorf(px / p.a[1]), iy = (int)floorf(py / p.a[1]);
-                    if ((ix + iy) & 1) { cr = p.a[2]; cg = p.a[3]; cb = p.a[4]; }
-                }
-            }
-        } else if (type == SRL_PRIM_SPHERE) h = srl_hit_sphere(c.eye, d, p.a, p.a[3], t, n);
-        else if (type == SRL_PRIM_CAPSULE) h = srl_hit_capsule(c.eye, d, p.a, p.a + 3, p.a[6], t, n);
-        else if (type == SRL_PRIM_CYL) h = srl_hit_cyl(c.eye, d, p.a[0], p.a[1], p.a[2], p.a[3], p.a[4], t, n);
-        else h = srl_hit_box(c.eye, d, p.a, t, n);
-        if (h && t < best) { best = t; hit = true; bn[0] = n[0]; bn[1] = n[1]; bn[2] = n[2]; col[0] = cr; col[1] = cg; col[2] = cb; }
+    float best = 1e30f;
+    int win = -1;
+    while (mask) {
+#if defined(__CUDA_ARCH__)
+        const int k = __ffsll((long long)mask) - 1;
+#else
+        const int k = __builtin_ctzll(mask);
+#endif
+        mask &= mask - 1ull;
+        float t = 0.f;
+        if (srl_hit_t(prep[k], d, t) && t < best) { best = t; win = k; }
     }
-    float shade = 1.f;
-    if (hit) {
+    float shade = 1.f, col[3] = {0.84f, 0.89f, 0.95f};                 // background (above the horizon)
+    if (win >= 0) {
+        const SrlPrim& p = prims[win];
+        const float P[3] = {c.eye[0] + best * d[0], c.eye[1] + best * d[1], c.eye[2] + best * d[2]};
+        float n[3];
+        srl_normal_at(p, P, n);
+        col[0] = p.r; col[1] = p.g; col[2] = p.b;
+        if ((int)p.type == SRL_PRIM_PLANE && p.a[1] > 0.f) {
+            const int ix = (int)floorf(P[0] / p.a[1]), iy = (int)floorf(P[1] / p.a[1]);
+            if ((ix + iy) & 1) { col[0] = p.a[2]; col[1] = p.a[3]; col[2] = p.a[4]; }
+        }
         const float L[3] = {0.3713907f, 0.5570860f, 0.7427814f};     // normalised (2, 3, 4): one fixed directional light, no shadows
-        const float nl = bn[0] * L[0] + bn[1] * L[1] + bn[2] * L[2];
+        const float nl = n[0] * L[0] + n[1] * L[1] + n[2] * L[2];
         shade = 0.55f + 0.45f * (nl > 0.f ? nl : 0.f);
     }
     for (int k = 0; k < 3; ++k) {
