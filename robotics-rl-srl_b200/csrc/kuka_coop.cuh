@@ -63,15 +63,16 @@ enum {
 #define KC_CTS 9
 #define KC_OFF_MA (KC_OFF_CT + KK_MAXC * KC_CTS)   // M, lower triangle (every lane then inverts it in registers)
 #define KC_OFF_BIAS (KC_OFF_MA + KK_NB * KC_MS)    // [12] bias torques
-#define KC_OFF_ROWS (KC_OFF_BIAS + KK_NB)          // 3 * KK_MAXC constraint rows of KC_RS words: J[14], W[14], 1/D, target
-#define KC_RS 31
+#define KC_OFF_ROWS (((KC_OFF_BIAS + KK_NB + 3) / 4) * 4)   // 3 * KK_MAXC constraint rows of KC_RS words in the KK_ROW_* layout (kuka_params.cuh), 16-byte aligned
+#define KC_RS 36                                   // = 4 (mod 32): the 4 lanes that fill 4 consecutive rows hit different banks; a multiple of 4 words
 #define KC_OFF_END (KC_OFF_ROWS + 3 * KK_MAXC * KC_RS)
 #define KC_OFF_CAND KC_OFF_MA                      // collision candidates per sphere (count, then KC_CANDS records of 8 words: shape, dist, n, pt):
 #define KC_CANDS 3                                 // consumed by the collect phase before the dynamics write M, L, rows -- same storage
 #define KC_CANDW (1 + KC_CANDS * 8)
 #define KC_WORDS KC_OFF_END
 #define KC_ROWS4 ((KC_WORDS + 3) / 4)              // 16-byte rows per env
-static_assert(KC_BS % 4 == 1 && KC_MS % 4 == 1 && KC_RS % 4 == 3 && KC_CS % 4 == 1, "lane-indexed strides must be odd (1 or 3 mod 4)");
+static_assert(KC_BS % 4 == 1 && KC_MS % 4 == 1 && KC_CS % 4 == 1, "lane-indexed strides must be odd (1 or 3 mod 4)");
+static_assert(KC_RS % 32 == 4 && KC_RS >= KK_ROWW && KC_OFF_ROWS % 4 == 0, "constraint rows: 16-byte aligned, consecutive rows 4 banks apart");
 static_assert(KC_OFF_CAND + KM_MAX_SPHERES * KC_CANDW <= KC_OFF_END, "collision candidates must fit in the storage they share");
 
 // per-CTA constant tables (same for every env): body records of KC_CS words, then sphere records of 5 words
@@ -453,11 +454,11 @@ KC_F void kc_ph_mass(const S& s, int u) {
     }
 }
 
-// Phase C1 (A = M^-1 in registers, lower triangle valid): constraint rows of the contact manifold -- Jacobian, W = M^-1 J^T, 1 / D, target --
-// row r -> lane r & 3.
-template <bool TWOB, class S>
-KC_F void kc_ph_rows(const S& s, const KukaParams& P, const float (&A)[KK_NB][KK_NB], int nc, int u) {
-    constexpr int ND = TWOB ? KK_NB + 2 : KK_NB + 1;
+// Phase C1 (A = M^-1 in registers, lower triangle valid, UNSCALED): constraint rows of the contact manifold -- Jacobian, W = M^-1 J^T, 1 / D,
+// target -- row r -> lane r & 3, in the KK_ROW_* layout.  SCALED: stored for the scaled system of the sweeps (kuka_physics_step): J_j / sigma_j
+// and sigma_j W_j on the 12 arm DoF, target - J . tgt (tgt = the motor rows' target velocities).
+template <bool TWOB, bool SCALED, class S>
+KC_F void kc_ph_rows(const S& s, const KukaParams& P, const float (&A)[KK_NB][KK_NB], int nc, int u, const float* tgt = nullptr) {
 #pragma unroll 1
     for (int r = u; r < 3 * nc; r += KC_G) {
         const int c = r < nc ? r : (r - nc) >> 1;
@@ -478,27 +479,27 @@ KC_F void kc_ph_rows(const S& s, const KukaParams& P, const float (&A)[KK_NB][KK
         const int body = (int)s[co], shape = (int)s[co + 1];
         float J[KK_NB];
 #pragma unroll
-        for (int j = 0; j < KK_NB; ++j) {
+        for (int j = 0; j < KK_NB; ++j)
             J[j] = kc_anc(j, body) ? kc_dot(dir, kc_cross(kc_ld3(s, j * KC_BS + KB_A), kc_sub(pt, kc_ld3(s, j * KC_BS + KB_P)))) : 0.f;
-            s[ro + j] = J[j];
-        }
         const float jb = shape == 1 ? -dir.z : 0.f, jb2 = TWOB && shape == 3 ? -dir.z : 0.f;
-        s[ro + KK_NB] = jb;
-        if (TWOB) s[ro + ND - 1] = jb2;
-        float D = 0.f;
+        float D = 0.f, off = 0.f;
 #pragma unroll
         for (int i = 0; i < KK_NB; ++i) {
             float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < KK_NB; ++j) acc = fmaf(i >= j ? A[i][j] : A[j][i], J[j], acc);
-            s[ro + 14 + i] = acc; D = fmaf(J[i], acc, D);
+            D = fmaf(J[i], acc, D);
+            if (SCALED) off = fmaf(J[i], tgt[i], off);
+            s[ro + KK_ROW_J + i] = SCALED ? J[i] * P.sat_isig[i] : J[i];
+            s[ro + KK_ROW_W + i] = SCALED ? acc * P.sat_sig[i] : acc;
         }
-        s[ro + 14 + KK_NB] = jb * P.btn_minv;
+        s[ro + KK_ROW_J + KK_NB] = jb; s[ro + KK_ROW_W + KK_NB] = jb * P.btn_minv;
+        s[ro + KK_ROW_J + KK_NB + 1] = jb2; s[ro + KK_ROW_W + KK_NB + 1] = jb2 * P.btn_minv;
         D = fmaf(jb, jb * P.btn_minv, D);
-        if (TWOB) { s[ro + 14 + ND - 1] = jb2 * P.btn_minv; D = fmaf(jb2, jb2 * P.btn_minv, D); }
-        s[ro + 28] = 1.0f / D;
+        if (TWOB) D = fmaf(jb2, jb2 * P.btn_minv, D);
+        s[ro + KK_ROW_INVD] = 1.0f / D;
         const float pen = s[co + 2];
-        s[ro + 29] = r < nc ? (pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt) : 0.f;
+        s[ro + KK_ROW_TGT] = (r < nc ? (pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt) : 0.f) - off;
     }
 }
 

@@ -37,13 +37,6 @@
 #ifndef KK_SWEEP_UNROLL
 #define KK_SWEEP_UNROLL 1
 #endif
-// Saturating form of the fast sweep (round 2): the motor impulses are carried as lam' = (lam + max_imp) / (2 max_imp) in [0, 1], so the
-// projection onto [-max_imp, +max_imp] is the .SAT modifier of the FFMA that produces the new impulse -- the two FMNMX leave the sweep and the
-// loop-carried path of a row shrinks from FFMA -> FMNMX -> FMNMX -> FADD (18 cycles) to FFMA.SAT -> FADD (8).  The residual velocities are carried
-// as r'_j = sigma_j (v_j - target_j) and M^-1 as sigma_i sigma_j A_ij (sigma = 2 max_imp), which keeps the matrix symmetric (78 registers).
-#ifndef KK_SWEEP_SAT
-#define KK_SWEEP_SAT 1
-#endif
 // a second copy of the sweep loop without the contact watch, taken when no lane of the warp has a contact row to watch
 #ifndef KK_SWEEP_TIGHT
 #define KK_SWEEP_TIGHT 1
@@ -52,17 +45,12 @@
 #ifndef KK_TIGHT_UNROLL
 #define KK_TIGHT_UNROLL 1
 #endif
-// fold the previous row's contribution into the impulse update (shorter loop-carried path, one more FFMA per row) or not: with the FFMA.SAT
-// clamp the plain form is already issue-bound (B200, 4096 envs x 128 steps: 5.07 ms against 5.15 ms deferred; profiles/r02_ab_kuka_sweep.txt)
-#ifndef KK_SWEEP_DEFER
-#define KK_SWEEP_DEFER 0
-#endif
-// lam += d in place instead of lam = s (one FADD on the FMA pipe per row instead of a half-rate MOV at the loop end)
-#ifndef KK_SWEEP_LAM_ACC
-#define KK_SWEEP_LAM_ACC 1
-#endif
+// Measured and dropped (profiles/r02_ab_kuka_sweep.txt): folding the previous row's contribution into the impulse update ("deferred" form:
+// shorter loop-carried path, one more FFMA per row -- 5.15 ms against 5.07 ms, the saturating form is already issue-bound), and the
+// unscaled sweep with FMNMX clamps (round 1's form).
 
 struct f3 { float x, y, z; };
+struct alignas(16) kk_f4 { float x, y, z, w; };   // one 128-bit load (host-compilable stand-in for float4)
 KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 KK_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 KK_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -778,18 +766,28 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         if ((P.upper[i] - e.q[i]) <= P.lim_eps) lim_hi_mask |= 1u << i;
         lim_lam_lo[i] = 0.f; lim_lam_hi[i] = 0.f;
     }
-    // ---- contact rows: J, W = M^-1 J^T, 1/D, target; two friction rows each (rare path, local memory) ----
+    // ---- the SCALED system the sweeps run on (round 2): impulses as lam' = (lam + max_imp) / sigma in [0, 1] with sigma = 2 max_imp, residuals
+    //      as v'_j = sigma_j (v_j - target_j), M^-1 as sigma_i sigma_j A_ij (symmetric: 78 registers).  The projection of a motor impulse onto
+    //      [-max_imp, +max_imp] is then the .SAT modifier of the FFMA that produces it: the loop-carried path of a row is FFMA.SAT -> FADD (8
+    //      cycles) instead of FFMA -> FMNMX -> FMNMX -> FADD (18).  The button DoF (KK_NB, and ND - 1 of the second button) stay unscaled. ----
+    float cs[KK_NB];
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) {
+        cs[i] = invd[i] * P.sat_isig2[i];                  // 1 / (sigma_i^2 A_ii)
+        v[i] = (v[i] - tgt[i]) * P.sat_sig[i];
+        lam[i] = 0.5f;                                     // lam = 0
+    }
+    // ---- contact rows: J, W = M^-1 J^T (unscaled A), 1/D, target; two friction rows each.  Stored for the scaled system:
+    //      J'_j = J_j / sigma_j and W'_j = sigma_j W_j on the 12 arm DoF, target' = target - J . tgt.  One row = KK_ROWW words: J'[0..13],
+    //      1/D, target', W'[16..29] -- 16-byte groups, so that a row is eight 128-bit loads from the scratch area (COOP) or local memory. ----
     const int nc = COOP ? nc_coop : ct.n;
-    float cJ[COOP ? 1 : 3 * KK_MAXC][ND], cW[COOP ? 1 : 3 * KK_MAXC][ND], c_invd[COOP ? 1 : 3 * KK_MAXC], c_tgt[COOP ? 1 : 3 * KK_MAXC], c_lam[3 * KK_MAXC];
-#define KK_CJ(r, j) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + (j)] : cJ[COOP ? 0 : (r)][j])
-#define KK_CW(r, j) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 14 + (j)] : cW[COOP ? 0 : (r)][j])
-#define KK_CINVD(r) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 28] : c_invd[COOP ? 0 : (r)])
-#define KK_CTGT(r) (COOP ? sc[KC_OFF_ROWS + (r) * KC_RS + 29] : c_tgt[COOP ? 0 : (r)])
+    alignas(16) float cR[COOP ? 1 : 3 * KK_MAXC][KK_ROWW];
+    float c_lam[3 * KK_MAXC];
     if constexpr (COOP) {
         if (nc > 0) {           // rows dealt to the 4 lanes, through the scratch area
 #if defined(__CUDACC__)
             __syncwarp(gmask);
-            kc_ph_rows<TWOB>(sc, P, A, nc, u);
+            kc_ph_rows<TWOB, true>(sc, P, A, nc, u, tgt);
             __syncwarp(gmask);
 #endif
             for (int r = 0; r < 3 * nc; ++r) c_lam[r] = 0.f;
@@ -812,32 +810,55 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 dir = ((r - nc) & 1) ? t2 : t1;
             }
             const int body = ct.body[c];
+            float J[KK_NB];
 #pragma unroll
             for (int j = 0; j < KK_NB; ++j) {
                 const bool anc = (j == body) || (j <= 7 && j < body) || (j == 8 && body == 9) || (j == 10 && body == 11);
-                cJ[r][j] = anc ? dot3(dir, cross3(k.a[j], ct.pt[c] - k.p[j])) : 0.f;
+                J[j] = anc ? dot3(dir, cross3(k.a[j], ct.pt[c] - k.p[j])) : 0.f;
             }
-            cJ[r][KK_NB] = ct.shape[c] == 1 ? -dir.z : 0.f;
-            float D = 0.f;
+            float* row = cR[COOP ? 0 : r];
+            float D = 0.f, off = 0.f;
 #pragma unroll
             for (int i = 0; i < KK_NB; ++i) {
-                float s = 0.f;
+                float w = 0.f;
 #pragma unroll
-                for (int j = 0; j < KK_NB; ++j) s = fmaf(KK_A(i, j), cJ[r][j], s);
-                cW[r][i] = s; D = fmaf(cJ[r][i], s, D);
+                for (int j = 0; j < KK_NB; ++j) w = fmaf(KK_A(i, j), J[j], w);
+                D = fmaf(J[i], w, D); off = fmaf(J[i], tgt[i], off);
+                row[KK_ROW_J + i] = J[i] * P.sat_isig[i];
+                row[KK_ROW_W + i] = w * P.sat_sig[i];
             }
-            cW[r][KK_NB] = cJ[r][KK_NB] * P.btn_minv;
-            D = fmaf(cJ[r][KK_NB], cW[r][KK_NB], D);
-            if (TWOB) {
-                cJ[r][ND - 1] = ct.shape[c] == 3 ? -dir.z : 0.f;
-                cW[r][ND - 1] = cJ[r][ND - 1] * P.btn_minv;
-                D = fmaf(cJ[r][ND - 1], cW[r][ND - 1], D);
-            }
-            c_invd[r] = 1.0f / D;
+            const float jb = ct.shape[c] == 1 ? -dir.z : 0.f, jb2 = TWOB && ct.shape[c] == 3 ? -dir.z : 0.f;
+            row[KK_ROW_J + KK_NB] = jb; row[KK_ROW_W + KK_NB] = jb * P.btn_minv;
+            row[KK_ROW_J + KK_NB + 1] = jb2; row[KK_ROW_W + KK_NB + 1] = jb2 * P.btn_minv;
+            D = fmaf(jb, jb * P.btn_minv, D);
+            if (TWOB) D = fmaf(jb2, jb2 * P.btn_minv, D);
+            row[KK_ROW_INVD] = 1.0f / D;
             c_lam[r] = 0.f;
-            if (r < nc) { const float pen = ct.dist[c]; c_tgt[r] = pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt; }
-            else c_tgt[r] = 0.f;
+            const float pen = ct.dist[c];
+            row[KK_ROW_TGT] = (r < nc ? (pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt) : 0.f) - off;
         }
+    }
+    // the scaled matrix (after the rows: W = M^-1 J^T uses the unscaled one)
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) A[i][j] *= P.sat_ss[i * (i + 1) / 2 + j];
+    // J' . v of one stored row: four independent partial sums (the loop-carried path of a contact row is 4 FFMA + 2 FADD, not 14 FFMA)
+#define KK_ROW_PTR(r) (COOP ? &sc[KC_OFF_ROWS + (r) * KC_RS] : cR[COOP ? 0 : (r)])
+#define KK_ROW_LOAD4(dst, ptr, base)                                                                                   \
+    _Pragma("unroll")                                                                                                  \
+    for (int q4 = 0; q4 < 4; ++q4) {                                                                                   \
+        const kk_f4 t4 = *reinterpret_cast<const kk_f4*>((ptr) + (base) + 4 * q4);                                   \
+        dst[4 * q4] = t4.x; dst[4 * q4 + 1] = t4.y; dst[4 * q4 + 2] = t4.z; dst[4 * q4 + 3] = t4.w;                    \
+    }
+#define KK_ROW_DOT(Jr, out)                                                                                            \
+    {                                                                                                                  \
+        float p0 = Jr[0] * v[0], p1 = Jr[1] * v[1], p2 = Jr[2] * v[2], p3 = Jr[3] * v[3];                              \
+        p0 = fmaf(Jr[4], v[4], p0); p1 = fmaf(Jr[5], v[5], p1); p2 = fmaf(Jr[6], v[6], p2); p3 = fmaf(Jr[7], v[7], p3); \
+        p0 = fmaf(Jr[8], v[8], p0); p1 = fmaf(Jr[9], v[9], p1); p2 = fmaf(Jr[10], v[10], p2); p3 = fmaf(Jr[11], v[11], p3); \
+        p0 = fmaf(Jr[12], v[12], p0);                                                                                  \
+        if (TWOB) p1 = fmaf(Jr[13], v[ND - 1], p1);                                                                    \
+        out = (p0 + p1) + (p2 + p3);                                                                                   \
     }
     // ---- projected Gauss-Seidel: row order = motors (button first), limits (button first), contact normals, friction ----
     // Button rows are made branch-free: an inactive limit row gets the bound [0, 0] (an exact no-op).
@@ -856,59 +877,22 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         s2 = fminf(fmaxf(fmaf(b2l_hi_t + v[ND - 1], b_invd, b2l_hi_lam), 0.f), b2l_hi_hi);                             \
         v[ND - 1] = fmaf(-P.btn_minv, s2 - b2l_hi_lam, v[ND - 1]); b2l_hi_lam = s2;                                    \
     }
-    float mi[KK_NB];  // impulse bounds in vector registers: no uniform-register reloads inside the sweep
-#pragma unroll
-    for (int i = 0; i < KK_NB; ++i) asm volatile("mov.f32 %0, %1;" : "=f"(mi[i]) : "f"(P.maximp[i]));  // opaque copy: keeps ptxas from re-reading the constant bank
+    // one arm motor row of the scaled system + its update of the 12 residuals
+#define KK_MOTOR_ROWS()                                                                                                \
+    _Pragma("unroll")                                                                                                  \
+    for (int i = 0; i < KK_NB; ++i) {                                                                                  \
+        const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                                       \
+        const float d = s - lam[i];                                                                                    \
+        lam[i] += d;            /* in place: no register rename, no MOV at the loop end; equals s whenever s - lam is exact */ \
+        _Pragma("unroll")                                                                                              \
+        for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);                                              \
+    }
     int it0 = 0;                 // first sweep the general loop still has to do
-    bool resume_mid_sweep = false;  // the fast path already ran the motor + button rows of sweep it0
+    bool resume_mid_sweep = false;  // the fast loop already ran the motor + button rows of sweep it0
     if ((lim_lo_mask | lim_hi_mask) == 0u) {
-        // FAST PATH (no arm joint on a limit): straight-line sweep, registers only.  Contact rows of the manifold are
+        // FAST LOOP (no arm joint on a limit): straight-line sweep, registers only.  Contact rows of the manifold are
         // WATCHED: while every normal row is separating (lam = 0 and J v >= target) it and its friction rows are exact
         // no-ops; the first time one would activate, the solve continues in the general loop from that very row.
-        // The 12 motor rows have unit Jacobians and constant targets, so the loop carries the residuals r_i = v_i - target_i, and the
-        // previous row's contribution to r_i is folded into the impulse update algebraically,
-        //   lam_i - r_i / D_i  =  [lam_i - r'_i / D_i]  -  (A_{i,i-1} / D_i) * delta_{i-1},
-        // where r'_i lacks only the previous row's update (applied off the critical path afterwards).
-        float c_wt[KK_MAXC];     // contact watch thresholds against the residual velocities: c_tgt - J . target
-#if KK_SWEEP_SAT
-        // Saturating form: impulses as lam' = (lam + max_imp) / sigma in [0, 1] with sigma = 2 max_imp, residuals as sigma_j r_j, the matrix as
-        // sigma_i sigma_j A_ij (symmetric: 78 registers); the clamp is the .SAT of the FFMA on the loop-carried path (FFMA.SAT -> FADD per row).
-        float cs[KK_NB], kk[KK_NB];
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) A[i][j] *= P.sat_ss[i * (i + 1) / 2 + j];
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i) {
-            cs[i] = invd[i] * P.sat_isig2[i];                  // 1 / (sigma_i^2 A_ii)
-            kk[i] = i > 0 ? cs[i] * A[i][i - 1] : 0.f;
-            v[i] = (v[i] - tgt[i]) * P.sat_sig[i];
-            lam[i] = 0.5f;                                     // lam = 0
-        }
-        float cJw[KK_MAXC][ND];   // contact watch: Jacobian rows against the scaled residuals
-        for (int c = 0; c < nc; ++c) {
-            float off = 0.f;
-#pragma unroll
-            for (int j = 0; j < KK_NB; ++j) { off = fmaf(KK_CJ(c, j), tgt[j], off); cJw[c][j] = KK_CJ(c, j) * P.sat_isig[j]; }
-#pragma unroll
-            for (int j = KK_NB; j < ND; ++j) cJw[c][j] = KK_CJ(c, j);
-            c_wt[c] = KK_CTGT(c) - off;
-        }
-#define KK_WATCH_J(c, j) cJw[c][j]
-#else
-        float kk[KK_NB];
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i) kk[i] = i > 0 ? invd[i] * A[i][i - 1] : 0.f;
-        for (int c = 0; c < nc; ++c) {
-            float off = 0.f;
-#pragma unroll
-            for (int j = 0; j < KK_NB; ++j) off = fmaf(KK_CJ(c, j), tgt[j], off);
-            c_wt[c] = KK_CTGT(c) - off;
-        }
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i) v[i] -= tgt[i];
-#define KK_WATCH_J(c, j) KK_CJ(c, j)
-#endif
         // loop invariants of the button rows in vector registers (opaque copies: no uniform-register / constant-bank reloads inside the sweep)
         float bminv, nbminv, lo_hi, hi_hi, lo_t, hi_t;
         asm volatile("mov.f32 %0, %1;" : "=f"(bminv) : "f"(P.btn_minv));
@@ -921,36 +905,6 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         bool more = true;
         int it = 0;
         // one sweep over the button rows and the 12 motor rows
-#if KK_SWEEP_SAT
-#if KK_SWEEP_DEFER
-#define KK_ROW(i)                                                                                                        \
-                    float s;                                                                                             \
-                    if (i == 0) s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                             \
-                    else {                                                                                               \
-                        const float e = fmaf(-cs[i], v[i], lam[i]);   /* off the critical path (v[i] lacks row i-1's update) */ \
-                        s = __saturatef(fmaf(-kk[i], dprev, e));      /* critical path: FFMA.SAT */                      \
-                        v[i] = fmaf(A[i][i - 1], dprev, v[i]);        /* deferred update from row i-1 */                 \
-                    }                                                                                                    \
-                    const float d = s - lam[i];                                                                          \
-                    if (KK_SWEEP_LAM_ACC) lam[i] += d; else lam[i] = s;   /* in place: no register rename, no MOV at the loop end; equals s whenever s - lam is exact */
-#define KK_ROW_SKIP(i, j) ((j) == (i) + 1)
-#else
-#define KK_ROW(i)                                                                                                        \
-                    const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                             \
-                    const float d = s - lam[i];                                                                          \
-                    if (KK_SWEEP_LAM_ACC) lam[i] += d; else lam[i] = s;
-#define KK_ROW_SKIP(i, j) false
-#endif
-#else
-#define KK_ROW(i)                                                                                                        \
-                    const float e = fmaf(-invd[i], v[i], lam[i]);                  /* v[i] holds v_i - target_i */       \
-                    const float sraw = i > 0 ? fmaf(-kk[i], dprev, e) : e;        /* critical path */                   \
-                    if (i > 0) v[i] = fmaf(A[i][i - 1], dprev, v[i]);             /* deferred update from row i-1 */    \
-                    const float s = fminf(fmaxf(sraw, -mi[i]), mi[i]);                                                   \
-                    const float d = s - lam[i];                                                                          \
-                    lam[i] = s;
-#define KK_ROW_SKIP(i, j) ((j) == (i) + 1)
-#endif
 #define KK_SWEEP_BODY()                                                                                                  \
                 {   /* button motor + the two limit rows (an independent 1-DoF chain, fills issue slots) */              \
                     float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);                          \
@@ -961,15 +915,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                     v[KK_NB] = fmaf(nbminv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;                                     \
                 }                                                                                                        \
                 KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()                                                                   \
-                float dprev = 0.f;                                                                                       \
-                _Pragma("unroll")                                                                                        \
-                for (int i = 0; i < KK_NB; ++i) {                                                                        \
-                    KK_ROW(i)                                                                                            \
-                    _Pragma("unroll")                                                                                    \
-                    for (int j = 0; j < KK_NB; ++j)                                                                      \
-                        if (!KK_ROW_SKIP(i, j)) v[j] = fmaf(KK_A(j, i), d, v[j]);   /* v[i+1] is updated by the next row when deferred */ \
-                    dprev = d;                                                                                           \
-                }
+                KK_MOTOR_ROWS()
         if (P.iters > 0) {
             int left = P.iters;
             asm volatile("mov.u32 %0, %0;" : "+r"(left));
@@ -983,23 +929,23 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             if (quiet) {
                 constexpr int tight_unroll = KK_TIGHT_UNROLL;
 #pragma unroll tight_unroll
-                do { KK_SWEEP_BODY() (void)dprev; } while (--left > 0);
+                do { KK_SWEEP_BODY() } while (--left > 0);
                 it = P.iters;
             } else {
                 constexpr int sweep_unroll = KK_SWEEP_UNROLL;
 #pragma unroll sweep_unroll
                 do {
                     KK_SWEEP_BODY()
-                    (void)dprev;
                     ++it;
                     more = --left > 0;
                     if (nc > 0) {
 #pragma unroll 1
                         for (int c = 0; c < nc; ++c) {
-                            float jv = 0.f;
-#pragma unroll
-                            for (int j = 0; j < ND; ++j) jv = fmaf(KK_WATCH_J(c, j), v[j], jv);
-                            act = act | (c_wt[c] - jv > 0.f);
+                            const float* row = KK_ROW_PTR(c);
+                            float Jr[16], jv;
+                            KK_ROW_LOAD4(Jr, row, KK_ROW_J)
+                            KK_ROW_DOT(Jr, jv)
+                            act = act | (Jr[KK_ROW_TGT] - jv > 0.f);
                         }
                         if (act) more = false;
                     }
@@ -1007,29 +953,10 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             }
         }
 #undef KK_SWEEP_BODY
-#undef KK_ROW
-#undef KK_ROW_SKIP
         if (act) { it0 = it - 1; resume_mid_sweep = true; } else it0 = it;
-#undef KK_WATCH_J
-#if KK_SWEEP_SAT
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i) {           // back to velocities and impulses
-            v[i] = fmaf(v[i], P.sat_isig[i], tgt[i]);
-            lam[i] = fmaf(lam[i], P.sat_sig[i], -mi[i]);
-        }
-        if (it0 < P.iters) {                        // the general loop continues with the unscaled matrix (rare: a contact activated)
-#pragma unroll
-            for (int i = 0; i < KK_NB; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) A[i][j] *= P.sat_iss[i * (i + 1) / 2 + j];
-        }
-#else
-#pragma unroll
-        for (int i = 0; i < KK_NB; ++i) v[i] += tgt[i];
-#endif
     }
     if (it0 < P.iters) {
-        // GENERAL PATH (a joint on its limit and / or an active contact): same row order, plain form.
+        // GENERAL LOOP (a joint on its limit and / or an active contact): same row order, same scaled system.
 #pragma unroll 1
         for (int it = it0; it < P.iters; ++it) {
             if (!resume_mid_sweep) {
@@ -1038,14 +965,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 v[KK_NB] = fmaf(P.btn_minv, s - b_lam, v[KK_NB]); b_lam = s;
             }
             KK_BUTTON2_MOTOR()
-#pragma unroll
-            for (int i = 0; i < KK_NB; ++i) {  // arm motors: unit Jacobian, W = A[:, i]
-                const float s = fminf(fmaxf(fmaf(tgt[i] - v[i], invd[i], lam[i]), -mi[i]), mi[i]);
-                const float d = s - lam[i];
-                lam[i] = s;
-#pragma unroll
-                for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
-            }
+            KK_MOTOR_ROWS()
             {   // button limits
                 float s = fminf(fmaxf(fmaf(bl_lo_t - v[KK_NB], b_invd, bl_lo_lam), 0.f), bl_lo_hi);
                 v[KK_NB] = fmaf(P.btn_minv, s - bl_lo_lam, v[KK_NB]); bl_lo_lam = s;
@@ -1056,42 +976,55 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             }
             resume_mid_sweep = false;
             if (lim_lo_mask | lim_hi_mask) {
+                // arm joint limits, J = +-e_i.  In the scaled variables v_i = v'_i / sigma_i + tgt_i, and an impulse step d moves the residuals
+                // by sigma_j A_ji d = A'_ji (d / sigma_i).
 #pragma unroll
                 for (int i = 0; i < KK_NB; ++i) {
                     if (lim_lo_mask & (1u << i)) {  // J = +e_i
                         const float t = -P.erp * (e.q[i] - P.lower[i]) * P.inv_dt;
-                        const float s = fminf(fmaxf(fmaf(t - v[i], invd[i], lim_lam_lo[i]), 0.f), P.lim_maximp);
-                        const float d = s - lim_lam_lo[i]; lim_lam_lo[i] = s;
+                        const float s = fminf(fmaxf(fmaf(-invd[i] * P.sat_isig[i], v[i], fmaf(t - tgt[i], invd[i], lim_lam_lo[i])), 0.f), P.lim_maximp);
+                        const float d = (s - lim_lam_lo[i]) * P.sat_isig[i]; lim_lam_lo[i] = s;
 #pragma unroll
                         for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);
                     }
                     if (lim_hi_mask & (1u << i)) {  // J = -e_i
                         const float t = -P.erp * (P.upper[i] - e.q[i]) * P.inv_dt;
-                        const float s = fminf(fmaxf(fmaf(t + v[i], invd[i], lim_lam_hi[i]), 0.f), P.lim_maximp);
-                        const float d = s - lim_lam_hi[i]; lim_lam_hi[i] = s;
+                        const float s = fminf(fmaxf(fmaf(invd[i] * P.sat_isig[i], v[i], fmaf(t + tgt[i], invd[i], lim_lam_hi[i])), 0.f), P.lim_maximp);
+                        const float d = (s - lim_lam_hi[i]) * P.sat_isig[i]; lim_lam_hi[i] = s;
 #pragma unroll
                         for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(-KK_A(j, i), d, v[j]);
                     }
                 }
             }
+#pragma unroll 1
             for (int r = 0; r < 3 * nc; ++r) {
                 float lo = 0.f, hi = 1e10f;
                 if (r >= nc) {
                     hi = P.mu * c_lam[(r - nc) >> 1]; lo = -hi;
                     if (hi == 0.f && c_lam[r] == 0.f) continue;  // friction under a zero normal impulse: bounds [0, 0], an exact no-op
                 }
-                float jv = 0.f;
-#pragma unroll
-                for (int j = 0; j < ND; ++j) jv = fmaf(KK_CJ(r, j), v[j], jv);
-                const float s = fminf(fmaxf(fmaf(KK_CTGT(r) - jv, KK_CINVD(r), c_lam[r]), lo), hi);
+                const float* row = KK_ROW_PTR(r);
+                float Jr[16], Wr[16], jv;
+                KK_ROW_LOAD4(Jr, row, KK_ROW_J)
+                KK_ROW_LOAD4(Wr, row, KK_ROW_W)
+                KK_ROW_DOT(Jr, jv)
+                const float s = fminf(fmaxf(fmaf(Jr[KK_ROW_TGT] - jv, Jr[KK_ROW_INVD], c_lam[r]), lo), hi);
                 const float d = s - c_lam[r];
                 if (d == 0.f) continue;       // inactive (separating) contact: nothing to apply
                 c_lam[r] = s;
 #pragma unroll
-                for (int j = 0; j < ND; ++j) v[j] = fmaf(KK_CW(r, j), d, v[j]);
+                for (int j = 0; j < KK_NB + 1; ++j) v[j] = fmaf(Wr[j], d, v[j]);
+                if (TWOB) v[ND - 1] = fmaf(Wr[KK_NB + 1], d, v[ND - 1]);
             }
         }
     }
+#undef KK_MOTOR_ROWS
+#undef KK_ROW_PTR
+#undef KK_ROW_LOAD4
+#undef KK_ROW_DOT
+    // back to velocities
+#pragma unroll
+    for (int i = 0; i < KK_NB; ++i) v[i] = fmaf(v[i], P.sat_isig[i], tgt[i]);
     // ---- semi-implicit Euler ----
 #pragma unroll
     for (int i = 0; i < KK_NB; ++i) { e.qd[i] = v[i]; e.q[i] = fmaf(P.dt, v[i], e.q[i]); }

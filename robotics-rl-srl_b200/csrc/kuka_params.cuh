@@ -11,6 +11,12 @@
 #define KK_NB 12           // movable bodies: PyBullet joints 0-8, 10, 11, 13
 #define KK_ND 13           // + button glider
 #define KK_MAXC 4          // contact rows kept per step (KM_SC_MAX_CONTACTS)
+// one stored constraint row (contact normal / friction): J[14] at 0, 1 / D, target, W[14] at 16 -- 16-byte groups (eight 128-bit loads per row)
+#define KK_ROW_J 0
+#define KK_ROW_INVD 14
+#define KK_ROW_TGT 15
+#define KK_ROW_W 16
+#define KK_ROWW 32
 
 struct KukaParams {
     // ---- per body ----

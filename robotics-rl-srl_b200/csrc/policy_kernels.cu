@@ -8,8 +8,12 @@
 
 namespace {
 
-constexpr int POLICY_BLOCK = 64;     // 4096 envs -> 64 CTAs; one env per thread
 constexpr int H = SRL_POLICY_HIDDEN;
+constexpr int POLICY_LANES = 4;                   // lanes per env: lane u computes the outputs o = 4 j + u of every layer
+constexpr int POLICY_ENVS = 32;                   // envs per CTA -> 4096 envs = 128 CTAs of 128 threads (round 1: 64 CTAs of 64, one env per thread, 55 us)
+constexpr int POLICY_BLOCK = POLICY_ENVS * POLICY_LANES;
+constexpr int WS = H + 4;                         // padded row stride of the 64-wide rows: 16-byte aligned, and the 4 rows the lanes of an env read at
+                                                  // the same time (o, o + 1, o + 2, o + 3) start 4 banks apart -- LDS.128 without bank conflicts
 
 struct PolicyArgs {
     srl_mlp_policy p;
@@ -20,58 +24,163 @@ struct PolicyArgs {
     float* obs_buf; void* act_env; void* act_buf; float* logp; float* value;
 };
 
-// shared-memory layout (floats): the 16-byte aligned 64-wide rows first, then the small pieces, then the activation columns
-__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int count) {
-    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
+// Staging of the weights: every thread first ISSUES all of its global loads (registers), then stores them to shared memory -- one exposed
+// L2 latency for the whole set instead of one per array (a load -> store loop per array cost ~1 us each, 12 arrays).
+template <int PER>
+struct RowRegs { float4 v[PER]; };
+// 64-wide rows -> padded shared rows, 16 bytes per load; PER = ceil(rows * 16 / POLICY_BLOCK)
+template <int PER>
+__device__ __forceinline__ void rows_load(RowRegs<PER>& r, const float* __restrict__ src, int rows, bool vec) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * POLICY_BLOCK;
+        r.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < rows * (H / 4)) {
+            if (vec) r.v[k] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            else r.v[k] = make_float4(__ldg(src + 4 * i), __ldg(src + 4 * i + 1), __ldg(src + 4 * i + 2), __ldg(src + 4 * i + 3));   // a view at an odd offset
+        }
+    }
+}
+template <int PER>
+__device__ __forceinline__ void rows_store(const RowRegs<PER>& r, float* dst, int rows) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * POLICY_BLOCK;
+        if (i < rows * (H / 4)) *reinterpret_cast<float4*>(dst + (i >> 4) * WS + 4 * (i & 15)) = r.v[k];
+    }
+}
+template <int PER>
+struct VecRegs { float v[PER]; };
+template <int PER>
+__device__ __forceinline__ void vec_load(VecRegs<PER>& r, const float* __restrict__ src, int count) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * POLICY_BLOCK;
+        r.v[k] = i < count ? __ldg(src + i) : 0.f;
+    }
+}
+template <int PER>
+__device__ __forceinline__ void vec_store(const VecRegs<PER>& r, float* dst, int count) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * POLICY_BLOCK;
+        if (i < count) dst[i] = r.v[k];
+    }
+}
+
+struct TowerSmem { const float *w1, *b1, *w2, *b2, *w3, *b3; };
+
+__device__ __forceinline__ void load_column(const float* h, float (&a)[H]) {
+#pragma unroll
+    for (int i4 = 0; i4 < H / 4; ++i4) {
+        const float4 v = *reinterpret_cast<const float4*>(h + 4 * i4);
+        a[4 * i4] = v.x; a[4 * i4 + 1] = v.y; a[4 * i4 + 2] = v.z; a[4 * i4 + 3] = v.w;
+    }
+}
+// one padded 64-wide row against the activations: the four partial sums and their combination of policy_core.h's srl_mlp_tower
+__device__ __forceinline__ float dot_row(const float* row, const float (&a)[H], float bias) {
+    float s0 = bias, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i4 = 0; i4 < H / 4; ++i4) {
+        const float4 w = *reinterpret_cast<const float4*>(row + 4 * i4);
+        s0 = fmaf(w.x, a[4 * i4 + 0], s0); s1 = fmaf(w.y, a[4 * i4 + 1], s1);
+        s2 = fmaf(w.z, a[4 * i4 + 2], s2); s3 = fmaf(w.w, a[4 * i4 + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// One 64-64 tower of one env, computed by the 4 lanes of its group: same arithmetic, value by value, as srl_mlp_tower (policy_core.h).
+// `h` is the env's 64-float activation column in shared memory (every lane writes its 16 outputs, the group synchronises, every lane reads
+// all 64); `out` (shared, n_out floats) receives the last layer, output k from lane k % 4.  gmask = the group's 4 lanes.
+__device__ __forceinline__ void tower_4lanes(const TowerSmem& W, int D, int n_out, const float* x, float* h, float* out, int u, unsigned gmask) {
+#pragma unroll 4
+    for (int j = 0; j < H / POLICY_LANES; ++j) {            // layer 1: obs_dim -> 64
+        const int o = POLICY_LANES * j + u;
+        float acc = W.b1[o];
+        for (int d = 0; d < D; ++d) acc = fmaf(W.w1[o * D + d], x[d], acc);
+        h[o] = tanhf(acc);
+    }
+    __syncwarp(gmask);
+    float a[H];
+    load_column(h, a);
+    __syncwarp(gmask);                                       // everyone has read layer 1 before layer 2 overwrites the column
+#pragma unroll 2
+    for (int j = 0; j < H / POLICY_LANES; ++j) {            // layer 2: 64 -> 64
+        const int o = POLICY_LANES * j + u;
+        h[o] = tanhf(dot_row(W.w2 + o * WS, a, W.b2[o]));
+    }
+    __syncwarp(gmask);
+    load_column(h, a);
+    __syncwarp(gmask);
+    for (int k = u; k < n_out; k += POLICY_LANES) out[k] = dot_row(W.w3 + k * WS, a, W.b3[k]);   // layer 3: 64 -> n_out
+    __syncwarp(gmask);
 }
 
 __global__ void __launch_bounds__(POLICY_BLOCK) policy_act_kernel(const __grid_constant__ PolicyArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int D = a.p.obs_dim, A = a.p.n_out;
-    float* pi_w2 = smem;            float* vf_w2 = pi_w2 + H * H;
-    float* pi_w3 = vf_w2 + H * H;   float* vf_w3 = pi_w3 + SRL_POLICY_MAX_OUT * H;
-    float* pi_w1 = vf_w3 + H;       float* vf_w1 = pi_w1 + H * SRL_POLICY_MAX_OBS;
-    float* pi_b1 = vf_w1 + H * SRL_POLICY_MAX_OBS; float* vf_b1 = pi_b1 + H;
-    float* pi_b2 = vf_b1 + H;       float* vf_b2 = pi_b2 + H;
-    float* pi_b3 = vf_b2 + H;       float* vf_b3 = pi_b3 + SRL_POLICY_MAX_OUT;
-    float* s_logstd = vf_b3 + 4;    float* cols = s_logstd + SRL_POLICY_MAX_OUT;    // cols: H x POLICY_BLOCK, 16-byte aligned by construction
-    stage(pi_w2, a.p.pi_w2, H * H); stage(vf_w2, a.p.vf_w2, H * H);
-    stage(pi_w3, a.p.pi_w3, A * H); stage(vf_w3, a.p.vf_w3, H);
-    stage(pi_w1, a.p.pi_w1, H * D); stage(vf_w1, a.p.vf_w1, H * D);
-    stage(pi_b1, a.p.pi_b1, H); stage(vf_b1, a.p.vf_b1, H); stage(pi_b2, a.p.pi_b2, H); stage(vf_b2, a.p.vf_b2, H);
-    stage(pi_b3, a.p.pi_b3, A); stage(vf_b3, a.p.vf_b3, 1);
-    if (!a.p.discrete) stage(s_logstd, a.p.logstd, A);
+    float* pi_w2 = smem;                 float* vf_w2 = pi_w2 + H * WS;
+    float* pi_w3 = vf_w2 + H * WS;       float* vf_w3 = pi_w3 + SRL_POLICY_MAX_OUT * WS;
+    float* cols = vf_w3 + WS;            // [POLICY_ENVS][WS] activation columns (16-byte aligned, envs 4 banks apart)
+    float* pi_w1 = cols + POLICY_ENVS * WS;          float* vf_w1 = pi_w1 + H * SRL_POLICY_MAX_OBS;
+    float* pi_b1 = vf_w1 + H * SRL_POLICY_MAX_OBS;   float* vf_b1 = pi_b1 + H;
+    float* pi_b2 = vf_b1 + H;            float* vf_b2 = pi_b2 + H;
+    float* pi_b3 = vf_b2 + H;            float* vf_b3 = pi_b3 + SRL_POLICY_MAX_OUT;
+    float* s_logstd = vf_b3 + 4;         float* outs = s_logstd + SRL_POLICY_MAX_OUT;   // [POLICY_ENVS][SRL_POLICY_MAX_OUT + 1]: logits / mean, value
+    {
+        constexpr int W2PER = H * (H / 4) / POLICY_BLOCK, W3PER = (SRL_POLICY_MAX_OUT * (H / 4) + POLICY_BLOCK - 1) / POLICY_BLOCK;
+        constexpr int W1PER = (H * SRL_POLICY_MAX_OBS + POLICY_BLOCK - 1) / POLICY_BLOCK;
+        static_assert(H * (H / 4) % POLICY_BLOCK == 0 && H <= POLICY_BLOCK && SRL_POLICY_MAX_OUT <= POLICY_BLOCK, "staging shape");
+        const bool vec = ((reinterpret_cast<uintptr_t>(a.p.pi_w2) | reinterpret_cast<uintptr_t>(a.p.vf_w2) | reinterpret_cast<uintptr_t>(a.p.pi_w3) |
+                           reinterpret_cast<uintptr_t>(a.p.vf_w3)) & 15u) == 0;
+        RowRegs<W2PER> r_pw2, r_vw2; RowRegs<W3PER> r_pw3; RowRegs<1> r_vw3;
+        VecRegs<W1PER> r_pw1, r_vw1; VecRegs<1> r_pb1, r_vb1, r_pb2, r_vb2, r_pb3, r_vb3, r_ls;
+        rows_load(r_pw2, a.p.pi_w2, H, vec); rows_load(r_vw2, a.p.vf_w2, H, vec); rows_load(r_pw3, a.p.pi_w3, A, vec); rows_load(r_vw3, a.p.vf_w3, 1, vec);
+        vec_load(r_pw1, a.p.pi_w1, H * D); vec_load(r_vw1, a.p.vf_w1, H * D);
+        vec_load(r_pb1, a.p.pi_b1, H); vec_load(r_vb1, a.p.vf_b1, H); vec_load(r_pb2, a.p.pi_b2, H); vec_load(r_vb2, a.p.vf_b2, H);
+        vec_load(r_pb3, a.p.pi_b3, A); vec_load(r_vb3, a.p.vf_b3, 1);
+        vec_load(r_ls, a.p.discrete ? a.p.pi_b3 : a.p.logstd, a.p.discrete ? 0 : A);
+        rows_store(r_pw2, pi_w2, H); rows_store(r_vw2, vf_w2, H); rows_store(r_pw3, pi_w3, A); rows_store(r_vw3, vf_w3, 1);
+        vec_store(r_pw1, pi_w1, H * D); vec_store(r_vw1, vf_w1, H * D);
+        vec_store(r_pb1, pi_b1, H); vec_store(r_vb1, vf_b1, H); vec_store(r_pb2, pi_b2, H); vec_store(r_vb2, vf_b2, H);
+        vec_store(r_pb3, pi_b3, A); vec_store(r_vb3, vf_b3, 1);
+        vec_store(r_ls, s_logstd, a.p.discrete ? 0 : A);
+    }
     const unsigned long long seed = a.rng[0], counter = a.rng[1];    // read before this CTA arrives: the counter moves only after ALL CTAs arrived
     __syncthreads();
-    const int i = blockIdx.x * POLICY_BLOCK + threadIdx.x;
-    if (i < a.n) {
+    const int slot = threadIdx.x / POLICY_LANES, u = threadIdx.x % POLICY_LANES;
+    const int i = blockIdx.x * POLICY_ENVS + slot;
+    const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+    if (i < a.n) {                                           // the 4 lanes of a group agree on i: a group is in or out as a whole
         float x[SRL_POLICY_MAX_OBS];
-        for (int d = 0; d < D; ++d) {
-            x[d] = a.obs[(size_t)i * D + d];
-            if (a.obs_buf) a.obs_buf[(size_t)i * D + d] = x[d];
-        }
-        float* col = cols + threadIdx.x;
-        float out[SRL_POLICY_MAX_OUT], v[1];
-        const SrlTowerWeights Wpi = {pi_w1, pi_b1, pi_w2, pi_b2, pi_w3, pi_b3};
-        const SrlTowerWeights Wvf = {vf_w1, vf_b1, vf_w2, vf_b2, vf_w3, vf_b3};
-        srl_mlp_tower(Wpi, D, A, x, col, POLICY_BLOCK, out);
-        srl_mlp_tower(Wvf, D, 1, x, col, POLICY_BLOCK, v);
-        a.value[i] = v[0];
-        const unsigned long long env = a.env_offset + (unsigned long long)i;
-        float lp;
-        if (a.p.discrete) {
-            const int act = srl_sample_categorical(out, A, seed, env, (uint32_t)counter, &lp);
-            reinterpret_cast<int32_t*>(a.act_env)[i] = act;
-            if (a.act_buf) reinterpret_cast<long long*>(a.act_buf)[i] = (long long)act;
-        } else {
-            float smp[SRL_POLICY_MAX_OUT], clp[SRL_POLICY_MAX_OUT];
-            srl_sample_gaussian(out, s_logstd, A, seed, env, (uint32_t)counter, smp, clp, &lp);
-            for (int k = 0; k < A; ++k) {
-                reinterpret_cast<float*>(a.act_env)[(size_t)i * A + k] = clp[k];
-                if (a.act_buf) reinterpret_cast<float*>(a.act_buf)[(size_t)i * A + k] = smp[k];
+        for (int d = 0; d < D; ++d) x[d] = a.obs[(size_t)i * D + d];
+        if (a.obs_buf && u == 0) for (int d = 0; d < D; ++d) a.obs_buf[(size_t)i * D + d] = x[d];
+        float* col = cols + slot * WS;
+        float* out = outs + slot * (SRL_POLICY_MAX_OUT + 1);
+        const TowerSmem Wpi = {pi_w1, pi_b1, pi_w2, pi_b2, pi_w3, pi_b3};
+        const TowerSmem Wvf = {vf_w1, vf_b1, vf_w2, vf_b2, vf_w3, vf_b3};
+        tower_4lanes(Wpi, D, A, x, col, out, u, gmask);
+        tower_4lanes(Wvf, D, 1, x, col, out + SRL_POLICY_MAX_OUT, u, gmask);
+        if (u == 0) {                                        // the group's lead lane samples and stores
+            float lg[SRL_POLICY_MAX_OUT];
+            for (int k = 0; k < A; ++k) lg[k] = out[k];
+            a.value[i] = out[SRL_POLICY_MAX_OUT];
+            const unsigned long long env = a.env_offset + (unsigned long long)i;
+            float lp;
+            if (a.p.discrete) {
+                const int act = srl_sample_categorical(lg, A, seed, env, (uint32_t)counter, &lp);
+                reinterpret_cast<int32_t*>(a.act_env)[i] = act;
+                if (a.act_buf) reinterpret_cast<long long*>(a.act_buf)[i] = (long long)act;
+            } else {
+                float smp[SRL_POLICY_MAX_OUT], clp[SRL_POLICY_MAX_OUT];
+                srl_sample_gaussian(lg, s_logstd, A, seed, env, (uint32_t)counter, smp, clp, &lp);
+                for (int k = 0; k < A; ++k) {
+                    reinterpret_cast<float*>(a.act_env)[(size_t)i * A + k] = clp[k];
+                    if (a.act_buf) reinterpret_cast<float*>(a.act_buf)[(size_t)i * A + k] = smp[k];
+                }
             }
+            a.logp[i] = lp;
         }
-        a.logp[i] = lp;
     }
     // the LAST CTA to retire advances the step counter: every CTA has read it by then, and the next launch sees the new value
     __syncthreads();
@@ -150,8 +259,8 @@ __global__ void __launch_bounds__(FILTER_BLOCK) obs_filter_kernel(int n, int D, 
 }
 
 constexpr size_t policy_smem_bytes() {
-    return sizeof(float) * (size_t)(2 * H * H + SRL_POLICY_MAX_OUT * H + H + 2 * H * SRL_POLICY_MAX_OBS + 4 * H + SRL_POLICY_MAX_OUT + 4 +
-                                    SRL_POLICY_MAX_OUT + H * POLICY_BLOCK);
+    return sizeof(float) * (size_t)(2 * H * WS + SRL_POLICY_MAX_OUT * WS + WS + POLICY_ENVS * WS + 2 * H * SRL_POLICY_MAX_OBS + 4 * H + SRL_POLICY_MAX_OUT + 4 +
+                                    SRL_POLICY_MAX_OUT + POLICY_ENVS * (SRL_POLICY_MAX_OUT + 1));
 }
 
 }  // namespace
@@ -179,7 +288,7 @@ int srl_policy_act(const srl_mlp_policy* p, int n, const float* obs, uint64_t* r
     PolicyArgs a;
     a.p = *p; a.n = n; a.obs = obs; a.rng = reinterpret_cast<unsigned long long*>(rng); a.env_offset = env_offset;
     a.obs_buf = obs_buf; a.act_env = act_env; a.act_buf = act_buf; a.logp = logp; a.value = value;
-    policy_act_kernel<<<(n + POLICY_BLOCK - 1) / POLICY_BLOCK, POLICY_BLOCK, smem, (cudaStream_t)stream>>>(a);
+    policy_act_kernel<<<(n + POLICY_ENVS - 1) / POLICY_ENVS, POLICY_BLOCK, smem, (cudaStream_t)stream>>>(a);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -134,19 +134,19 @@ static void run_cases(const KukaParams& P0, int cases) {
             for (int j = 0; j <= i; ++j) cmp(4, "M^-1", A[i][j], Anew[i][j], 5e-3 * sqrt(fabs((double)A[i][i] * A[j][j])), 0.0);
         // ---- contact rows against a plain restatement ----
         if (nc > 0) {
-            KC_RUN((kc_ph_rows<TWOB>(s, P, Anew, nc, u)));
+            KC_RUN((kc_ph_rows<TWOB, false>(s, P, Anew, nc, u)));
             for (int r = 0; r < 3 * nc; ++r) {
                 const int ro = KC_OFF_ROWS + r * KC_RS;
                 double D = 0;
                 for (int i = 0; i < KK_NB; ++i) {
                     double w = 0;
                     for (int j = 0; j < KK_NB; ++j) w += (double)(i >= j ? Anew[i][j] : Anew[j][i]) * s[ro + j];
-                    cmp(5, "row W", w, s[ro + 14 + i], 1e-3 * (fabs(w) + sqrt(fabs((double)A[i][i]))), 0.0);
+                    cmp(5, "row W", w, s[ro + KK_ROW_W + i], 1e-3 * (fabs(w) + sqrt(fabs((double)A[i][i]))), 0.0);
                     D += w * s[ro + i];
                 }
                 D += (double)s[ro + KK_NB] * s[ro + KK_NB] * P.btn_minv;
                 if (TWOB) D += (double)s[ro + KK_NB + 1] * s[ro + KK_NB + 1] * P.btn_minv;
-                cmp(5, "row 1/D", 1.0 / D, s[ro + 28], 0.0, 2e-3);
+                cmp(5, "row 1/D", 1.0 / D, s[ro + KK_ROW_INVD], 0.0, 2e-3);
                 if (r < nc) {
                     // the normal row's Jacobian: n . (a_j x (pt - p_j)) for the ancestors of the contact body
                     const int c = r, body = ct.body[c];
@@ -156,7 +156,7 @@ static void run_cases(const KukaParams& P0, int cases) {
                         cmp(5, "row J", anc ? dot3(ct.nrm[c], lever) : 0.f, s[ro + j], 1e-5, 1e-4);
                     }
                     const float pen = ct.dist[c];
-                    cmp(5, "row target", pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt, s[ro + 29], 1e-3, 1e-4);
+                    cmp(5, "row target", pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt, s[ro + KK_ROW_TGT], 1e-3, 1e-4);
                 }
             }
         }
