@@ -21,6 +21,7 @@ rl_baselines/rl_algorithm/ppo2.py:58-72): a single kernel launch, 4096 x 128 env
                  mobile_config4   = configs[3], MobileRobotGymEnv-v0, 8192 envs/GPU, T = 1024 fused rollouts, at every N
                  plumbing_config1 = configs[0], MobileRobotGymEnv-v0, 4 env OBJECTS behind the reference-shaped
                                     (Dummy)VecEnv plumbing, random agent, 1600 steps (rank 0)
+                 render_kuka      = image observations: one srl_sim_render of 4096 Kuka frames, 224 x 224 (rank 0)
   --impl reference : the reference arm.  PyBullet is not installable here, so it times the oracle -- the CPU
           restatement of the reference's step -- with every host thread, on the same configs.
 """
@@ -363,6 +364,45 @@ def plumbing_config1(library, device, steps=1600, num_cpu=4, seed=0):
             "launches_per_env_step": 1, "note": "one N=1 simulator launch + one synchronising read-back per env object and step: Python / launch-latency bound"}
 
 
+def render_leg(be, n=4096, width=224, height=224, reps=10):
+    """Image observations: device time of one srl_sim_render of n Kuka frames (primitive lists, prepared primitives, raster:
+    3 launches), CUDA events, a 256 MB L2 flush between repetitions; the kernel is instruction-issue bound, so the roofline entry is the
+    byte floor of the output only (3 W H bytes per frame at the measured HBM peak)."""
+    import numpy as np
+    import torch
+    from srl_sim.model import load_kuka_scene
+    from srl_sim.render import KUKA_CAMERA, camera
+    st = be.stream()
+    sim = be.make_sim("KukaButtonGymEnv-v0", n, model_blob=load_kuka_scene().blob, seed=0, random_target=True)
+    sim.reset(stream=st)
+    T = 32
+    acts = torch.randint(0, 6, (T, n), dtype=torch.int32, device=be.torch_device)
+    o = be.zeros((T, n, 3), np.float32); r = be.zeros((T, n), np.float32); d = be.zeros((T, n), np.uint8)
+    sim.rollout(T, acts, None, o, r, d, stream=st)
+    buf = be.zeros((n, height, width, 3), np.uint8)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=be.torch_device)
+    cam = camera(**KUKA_CAMERA)
+    for _ in range(3):
+        sim.render(cam, width, height, buf, stream=st)
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream()); sim.render(cam, width, height, buf, stream=st); e1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
+    sim.close()
+    t = float(np.median(ms)) * 1e-3
+    out_bytes = 3 * width * height * n
+    peaks, src = _peaks()
+    hbm = float(peaks.get("hbm_gbs", 0.0) or 0.0) * 1e9
+    return {"metric": "frames/sec srl_sim_render KukaButtonGymEnv-v0 %dx%d @%d envs" % (width, height, n), "value": n / t, "unit": "frames/s",
+            "ms_per_call": t * 1e3, "gpu_launches_per_call": 3, "bytes_written_per_call": out_bytes,
+            "roofline": {"bound": "issue (ray / primitive arithmetic; profiles/r02_render_raster_ncu.txt: 80 % of the issue slots)",
+                         "hbm_floor_ms": (out_bytes / hbm * 1e3) if hbm else None, "hbm_frac": (out_bytes / t / hbm) if hbm else None, "peak_source": src},
+            "config": {"workload": "one 224 x 224 RGB frame per env through the env's fixed camera, analytic-primitive ray caster (DESIGN.md 5.3)",
+                       "l2": "256 MB flush between repetitions", "reps": reps}}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's own step on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -548,6 +588,10 @@ def run_b200(args):
             secondary["plumbing_config1"] = plumbing_config1(be.library, local_rank)
         except Exception as ex:      # never lose the headline line to the secondary leg
             secondary["plumbing_config1"] = {"error": repr(ex)}
+        try:
+            secondary["render_kuka"] = render_leg(be)
+        except Exception as ex:
+            secondary["render_kuka"] = {"error": repr(ex)}
     metric, config = metric_and_config(args.workload, world)
     line = {"metric": metric, "value": main["value"], "unit": "env-steps/s",
             "n_gpus": world, "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],

@@ -65,14 +65,15 @@ enum {
 #define KC_OFF_BIAS (KC_OFF_MA + KK_NB * KC_MS)    // [12] bias torques
 #define KC_OFF_ROWS (((KC_OFF_BIAS + KK_NB + 3) / 4) * 4)   // 3 * KK_MAXC constraint rows of KC_RS words in the KK_ROW_* layout (kuka_params.cuh), 16-byte aligned
 #define KC_RS 36                                   // = 4 (mod 32): the 4 lanes that fill 4 consecutive rows hit different banks; a multiple of 4 words
-#define KC_OFF_END (KC_OFF_ROWS + 3 * KK_MAXC * KC_RS)
+#define KC_OFF_WT (KC_OFF_ROWS + 3 * KK_MAXC * KC_RS)   // watch matrix [12][4]: Wt[i][c] = W'_i of normal row c (0 for c >= nc) -- one 128-bit load per motor row
+#define KC_OFF_END (KC_OFF_WT + KK_NB * 4)
 #define KC_OFF_CAND KC_OFF_MA                      // collision candidates per sphere (count, then KC_CANDS records of 8 words: shape, dist, n, pt):
 #define KC_CANDS 3                                 // consumed by the collect phase before the dynamics write M, L, rows -- same storage
 #define KC_CANDW (1 + KC_CANDS * 8)
 #define KC_WORDS KC_OFF_END
 #define KC_ROWS4 ((KC_WORDS + 3) / 4)              // 16-byte rows per env
 static_assert(KC_BS % 4 == 1 && KC_MS % 4 == 1 && KC_CS % 4 == 1, "lane-indexed strides must be odd (1 or 3 mod 4)");
-static_assert(KC_RS % 32 == 4 && KC_RS >= KK_ROWW && KC_OFF_ROWS % 4 == 0, "constraint rows: 16-byte aligned, consecutive rows 4 banks apart");
+static_assert(KC_RS % 32 == 4 && KC_RS >= KK_ROWW && KC_OFF_ROWS % 4 == 0 && KC_OFF_WT % 4 == 0 && KK_MAXC == 4, "constraint rows: 16-byte aligned, consecutive rows 4 banks apart");
 static_assert(KC_OFF_CAND + KM_MAX_SPHERES * KC_CANDW <= KC_OFF_END, "collision candidates must fit in the storage they share");
 
 // per-CTA constant tables (same for every env): body records of KC_CS words, then sphere records of 5 words
@@ -492,6 +493,7 @@ KC_F void kc_ph_rows(const S& s, const KukaParams& P, const float (&A)[KK_NB][KK
             if (SCALED) off = fmaf(J[i], tgt[i], off);
             s[ro + KK_ROW_J + i] = SCALED ? J[i] * P.sat_isig[i] : J[i];
             s[ro + KK_ROW_W + i] = SCALED ? acc * P.sat_sig[i] : acc;
+            if (SCALED && r < nc) s[KC_OFF_WT + 4 * i + r] = acc * P.sat_sig[i];     // the watch matrix column of this normal row
         }
         s[ro + KK_ROW_J + KK_NB] = jb; s[ro + KK_ROW_W + KK_NB] = jb * P.btn_minv;
         s[ro + KK_ROW_J + KK_NB + 1] = jb2; s[ro + KK_ROW_W + KK_NB + 1] = jb2 * P.btn_minv;
@@ -500,6 +502,10 @@ KC_F void kc_ph_rows(const S& s, const KukaParams& P, const float (&A)[KK_NB][KK
         s[ro + KK_ROW_INVD] = 1.0f / D;
         const float pen = s[co + 2];
         s[ro + KK_ROW_TGT] = (r < nc ? (pen > 0.f ? -pen * P.inv_dt : -P.erp * pen * P.inv_dt) : 0.f) - off;
+    }
+    if (SCALED && u >= nc) {             // watch matrix columns without a contact: zeros (lane u owns column u; columns < nc were written with row u above)
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) s[KC_OFF_WT + 4 * i + u] = 0.f;
     }
 }
 

@@ -669,7 +669,7 @@ KK_DEV void kuka_spd_inverse(float (&M)[KK_NB][KK_NB]) {
 struct KkNoScratch { float dummy; KK_DEV float& operator[](int) const { return const_cast<float&>(dummy); } };
 template <bool JOINTS, bool TWOB, bool COOP = false, class SC = KkNoScratch>
 KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k, const KukaContacts& ct, bool button_armed, const float* q_joints,
-                              const SC& sc = SC(), int u = 0, unsigned gmask = 0u, int nc_coop = 0) {
+                              const SC& sc = SC(), int u = 0, unsigned gmask = 0u, int nc_coop = 0, unsigned* dbg = nullptr) {
     constexpr int ND = TWOB ? KK_NB + 2 : KK_NB + 1;
     // ---- applyAction: IK + motor set-points (kuka.py:142-187) ----
     float q_ik[7];
@@ -782,6 +782,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
     //      1/D, target', W'[16..29] -- 16-byte groups, so that a row is eight 128-bit loads from the scratch area (COOP) or local memory. ----
     const int nc = COOP ? nc_coop : ct.n;
     alignas(16) float cR[COOP ? 1 : 3 * KK_MAXC][KK_ROWW];
+    alignas(16) float cWt[COOP ? 1 : KK_NB][4];            // watch matrix (thread-per-env layout): cWt[i][c] = W'_i of normal row c, 0 for c >= nc
     float c_lam[3 * KK_MAXC];
     if constexpr (COOP) {
         if (nc > 0) {           // rows dealt to the 4 lanes, through the scratch area
@@ -794,6 +795,8 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         }
     } else
     if (nc > 0) {
+#pragma unroll
+        for (int i = 0; i < KK_NB; ++i) { cWt[COOP ? 0 : i][0] = 0.f; cWt[COOP ? 0 : i][1] = 0.f; cWt[COOP ? 0 : i][2] = 0.f; cWt[COOP ? 0 : i][3] = 0.f; }
         for (int r = 0; r < 3 * nc; ++r) {
             const int c = r < nc ? r : (r - nc) >> 1;
             f3 dir = ct.nrm[c];
@@ -826,6 +829,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 D = fmaf(J[i], w, D); off = fmaf(J[i], tgt[i], off);
                 row[KK_ROW_J + i] = J[i] * P.sat_isig[i];
                 row[KK_ROW_W + i] = w * P.sat_sig[i];
+                if (r < nc) cWt[COOP ? 0 : i][r] = w * P.sat_sig[i];
             }
             const float jb = ct.shape[c] == 1 ? -dir.z : 0.f, jb2 = TWOB && ct.shape[c] == 3 ? -dir.z : 0.f;
             row[KK_ROW_J + KK_NB] = jb; row[KK_ROW_W + KK_NB] = jb * P.btn_minv;
@@ -887,6 +891,21 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         _Pragma("unroll")                                                                                              \
         for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);                                              \
     }
+    // the same with the contact watch folded in: J'_c . v' of the (up to 4) watched normal rows is carried incrementally -- a motor row's step d
+    // moves it by W'_ci d (W' = A' J'^T: the column the general loop would apply) -- as 4 independent FFMA per row off the loop-carried path,
+    // fed by one 128-bit load of the watch matrix; recomputing the 14-term dot per contact after every sweep cost ~100 cycles per contact and
+    // sweep on the single resident warp (profiles/r02_lockstep_slot_timing_before.txt: 66 / 75 / 82 / 90 us per step with 1 / 2 / 3 / 4 contacts, 49 without)
+#define KK_MOTOR_ROWS_WATCH()                                                                                          \
+    _Pragma("unroll")                                                                                                  \
+    for (int i = 0; i < KK_NB; ++i) {                                                                                  \
+        const kk_f4 w4 = *reinterpret_cast<const kk_f4*>(wt + 4 * i);                                                  \
+        const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                                       \
+        const float d = s - lam[i];                                                                                    \
+        lam[i] += d;                                                                                                   \
+        _Pragma("unroll")                                                                                              \
+        for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);                                              \
+        wjv[0] = fmaf(w4.x, d, wjv[0]); wjv[1] = fmaf(w4.y, d, wjv[1]); wjv[2] = fmaf(w4.z, d, wjv[2]); wjv[3] = fmaf(w4.w, d, wjv[3]); \
+    }
     int it0 = 0;                 // first sweep the general loop still has to do
     bool resume_mid_sweep = false;  // the fast loop already ran the motor + button rows of sweep it0
     if ((lim_lo_mask | lim_hi_mask) == 0u) {
@@ -905,7 +924,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         bool more = true;
         int it = 0;
         // one sweep over the button rows and the 12 motor rows
-#define KK_SWEEP_BODY()                                                                                                  \
+#define KK_SWEEP_BUTTONS()                                                                                               \
                 {   /* button motor + the two limit rows (an independent 1-DoF chain, fills issue slots) */              \
                     float s = fminf(fmaxf(fmaf(b_tgt - v[KK_NB], b_invd, b_lam), -b_hi), b_hi);                          \
                     v[KK_NB] = fmaf(bminv, s - b_lam, v[KK_NB]); b_lam = s;                                              \
@@ -914,14 +933,13 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                     s = fminf(fmaxf(fmaf(hi_t + v[KK_NB], b_invd, bl_hi_lam), 0.f), hi_hi);                              \
                     v[KK_NB] = fmaf(nbminv, s - bl_hi_lam, v[KK_NB]); bl_hi_lam = s;                                     \
                 }                                                                                                        \
-                KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()                                                                   \
-                KK_MOTOR_ROWS()
+                KK_BUTTON2_MOTOR() KK_BUTTON2_LIMITS()
         if (P.iters > 0) {
             int left = P.iters;
             asm volatile("mov.u32 %0, %0;" : "+r"(left));
 #if defined(__CUDA_ARCH__) && KK_SWEEP_TIGHT
             // 93 % of the warp-sweeps watch no contact in ANY lane (profiles/r02): those run a loop that is nothing but the rows and one
-            // back edge (the watch's reconvergence scaffolding cost ~40 cycles per sweep).  Warp-uniform choice: no divergence.
+            // back edge.  Warp-uniform choice: no divergence.
             const bool quiet = __all_sync(__activemask(), nc == 0);
 #else
             const bool quiet = false;
@@ -929,32 +947,65 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             if (quiet) {
                 constexpr int tight_unroll = KK_TIGHT_UNROLL;
 #pragma unroll tight_unroll
-                do { KK_SWEEP_BODY() } while (--left > 0);
+                do { KK_SWEEP_BUTTONS() KK_MOTOR_ROWS() } while (--left > 0);
                 it = P.iters;
             } else {
+                // watched normal rows c < nc (slots c >= nc: zero column, threshold -inf -- they never fire): arm part of J' . v' carried in
+                // wjv, the button DoF added when the row is tested
+                const float* wt = COOP ? &sc[KC_OFF_WT] : &cWt[0][0];
+                float wjv[4], wthr[4], wjb[4], wjb2[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    wjv[c] = 0.f; wthr[c] = -1e30f; wjb[c] = 0.f; wjb2[c] = 0.f;
+                    if (c < nc) {
+                        const float* row = KK_ROW_PTR(c);
+                        float Jr[16];
+                        KK_ROW_LOAD4(Jr, row, KK_ROW_J)
+                        float p0 = Jr[0] * v[0], p1 = Jr[1] * v[1], p2 = Jr[2] * v[2], p3 = Jr[3] * v[3];
+                        p0 = fmaf(Jr[4], v[4], p0); p1 = fmaf(Jr[5], v[5], p1); p2 = fmaf(Jr[6], v[6], p2); p3 = fmaf(Jr[7], v[7], p3);
+                        p0 = fmaf(Jr[8], v[8], p0); p1 = fmaf(Jr[9], v[9], p1); p2 = fmaf(Jr[10], v[10], p2); p3 = fmaf(Jr[11], v[11], p3);
+                        wjv[c] = (p0 + p1) + (p2 + p3);
+                        wthr[c] = Jr[KK_ROW_TGT]; wjb[c] = Jr[KK_NB]; wjb2[c] = Jr[KK_NB + 1];
+                    }
+                }
+                if (nc == 0) {           // a quiet env in a warp that watches: its watch matrix was not written this step
+                    if constexpr (COOP) {
+#pragma unroll
+                        for (int i = 0; i < KK_NB; ++i) sc[KC_OFF_WT + 4 * i + u] = 0.f;
+#if defined(__CUDACC__)
+                        __syncwarp(gmask);
+#endif
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < KK_NB; ++i) { cWt[COOP ? 0 : i][0] = 0.f; cWt[COOP ? 0 : i][1] = 0.f; cWt[COOP ? 0 : i][2] = 0.f; cWt[COOP ? 0 : i][3] = 0.f; }
+                    }
+                }
                 constexpr int sweep_unroll = KK_SWEEP_UNROLL;
 #pragma unroll sweep_unroll
                 do {
-                    KK_SWEEP_BODY()
+                    KK_SWEEP_BUTTONS()
+                    KK_MOTOR_ROWS_WATCH()
                     ++it;
                     more = --left > 0;
-                    if (nc > 0) {
-#pragma unroll 1
-                        for (int c = 0; c < nc; ++c) {
-                            const float* row = KK_ROW_PTR(c);
-                            float Jr[16], jv;
-                            KK_ROW_LOAD4(Jr, row, KK_ROW_J)
-                            KK_ROW_DOT(Jr, jv)
-                            act = act | (Jr[KK_ROW_TGT] - jv > 0.f);
-                        }
-                        if (act) more = false;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float jv = fmaf(wjb[c], v[KK_NB], wjv[c]);
+                        if (TWOB) jv = fmaf(wjb2[c], v[ND - 1], jv);
+                        act = act | (wthr[c] - jv > 0.f);
                     }
+                    if (act) more = false;
                 } while (more);
             }
         }
-#undef KK_SWEEP_BODY
+#undef KK_SWEEP_BUTTONS
         if (act) { it0 = it - 1; resume_mid_sweep = true; } else it0 = it;
+#ifdef KK_TIMING
+        if (dbg && nc > 0) *dbg |= 1u;
+#endif
     }
+#ifdef KK_TIMING
+    if (dbg) { *dbg |= ((unsigned)nc & 15u) << 2; if (lim_lo_mask | lim_hi_mask) *dbg |= 64u; if (it0 < P.iters) *dbg |= 2u | ((unsigned)(P.iters - it0) & 255u) << 8; }
+#endif
     if (it0 < P.iters) {
         // GENERAL LOOP (a joint on its limit and / or an active contact): same row order, same scaled system.
 #pragma unroll 1
@@ -1019,6 +1070,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         }
     }
 #undef KK_MOTOR_ROWS
+#undef KK_MOTOR_ROWS_WATCH
 #undef KK_ROW_PTR
 #undef KK_ROW_LOAD4
 #undef KK_ROW_DOT

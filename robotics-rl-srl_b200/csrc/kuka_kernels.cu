@@ -214,6 +214,15 @@ enum { KUKA_OP_ROLLOUT = 0, KUKA_OP_RESET = 1, KUKA_OP_SETTLE = 2, KUKA_OP_PREFE
 //   op = PREFETCH (PREFETCH instantiation only): reset() of the env's NEXT episode into its `nx` record, for the envs whose record is
 //                 not valid -- the very instructions of the in-launch reset, so a record and an in-launch reset agree bit for bit
 // PREFETCH = false (the default instantiations): `nx` is ignored and the kernel is what it was before the feature existed.
+#ifdef KK_TIMING
+// diagnostic build (scripts/build_variant.sh timing -DKK_TIMING): per env slot of the LAST launch, cycles from kernel entry to the slot's exit (high word)
+// and what its last physics step did (low word: 1 watched loop, 2 general loop, nc << 2, 64 joint limit, general sweeps << 8, 1 << 16 episode finished,
+// 1 << 17 record taken, 1 << 18 helper slot)
+__device__ unsigned long long kk_timing[1 << 16];
+#define KK_TIMING_RECORD() do { if (lead) kk_timing[(warp * (COOP ? 8 : 32) + slot) & 0xFFFF] = ((unsigned long long)(clock64() - kk_t0) << 32) | dbgf | (helper ? 1u << 18 : 0u); } while (0)
+#else
+#define KK_TIMING_RECORD() do { } while (0)
+#endif
 template <bool JOINTS, bool TWOB, bool PREFETCH = false, bool COOP = false>
 __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ KukaDev d, int n, int op, int T,
                                                        const void* __restrict__ actions, const float* __restrict__ noise,
@@ -225,6 +234,9 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     // lanes per env (COOP = true: kuka_coop.cuh; group g = lane / 4 carries env g, `epw` <= 8 live groups): all 4 lanes hold identical copies of
     // the env state and run the env logic and the sweeps redundantly; `u` = lane within the group deals out the once-per-step work.
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#ifdef KK_TIMING
+    const long long kk_t0 = clock64(); unsigned dbgf = 0u;
+#endif
     const int slot = COOP ? lane >> 2 : lane;            // env slot within the warp
     const int u = COOP ? lane & 3 : 0;
     const bool lead = !COOP || u == 0;                   // the lane of the group that talks to global memory
@@ -370,6 +382,9 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
             }
             }
             const bool is_done = e.terminated || e.counter > P.max_steps;  // _termination() (:422-426)
+#ifdef KK_TIMING
+            if (is_done) dbgf |= 1u << 16;
+#endif
             e.ep_ret += reward; e.ep_len += 1;
             if (rew && lead) rew[off] = reward;
             if (done && lead) done[off] = is_done ? 1 : 0;
@@ -388,6 +403,9 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
                             rec = reinterpret_cast<volatile const int32_t*>(nx.episode)[i] == (int)e.episode ? 2 : 1;
                         }
                         if (COOP) rec = __shfl_sync(gmask, rec, lane & ~3);
+#ifdef KK_TIMING
+                        if (rec == 2) dbgf |= 1u << 17;
+#endif
                         if (rec == 2) {
                             const uint32_t total_steps = e.total_steps;         // the only field that runs across episodes
                             env_load<TWOB, true>(nx, i, e);
@@ -510,7 +528,11 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
         // ---- applyAction + stepSimulation ----
         if (!JOINTS) apply_ee_delta(P, e, dx, dy, dz);
         saved_cb = new_cb; saved_ct = new_ct; saved_a0 = new_a0; saved_a1 = new_a1;
+#ifdef KK_TIMING
+        kuka_physics_step<JOINTS, TWOB, COOP>(P, e, k, ct, armed, qj, sc, u, gmask, nc_reg, &dbgf);
+#else
         kuka_physics_step<JOINTS, TWOB, COOP>(P, e, k, ct, armed, qj, sc, u, gmask, nc_reg);
+#endif
         if constexpr (PREFETCH) { if (helper && --budget <= 0 && reset_left > 0) { partial = true; break; } }
         if (!in_reset) {
             // step2()'s repeat loop (:349-354): stop repeating once terminated / past the step limit
@@ -520,6 +542,7 @@ __global__ void __launch_bounds__(128, 1) kuka_kernel(const __grid_constant__ Ku
     }
     e.cbutton = saved_cb; e.ctable = saved_ct;
     if (TWOB) { e.cany0 = saved_a0; e.cany1 = saved_a1; }
+    KK_TIMING_RECORD();
     if constexpr (PREFETCH) {
         if (op == KUKA_OP_PREFETCH) {
             if (!lead) return;
@@ -934,6 +957,12 @@ int kuka_get_state(srl_sim* s, int field, void* dst, size_t bytes) {
         for (size_t i = 0; i < N; ++i) { D[2 * i] = b[i].w; D[2 * i + 1] = (double)ia[i].z; }
         return 0;
     }
+#ifdef KK_TIMING
+    case 99: {   // diagnostic build: the per-slot timing words of the last launch
+        if (cudaMemcpyFromSymbol(dst, kk_timing, bytes < sizeof(kk_timing) ? bytes : sizeof(kk_timing)) != cudaSuccess) return 1;
+        return 0;
+    }
+#endif
     case SRL_F_NEXT_RECORD: {
         if (!need(3, 4)) return 1;
         const KukaNextHost* nh = static_cast<const KukaNextHost*>(s->kuka_next);

@@ -197,64 +197,81 @@ __global__ void __launch_bounds__(POLICY_BLOCK) policy_act_kernel(const __grid_c
 
 constexpr int FILTER_BLOCK = 1024;
 
-// One CTA: batch mean and (two-pass, biased) variance in float64, Chan's parallel-variance merge into the running state
-// (the update of stable-baselines' RunningMeanStd), then the normalisation of the whole batch in float32.
+// One CTA: batch mean and biased variance in float64, Chan's parallel-variance merge into the running state (the update of stable-baselines'
+// RunningMeanStd), then the normalisation of the whole batch in float32.  ONE pass over the batch: the sums S1 = sum(x - m0), S2 = sum((x - m0)^2)
+// are taken about the running mean m0 (known before the batch is read), so mean = m0 + S1 / n and var = S2 / n - (S1 / n)^2 lose nothing to
+// cancellation (|x - m0| is of the order of the standard deviation; float64 throughout: ~1e-13 of numpy's two-pass result at n = 4096), one
+// block reduction of 2 D values instead of two of D with a second read in between, the D state updates by D threads (round 2: 16.4 us ->
+// see profiles/r02_step_launch_timing.txt; every phase of this kernel is a latency, there is no throughput to speak of).
 __global__ void __launch_bounds__(FILTER_BLOCK) obs_filter_kernel(int n, int D, const float* __restrict__ obs, double* state, int update,
                                                                    float clip, float eps, float* __restrict__ out) {
-    __shared__ double red[32][SRL_POLICY_MAX_OBS];
-    __shared__ double s_mean[SRL_POLICY_MAX_OBS], s_bm[SRL_POLICY_MAX_OBS];
+    __shared__ double red[32][2 * SRL_POLICY_MAX_OBS];
+    __shared__ double s_sum[2 * SRL_POLICY_MAX_OBS];
     __shared__ float s_mf[SRL_POLICY_MAX_OBS], s_inv[SRL_POLICY_MAX_OBS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto block_sum = [&](double (&acc)[SRL_POLICY_MAX_OBS], double* result) {   // result[d] valid in every thread after the call
-        for (int d = 0; d < D; ++d) {
-            double v = acc[d];
+    if (update) {
+        double m0[SRL_POLICY_MAX_OBS], acc[2 * SRL_POLICY_MAX_OBS];
+        for (int d = 0; d < D; ++d) { m0[d] = state[d]; acc[d] = 0.0; acc[D + d] = 0.0; }
+        // the batch is read as a flat array, FILTER_BLOCK elements apart, four loads in flight per thread (a rolled loop of dependent
+        // load -> accumulate steps is one DRAM / L2 latency per step); element e belongs to dimension e % D
+        const int total_in = n * D;
+        for (int e0 = tid; e0 < total_in; e0 += 4 * FILTER_BLOCK) {
+            float x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int e = e0 + k * FILTER_BLOCK; x[k] = e < total_in ? obs[e] : 0.f; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = e0 + k * FILTER_BLOCK;
+                if (e < total_in) {
+                    const int d = e % D;
+                    double c = (double)x[k];
+                    for (int q = 0; q < D; ++q) if (q == d) { c -= m0[q]; acc[q] += c; acc[D + q] = fma(c, c, acc[D + q]); }
+                }
+            }
+        }
+        for (int q = 0; q < 2 * D; ++q) {
+            double v = acc[q];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp][d] = v;
+            if (lane == 0) red[warp][q] = v;
         }
         __syncthreads();
         if (warp == 0) {
-            for (int d = 0; d < D; ++d) {
-                double v = red[lane][d];
+            for (int q = 0; q < 2 * D; ++q) {
+                double v = red[lane][q];
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) result[d] = v;
+                if (lane == 0) s_sum[q] = v;
             }
         }
         __syncthreads();
-    };
-    if (update) {
-        double acc[SRL_POLICY_MAX_OBS];
-        for (int d = 0; d < D; ++d) acc[d] = 0.0;
-        for (int i = tid; i < n; i += FILTER_BLOCK)
-            for (int d = 0; d < D; ++d) acc[d] += (double)obs[(size_t)i * D + d];
-        block_sum(acc, s_bm);
-        double bm[SRL_POLICY_MAX_OBS];
-        for (int d = 0; d < D; ++d) { bm[d] = s_bm[d] / (double)n; acc[d] = 0.0; }
-        for (int i = tid; i < n; i += FILTER_BLOCK)
-            for (int d = 0; d < D; ++d) { const double c = (double)obs[(size_t)i * D + d] - bm[d]; acc[d] += c * c; }
-        __syncthreads();                         // every thread has read s_bm before block_sum overwrites the scratch it shares
-        block_sum(acc, s_mean);                  // s_mean temporarily holds the sums of squared deviations
-        if (tid == 0) {
+        if (tid < D) {
+            const int d = tid;
             const double count = state[2 * D], bc = (double)n, tot = count + bc;
-            for (int d = 0; d < D; ++d) {
-                const double bmean = s_bm[d] / bc, bvar = s_mean[d] / bc;
-                const double mean = state[d], var = state[D + d], delta = bmean - mean;
-                state[d] = mean + delta * bc / tot;
-                state[D + d] = (var * count + bvar * bc + delta * delta * count * bc / tot) / tot;
-            }
-            state[2 * D] = tot;
+            const double s1 = s_sum[d] / bc, bmean = state[d] + s1, bvar = s_sum[D + d] / bc - s1 * s1;
+            const double mean = state[d], var = state[D + d], delta = bmean - mean;
+            const double nm = mean + delta * bc / tot, nv = (var * count + bvar * bc + delta * delta * count * bc / tot) / tot;
+            state[d] = nm; state[D + d] = nv;
+            s_mf[d] = (float)nm; s_inv[d] = sqrtf((float)nv + eps);
         }
+        __syncthreads();                 // every thread d < D has read the count before thread 0 moves it
+        if (tid == 0) state[2 * D] += (double)n;
+    } else {
+        if (tid < D) { s_mf[tid] = (float)state[tid]; s_inv[tid] = sqrtf((float)state[D + tid] + eps); }
         __syncthreads();
     }
-    if (tid < D) {
-        s_mf[tid] = (float)state[tid];
-        s_inv[tid] = sqrtf((float)state[D + tid] + eps);
-    }
-    __syncthreads();
     const int total = n * D;
-    for (int e = tid; e < total; e += FILTER_BLOCK) {
-        const int d = e % D;
-        const float v = (obs[e] - s_mf[d]) / s_inv[d];
-        out[e] = fminf(fmaxf(v, -clip), clip);
+    for (int e0 = tid; e0 < total; e0 += 4 * FILTER_BLOCK) {
+        float x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int e = e0 + k * FILTER_BLOCK; x[k] = e < total ? obs[e] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = e0 + k * FILTER_BLOCK;
+            if (e < total) {
+                const int d = e % D;
+                const float v = (x[k] - s_mf[d]) / s_inv[d];
+                out[e] = fminf(fmaxf(v, -clip), clip);
+            }
+        }
     }
 }
 
