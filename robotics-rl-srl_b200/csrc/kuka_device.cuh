@@ -49,6 +49,13 @@
 // shorter loop-carried path, one more FFMA per row -- 5.15 ms against 5.07 ms, the saturating form is already issue-bound), and the
 // unscaled sweep with FMNMX clamps (round 1's form).
 
+#if defined(KK_TIMING)      // diagnostic build: first sweep in which no motor row moved (a fixed point of the fast loop)
+#define KK_PROBE_D(d) kk_probe_any |= ((d) != 0.f);
+#define KK_PROBE_SWEEP() { ++kk_probe_sweep; if (!kk_probe_any && !kk_probe_conv) kk_probe_conv = kk_probe_sweep; kk_probe_any = false; }
+#else
+#define KK_PROBE_D(d)
+#define KK_PROBE_SWEEP()
+#endif
 struct f3 { float x, y, z; };
 struct alignas(16) kk_f4 { float x, y, z, w; };   // one 128-bit load (host-compilable stand-in for float4)
 KK_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -888,6 +895,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                                       \
         const float d = s - lam[i];                                                                                    \
         lam[i] += d;            /* in place: no register rename, no MOV at the loop end; equals s whenever s - lam is exact */ \
+        KK_PROBE_D(d)                                                                                                  \
         _Pragma("unroll")                                                                                              \
         for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);                                              \
     }
@@ -902,11 +910,15 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
         const float s = __saturatef(fmaf(-cs[i], v[i], lam[i]));                                                       \
         const float d = s - lam[i];                                                                                    \
         lam[i] += d;                                                                                                   \
+        KK_PROBE_D(d)                                                                                                  \
         _Pragma("unroll")                                                                                              \
         for (int j = 0; j < KK_NB; ++j) v[j] = fmaf(KK_A(j, i), d, v[j]);                                              \
         wjv[0] = fmaf(w4.x, d, wjv[0]); wjv[1] = fmaf(w4.y, d, wjv[1]); wjv[2] = fmaf(w4.z, d, wjv[2]); wjv[3] = fmaf(w4.w, d, wjv[3]); \
     }
     int it0 = 0;                 // first sweep the general loop still has to do
+#if defined(KK_TIMING)
+    bool kk_probe_any = false; int kk_probe_sweep = 0, kk_probe_conv = 0;
+#endif
     bool resume_mid_sweep = false;  // the fast loop already ran the motor + button rows of sweep it0
     if ((lim_lo_mask | lim_hi_mask) == 0u) {
         // FAST LOOP (no arm joint on a limit): straight-line sweep, registers only.  Contact rows of the manifold are
@@ -947,7 +959,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
             if (quiet) {
                 constexpr int tight_unroll = KK_TIGHT_UNROLL;
 #pragma unroll tight_unroll
-                do { KK_SWEEP_BUTTONS() KK_MOTOR_ROWS() } while (--left > 0);
+                do { KK_SWEEP_BUTTONS() KK_MOTOR_ROWS() KK_PROBE_SWEEP() } while (--left > 0);
                 it = P.iters;
             } else {
                 // watched normal rows c < nc (slots c >= nc: zero column, threshold -inf -- they never fire): arm part of J' . v' carried in
@@ -985,6 +997,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
                 do {
                     KK_SWEEP_BUTTONS()
                     KK_MOTOR_ROWS_WATCH()
+                    KK_PROBE_SWEEP()
                     ++it;
                     more = --left > 0;
 #pragma unroll
@@ -1004,6 +1017,7 @@ KK_DEV void kuka_physics_step(const KukaParams& P, KukaEnv& e, const KukaKin& k,
 #endif
     }
 #ifdef KK_TIMING
+    if (dbg) *dbg |= ((unsigned)kk_probe_conv & 255u) << 24;
     if (dbg) { *dbg |= ((unsigned)nc & 15u) << 2; if (lim_lo_mask | lim_hi_mask) *dbg |= 64u; if (it0 < P.iters) *dbg |= 2u | ((unsigned)(P.iters - it0) & 255u) << 8; }
 #endif
     if (it0 < P.iters) {

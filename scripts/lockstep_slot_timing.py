@@ -23,6 +23,7 @@ for _ in range(10):
 sim.prefetch_resets(stream=st); torch.cuda.synchronize()
 words = np.zeros(1 << 16, np.uint64)
 cat = {}
+conv_all = []
 slowest = []
 for t in range(60):
     sim.step(acts[t], None, obs, rew, done, None, None, stream=st)
@@ -34,6 +35,7 @@ for t in range(60):
     w = words[:nslots]
     cyc = (w >> np.uint64(32)).astype(np.int64); fl = (w & np.uint64(0xFFFFFFFF)).astype(np.int64)
     live = cyc > 0
+    conv_all.extend(((fl[live & ((fl & (1 << 18)) == 0)] >> 24) & 255).tolist())
     k = int(np.argmax(cyc))
     slowest.append((ms * 1e3, cyc[k], fl[k]))
     for c, f in zip(cyc[live], fl[live]):
@@ -45,6 +47,10 @@ print("slowest slot of each launch: launch us, slot cycles (us at 1.965 GHz), fl
 for ms, c, f in slowest[:30]:
     print("  %.1f us  %d cycles (%.1f us)  helper=%d done=%d record=%d general=%d(%d sweeps) watch=%d limit=%d nc=%d"
           % (ms, c, c / 1965.0, (f >> 18) & 1, (f >> 16) & 1, (f >> 17) & 1, (f >> 1) & 1, (f >> 8) & 255, f & 1, (f >> 6) & 1, (f >> 2) & 15))
+conv = np.array(conv_all)
+print("first sweep of the fast loop in which no motor row moved (0 = never within 150): histogram over %d slot-steps" % conv.size)
+for lo, hi in ((0, 0), (1, 20), (21, 40), (41, 60), (61, 80), (81, 100), (101, 120), (121, 150)):
+    print("  %3d..%3d: %6.2f %%" % (lo, hi, 100.0 * ((conv >= lo) & (conv <= hi)).mean()))
 print("categories: count, mean exit time us, max us")
 for key, (cnt, tot, mx) in sorted(cat.items(), key=lambda kv: -kv[1][1] / kv[1][0]):
     print("  %-60s %7d  %.1f  %.1f" % (key, cnt, tot / cnt / 1965.0, mx / 1965.0))

@@ -71,3 +71,16 @@ for name, fn in (("srl_policy_act", lambda: fp.act(n, on, act_env, logp, val, st
         fn()
     e1.record(); torch.cuda.synchronize()
     print("%s: %.1f us per launch (50 back-to-back launches, %d envs)" % (name, 1e3 * e0.elapsed_time(e1) / 50, n))
+    # the same 50 launches replayed from a captured CUDA graph: device time without the host's enqueue rate (what the trainer's captured
+    # collection loop pays)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(50):
+                fn_s = (lambda: fp.act(n, on, act_env, logp, val, stream=side.cuda_stream)) if name == "srl_policy_act" else (lambda: fp.filter(n, obs, on, update=True, stream=side.cuda_stream))
+                fn_s()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side); g.replay(); e1.record(side); torch.cuda.synchronize()
+    print("%s: %.1f us per launch inside a captured graph of 50" % (name, 1e3 * e0.elapsed_time(e1) / 50))
