@@ -1,12 +1,13 @@
 /*
- * srl_policy.h -- C-ABI of the two per-step helpers a GPU-resident PPO2 rollout needs next to srl_sim_step
- * (same shared library, libsrl_sim_b200.so): the policy step and the observation filter.  They belong to the
+ * srl_policy.h -- C-ABI of the helpers a GPU-resident PPO2 consumer needs next to srl_sim_step (same shared library,
+ * libsrl_sim_b200.so): the policy step and the observation filter of the collection loop, and the minibatch gradient of the update.  They belong to the
  * CONSUMER of the simulator, not to the environment boundary of include/srl_sim.h.
  *
  * Reference interfaces they replace (paths relative to the reference repo):
  *   srl_policy_act  <- stable-baselines 2.5 `PPO2` runner's `model.step(obs)` with `MlpPolicy` (two separate 64-64 tanh
  *                      towers), chosen by rl_baselines/rl_algorithm/ppo2.py:58-72; one call per env step:
  *                      policy forward, sample, log-probability, value, rollout-buffer writes
+ *   srl_ppo2_grad   <- the loss + `tf.gradients` of stable-baselines 2.5 `PPO2.setup_model`, run once per minibatch by `PPO2._train_step`
  *   srl_obs_filter  <- stable-baselines `VecNormalize._obfilt` (norm_obs=True, clip_obs=10), wrapped around the envs
  *                      by rl_baselines/utils.py:224-227: running mean / variance update + normalisation
  *
@@ -53,6 +54,32 @@ int srl_policy_act(const srl_mlp_policy* policy, int n, const float* obs, uint64
  *   out = clip((obs_raw - mean) / sqrt(var + eps), -clip, clip) in float32.  obs_dim <= 8. */
 int srl_obs_filter(int n, int obs_dim, const float* obs_raw, double* state, int update, float clip, float eps,
                    float* obs_norm_out, void* stream);
+
+/* Gradient tensors of an MlpPolicy, same shapes and layout as the weights (torch: `param.grad`, contiguous float32). */
+typedef struct srl_mlp_grads {
+    uint32_t struct_size;   /* = sizeof(srl_mlp_grads); checked */
+    uint32_t reserved;
+    float *pi_w1, *pi_b1, *pi_w2, *pi_b2, *pi_w3, *pi_b3;
+    float *vf_w1, *vf_b1, *vf_w2, *vf_b2, *vf_w3, *vf_b3;
+    float *logstd;          /* Box only */
+} srl_mlp_grads;
+
+/* The gradient of stable-baselines' PPO2 loss over one minibatch, in one pass: what `loss.backward()` leaves in `param.grad` for
+ *   loss = pg_loss - ent_coef * entropy + vf_coef * vf_loss     (PPO2.setup_model of stable-baselines 2.5, chosen by
+ *                                                                 rl_baselines/rl_algorithm/ppo2.py:58-72 of the reference)
+ *   A = (adv - mean(adv)) / (std(adv) + 1e-8) over the minibatch, ratio = exp(logp - old_logp),
+ *   pg_loss = mean(max(-A ratio, -A clip(ratio, 1 - c, 1 + c))),
+ *   vf_loss = 0.5 mean(max((v - ret)^2, (old_value + clip(v - old_value, -c, c) - ret)^2)).
+ * Gradient clipping and the optimiser step stay with the caller.
+ *   idx        : nullable i64[minibatch] row indices into the rollout arrays (NULL: rows 0 .. minibatch - 1)
+ *   obs        : f32[rows, obs_dim]; actions : i64[rows] (Discrete) / f32[rows, n_out] (Box, the unclipped samples)
+ *   adv, ret, old_logp, old_value : f32[rows]
+ *   workspace  : device memory of at least srl_ppo2_workspace_bytes(...) bytes (per-CTA partial gradients; no state between calls)
+ * The gradient tensors are OVERWRITTEN (not accumulated).  Deterministic: partial sums are combined in a fixed order. */
+size_t srl_ppo2_workspace_bytes(int obs_dim, int n_out, int discrete, int minibatch);
+int srl_ppo2_grad(const srl_mlp_policy* policy, const srl_mlp_grads* grads, int minibatch, const int64_t* idx, const float* obs,
+                  const void* actions, const float* adv, const float* ret, const float* old_logp, const float* old_value,
+                  float cliprange, float ent_coef, float vf_coef, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

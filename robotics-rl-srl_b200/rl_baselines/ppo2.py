@@ -131,7 +131,7 @@ def allreduce_mean_gradients(params, dist, world):
 
 
 def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None, device=0, hyperparams=None, verbose=1, cuda_graph=True,
-          phase_times=None, fused_act=None, prefetch_resets=None, episode_window=40):
+          phase_times=None, fused_act=None, prefetch_resets=None, episode_window=40, fused_update=None):
     """PPO2.learn on a BatchedSRLVecEnv.  Returns a history of (timesteps, mean episode return, fps).
 
     ``cuda_graph``: the n_steps-long collection loop (policy forward, action sampling, observation filter, one simulator
@@ -145,6 +145,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
     ``prefetch_resets`` (default: on whenever the envs live on a GPU; a no-op for the kinds without records): create the envs with ``srl_cfg.prefetch_resets`` -- every lockstep launch then uses the idle slot of each warp as a helper that
     prepares the next-episode records, so that a step whose env finishes an episode copies a record in instead of running reset() inside
     the launch (include/srl_sim.h: srl_sim_prefetch_resets; validated bit-identical on B200 in round 2).
+    ``fused_update`` (default: on whenever the envs live on a GPU): the gradient of a minibatch step comes from the library's
+    ``srl_ppo2_grad`` (include/srl_policy.h: forward, PPO2 loss derivative and backward of both towers in one pass, every activation on chip)
+    instead of torch autograd over [minibatch, 64] tensors; gradient clipping, the data-parallel all-reduce and Adam stay in torch.
     ``phase_times``: optional dict; when given, every update synchronises between its phases and accumulates the wall time of
     ``collect`` / ``gae`` / ``optimise`` in it (a profiling aid: the synchronisations cost throughput)."""
     hp = dict(PPO2_DEFAULTS); hp.update(hyperparams or {})
@@ -288,7 +291,30 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                 adv[t].copy_(lastgae)
             torch.add(adv, buf["val"], out=ret)
 
+    fused_grad = None
+    if fused_update is None:
+        fused_update = on_gpu
+    if fused_update:
+        if not on_gpu:
+            raise ValueError("fused_update=True needs the CUDA library (there is no CPU fallback)")
+        if (T * N) % mb:
+            raise ValueError("fused_update=True needs n_steps * num_envs divisible by nminibatches")
+        from srl_sim.policy import FusedPPO2Grad
+        fused_grad = FusedPPO2Grad(env.backend.library, policy, mb)
+
+    def zero_grads():
+        if fused_grad is None:         # the fused gradient kernel overwrites its static .grad tensors: nothing to clear
+            opt.zero_grad(set_to_none=True)
+
     def minibatch_step(idx):
+        if fused_grad is not None:     # the kernel overwrites the static .grad tensors
+            fused_grad(idx, flat["obs"], flat["act"], flat_adv, flat_ret, flat["logp"], flat["val"], hp["cliprange"], hp["ent_coef"], hp["vf_coef"],
+                       stream=env.backend.stream())
+            if dist is not None:
+                allreduce_mean_gradients(params, dist, world)
+            nn.utils.clip_grad_norm_(params, hp["max_grad_norm"])
+            opt.step()
+            return
         logp, ent, v = policy.evaluate(flat["obs"][idx], flat["act"][idx])
         a_mb = flat_adv[idx]
         a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
@@ -373,7 +399,7 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
             perm = torch.randperm(T * N, device=dev)
             for s in range(0, T * N, mb):
                 if not graph_update:
-                    opt.zero_grad(set_to_none=True)
+                    zero_grads()
                     minibatch_step(perm[s:s + mb])
                     continue
                 idx_static.copy_(perm[s:s + mb])
@@ -384,13 +410,13 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
                     side = torch.cuda.Stream(device=dev)
                     side.wait_stream(cur)
                     with torch.cuda.stream(side):
-                        opt.zero_grad(set_to_none=True)
+                        zero_grads()
                         minibatch_step(idx_static)
                     cur.wait_stream(side)
                     mb_warm += 1
                 else:
                     mb_graph = torch.cuda.CUDAGraph()
-                    opt.zero_grad(set_to_none=True)
+                    zero_grads()
                     with torch.cuda.graph(mb_graph):   # gradients are allocated from the graph's pool and re-created by every replay
                         minibatch_step(idx_static)
                     mb_graph.replay()                  # the capture only recorded this minibatch: now run it

@@ -9,15 +9,22 @@ Reference pieces replaced: stable-baselines' ``PPO2`` runner ``model.step(obs)``
 There is no CPU fallback here either: :class:`FusedPolicy` needs the CUDA library and CUDA tensors.
 """
 import ctypes
-from ctypes import POINTER, Structure, byref, c_float, c_int, c_int32, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, Structure, byref, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
 
 HIDDEN, MAX_OBS, MAX_OUT = 64, 8, 8
-POLICY_EXPORTS = ["srl_policy_act", "srl_obs_filter"]
+POLICY_EXPORTS = ["srl_policy_act", "srl_obs_filter", "srl_ppo2_grad", "srl_ppo2_workspace_bytes"]
 
 
 class SrlMlpPolicy(Structure):
     """struct srl_mlp_policy (include/srl_policy.h)."""
     _fields_ = [("struct_size", c_uint32), ("obs_dim", c_int32), ("n_out", c_int32), ("discrete", c_int32)] + \
+               [(name, c_void_p) for name in ("pi_w1", "pi_b1", "pi_w2", "pi_b2", "pi_w3", "pi_b3",
+                                              "vf_w1", "vf_b1", "vf_w2", "vf_b2", "vf_w3", "vf_b3", "logstd")]
+
+
+class SrlMlpGrads(Structure):
+    """struct srl_mlp_grads (include/srl_policy.h)."""
+    _fields_ = [("struct_size", c_uint32), ("reserved", c_uint32)] + \
                [(name, c_void_p) for name in ("pi_w1", "pi_b1", "pi_w2", "pi_b2", "pi_w3", "pi_b3",
                                               "vf_w1", "vf_b1", "vf_w2", "vf_b2", "vf_w3", "vf_b3", "logstd")]
 
@@ -28,6 +35,11 @@ def bind(cdll):
     cdll.srl_policy_act.argtypes = [POINTER(SrlMlpPolicy), c_int, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     cdll.srl_obs_filter.restype = c_int
     cdll.srl_obs_filter.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p]
+    cdll.srl_ppo2_workspace_bytes.restype = c_size_t
+    cdll.srl_ppo2_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    cdll.srl_ppo2_grad.restype = c_int
+    cdll.srl_ppo2_grad.argtypes = [POINTER(SrlMlpPolicy), POINTER(SrlMlpGrads), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]
     return cdll
 
 
@@ -90,3 +102,41 @@ class FusedPolicy(object):
         rc = self._lib.srl_obs_filter(int(n), self.obs_dim, obs_raw.data_ptr(), self.filter_state.data_ptr(), int(bool(update)),
                                       self.clip, self.eps, obs_norm_out.data_ptr(), stream)
         self._library.check(rc, "srl_obs_filter")
+
+
+class FusedPPO2Grad(object):
+    """``srl_ppo2_grad``: the gradient of the PPO2 loss over one minibatch in one pass (forward, loss derivative, backward of both towers
+    with every activation on chip), written into the policy's ``.grad`` tensors -- what ``loss.backward()`` of
+    ``rl_baselines.ppo2``'s minibatch step produces.  Gradient clipping and the optimiser step stay with torch."""
+
+    def __init__(self, library, policy, minibatch):
+        import torch
+        self._lib = bind(library.lib)
+        self._library = library
+        self.struct, self._keep = policy_struct(policy)
+        dev = policy.pi[0].weight.device
+        if dev.type != "cuda":
+            raise ValueError("FusedPPO2Grad needs a policy on a CUDA device (there is no CPU fallback)")
+        lin = lambda tower: [m for m in tower if hasattr(m, "weight")]
+        params = [t for layer in lin(policy.pi) + lin(policy.vf) for t in (layer.weight, layer.bias)]
+        if not policy.discrete:
+            params.append(policy.logstd)
+        self.grads = SrlMlpGrads()
+        self.grads.struct_size = ctypes.sizeof(SrlMlpGrads)
+        names = ["pi_w1", "pi_b1", "pi_w2", "pi_b2", "pi_w3", "pi_b3", "vf_w1", "vf_b1", "vf_w2", "vf_b2", "vf_w3", "vf_b3"] + ([] if policy.discrete else ["logstd"])
+        for name, prm in zip(names, params):
+            prm.grad = torch.zeros_like(prm)               # static gradient tensors: the kernel overwrites them, the optimiser reads them (capturable)
+            setattr(self.grads, name, prm.grad.data_ptr())
+        self.params = params
+        self.minibatch = int(minibatch)
+        nbytes = int(self._lib.srl_ppo2_workspace_bytes(self.struct.obs_dim, self.struct.n_out, self.struct.discrete, self.minibatch))
+        if nbytes <= 0:
+            raise ValueError("srl_ppo2_workspace_bytes: unsupported shape")
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+
+    def __call__(self, idx, obs, actions, adv, ret, old_logp, old_value, cliprange, ent_coef, vf_coef, stream=None):
+        """All arguments are CUDA tensors of the whole rollout (``idx``: int64 [minibatch] rows, or None for the first ``minibatch`` rows)."""
+        rc = self._lib.srl_ppo2_grad(byref(self.struct), byref(self.grads), self.minibatch, None if idx is None else idx.data_ptr(), obs.data_ptr(),
+                                     actions.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_logp.data_ptr(), old_value.data_ptr(),
+                                     float(cliprange), float(ent_coef), float(vf_coef), self.workspace.data_ptr(), self.workspace.numel(), stream)
+        self._library.check(rc, "srl_ppo2_grad")

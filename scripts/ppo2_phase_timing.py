@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "robotics-rl-srl_b200"))
 from rl_baselines.ppo2 import train
 n, T, updates = 4096, 128, int(sys.argv[1]) if len(sys.argv) > 1 else 10
-for fused in (False, True):
+for fused in (True,):
     pt = {}
     hist = train("KukaButtonGymEnv-v0", n, n * T * updates, seed=0, verbose=0, phase_times=pt, fused_act=fused)
     tot = sum(pt.values())

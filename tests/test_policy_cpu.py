@@ -128,7 +128,7 @@ def test_cuda_library_exports_the_policy_helpers():
     """Every symbol include/srl_policy.h declares is exported by the sm_100a library (loading needs no GPU)."""
     import re
     hdr = open(os.path.join(ROOT, "include", "srl_policy.h")).read()
-    declared = sorted(set(re.findall(r"^int\s+(srl_\w+)\s*\(", hdr, flags=re.M)))
+    declared = sorted(set(re.findall(r"^(?:int|size_t)\s+(srl_\w+)\s*\(", hdr, flags=re.M)))
     assert declared == sorted(POLICY_EXPORTS)
     if not os.path.isfile(CUDA_LIB):
         pytest.skip("CUDA library not built")
@@ -136,3 +136,5 @@ def test_cuda_library_exports_the_policy_helpers():
     for name in declared:
         assert hasattr(lib, name), name
     assert ctypes.sizeof(SrlMlpPolicy) == 16 + 13 * 8             # 4 x int32 + 13 pointers, no padding
+    from srl_sim.policy import SrlMlpGrads
+    assert ctypes.sizeof(SrlMlpGrads) == 8 + 13 * 8

@@ -167,3 +167,77 @@ def test_policy_act_kernel_against_an_independent_float64_numpy_model(cuda_lib):
     # 4096 x 200 draws: the pooled frequencies follow the mean softmax to a few standard errors
     emp, exp = counts.sum(0) / counts.sum(), np.exp(logsm).mean(0)
     assert np.abs(emp - exp).max() < 5 * np.sqrt(0.25 / counts.sum()) + 1e-4, (emp, exp)
+
+
+def _torch_ppo2_grads(pol, idx, obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef):
+    """rl_baselines.ppo2's minibatch step up to loss.backward(), in torch (autograd): the reference of the fused gradient kernel."""
+    for p in pol.parameters():
+        p.grad = None
+    logp, ent, v = pol.evaluate(obs[idx], act[idx])
+    a_mb = adv[idx]
+    a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+    ratio = torch.exp(logp - old_logp[idx])
+    pg = torch.max(-a_mb * ratio, -a_mb * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+    vclip = old_val[idx] + torch.clamp(v - old_val[idx], -clip, clip)
+    vf_loss = 0.5 * torch.max((v - ret[idx]) ** 2, (vclip - ret[idx]) ** 2).mean()
+    loss = pg - ent_coef * ent.mean() + vf_coef * vf_loss
+    loss.backward()
+    return [p.grad.detach().clone() for p in pol.parameters()]
+
+
+@pytest.mark.parametrize("discrete,obs_dim,n_out,rows,mb", [(True, 3, 6, 5000, 4096), (False, 3, 3, 3000, 1000), (True, 2, 4, 900, 777), (False, 5, 7, 400, 33)])
+def test_fused_ppo2_gradient_matches_torch_autograd(cuda_lib, discrete, obs_dim, n_out, rows, mb):
+    """srl_ppo2_grad against autograd on the same minibatch: every parameter gradient within 2e-4 of the largest entry of its tensor (+ 2e-6:
+    float32 sums over up to 4096 samples in another order); ratios far outside the clip range, clipped values and a ragged last chunk
+    are part of the data; a second call gives the same bytes (fixed summation order)."""
+    from srl_sim.policy import FusedPPO2Grad
+    lib = cuda_lib
+    torch.manual_seed(3)
+    pol = _policy(obs_dim, discrete, n_out, seed=7).cuda()
+    with torch.no_grad():                      # trained-looking weights: the default head gain of 0.01 makes every logit ~0
+        for p in pol.parameters():
+            p.mul_(3.0)
+        if not discrete:
+            pol.logstd.copy_(torch.linspace(-0.5, 0.3, n_out))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn((rows, obs_dim), device="cuda", generator=g)
+    act = torch.randint(0, n_out, (rows,), device="cuda", generator=g) if discrete else torch.randn((rows, n_out), device="cuda", generator=g)
+    with torch.no_grad():
+        logp0, _, v0 = pol.evaluate(obs, act)
+    # ratios from ~0.3 to ~3 and value moves up to ~1: both sides of both clip ranges.  The loss gradient is DISCONTINUOUS at the clip
+    # boundaries (inside: the live branch, outside: possibly the dead one), so a sample that sits on a boundary to within float32 rounding
+    # is decided by the last bit of the forward pass -- torch itself answers differently for a batch of 1 and a batch of 32 there
+    # (scripts/ppo2_grad_debug2.py found one such row in 5000).  Keep the data 5 % away from the four boundaries.
+    dl = 0.4 * torch.randn(rows, device="cuda", generator=g)
+    for edge in (-float(np.log(1.2)), -float(np.log(0.8))):          # logp - old_logp = -dl at log(1 +- clip)
+        dl = torch.where((dl - edge).abs() < 0.01, dl * 1.2, dl)
+    dvn = 0.3 * torch.randn(rows, device="cuda", generator=g)
+    dvn = torch.where((dvn.abs() - 0.2).abs() < 0.01, dvn * 1.2, dvn)
+    old_logp = (logp0 + dl).contiguous()
+    old_val = (v0 + dvn).contiguous()
+    adv = torch.randn(rows, device="cuda", generator=g) * 2.0 + 0.5
+    ret = (v0 + torch.randn(rows, device="cuda", generator=g)).contiguous()
+    idx = torch.randperm(rows, device="cuda", generator=g)[:mb].contiguous()
+    clip, ent_coef, vf_coef = 0.2, 0.01, 0.5
+    want = _torch_ppo2_grads(pol, idx, obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef)
+    fused = FusedPPO2Grad(lib, pol, mb)
+    fused(idx, obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = [p.grad.detach().clone() for p in pol.parameters()]
+    assert len(got) == len(want)
+    for (name, _), a, b in zip(pol.named_parameters(), got, want):
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a - b).abs().max())
+        assert err <= 2e-4 * scale + 2e-6, (name, err, scale)       # the absolute floor: a bias gradient is a sum of terms that may cancel
+    fused(idx, obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for p, a in zip(pol.parameters(), got):
+        assert torch.equal(p.grad, a)
+    # idx = None: the first `mb` rows
+    want0 = _torch_ppo2_grads(pol, torch.arange(mb, device="cuda"), obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef)
+    fused2 = FusedPPO2Grad(lib, pol, mb)
+    fused2(None, obs, act, adv, ret, old_logp, old_val, clip, ent_coef, vf_coef, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for (name, p), b in zip(pol.named_parameters(), want0):
+        err, scale = float((p.grad - b).abs().max()), float(b.abs().max()) + 1e-12
+        assert err <= 2e-4 * scale + 2e-6, (name, err, scale)
