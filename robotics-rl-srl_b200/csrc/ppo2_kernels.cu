@@ -4,7 +4,7 @@
 // What it replaces: torch autograd over a 131 072-sample minibatch of config 3 -- ~150 launches, every activation of both 64-64 towers
 // written to and read back from HBM / L2 (33 MB per [mb, 64] tensor), 2.2 ms per minibatch step even when captured in a CUDA graph, 71 % of a
 // PPO2 update once the collection loop costs 99 us per env step.  Here a persistent CTA keeps the weights (and W2 transposed) in shared
-// memory, walks its share of the minibatch in chunks of 32 samples, and for each chunk runs forward -> PPO2 loss derivative -> backward with
+// memory, walks its share of the minibatch in chunks of 64 samples, and for each chunk runs forward -> PPO2 loss derivative -> backward with
 // every activation in shared memory and the weight gradients accumulating in registers; the per-CTA partial gradients are summed in a fixed
 // order by a second kernel (deterministic: no atomics).  Gradient clipping and Adam stay with torch (a dozen launches over 9.3 k parameters).
 //
@@ -19,7 +19,8 @@
 
 namespace {
 
-constexpr int H = 64, WS = 68, CH = 32, NT = 128, MAXO = 8, MAXD = 8;
+constexpr int H = 64, WS = 68, CH = 64, NT = 256, MAXO = 8, MAXD = 8;      // 64 samples per chunk, 8 warps per CTA (two per scheduler)
+static_assert(NT == 4 * CH && NT == 256, "thread roles: 4 threads per sample in the heads, 128 owners per tower of the W2 gradient patches");
 
 // offsets of the parameter tensors inside a flat gradient vector (the order of the per-CTA partials)
 struct Seg { int pw1, pb1, pw2, pb2, pw3, pb3, vw1, vb1, vw2, vb2, vw3, vb3, ls, P; };
@@ -173,12 +174,13 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
     const float amean = s_adv[0], ainv = s_adv[1], inv_mb = 1.0f / (float)a.mb;
     // ---- gradient accumulators (registers; every entry of the flat gradient has exactly one owner thread) ----
     const int eg = t >> 4, og = t & 15;          // forward / delta tiles: samples 4 eg + e, units og + 16 k
-    const int jq = t >> 3, iq = t & 7;           // W2 gradient patch: rows 4 jq + jj, columns 8 iq + ii
-    float gw2p[4][8], gw2v[4][8];
+    const bool own_pi = t < 128;                 // W2 gradient: threads 0..127 own the policy tower's 4 x 8 patches, 128..255 the value tower's
+    const int jq = (t & 127) >> 3, iq = t & 7;   // rows 4 jq + jj, columns 8 iq + ii
+    float gw2[4][8];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) { gw2p[jj][ii] = 0.f; gw2v[jj][ii] = 0.f; }
+        for (int ii = 0; ii < 8; ++ii) gw2[jj][ii] = 0.f;
     float gw3p[4] = {0.f, 0.f, 0.f, 0.f}, gw1p[4] = {0.f, 0.f, 0.f, 0.f}, gw1v[4] = {0.f, 0.f, 0.f, 0.f};
     float gw3v = 0.f, gb3 = 0.f, gls = 0.f, gb2 = 0.f, gb1 = 0.f;       // gb2 / gb1: t < 64 the policy tower's unit t, t >= 64 the value tower's unit t - 64
     const int nchunks = (a.mb + CH - 1) / CH;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
 #pragma unroll 8
                 for (int n = 0; n < CH; ++n) { s = fmaf(d3[n * (MAXO + 1) + MAXO], hbv[n * WS + t], s); sb += d2p[n * WS + t]; }
                 gw3v += s; gb2 += sb;
-            } else {
+            } else if (t < 2 * H) {
                 float sb = 0.f;
 #pragma unroll 8
                 for (int n = 0; n < CH; ++n) sb += d2v[n * WS + (t - H)];
@@ -367,25 +369,19 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
                 gls += s;
             }
             // W2 gradient patches: per sample one delta quad and two activation quads
+            {
+                const float* dsrc = own_pi ? d2p : d2v;
+                const float* hsrc = own_pi ? hap : hav;
 #pragma unroll 4
-            for (int n = 0; n < CH; ++n) {
-                const float4 dq = *reinterpret_cast<const float4*>(d2p + n * WS + 4 * jq);
-                const float4 h0 = *reinterpret_cast<const float4*>(hap + n * WS + 8 * iq), h1 = *reinterpret_cast<const float4*>(hap + n * WS + 8 * iq + 4);
-                const float dd[4] = {dq.x, dq.y, dq.z, dq.w}, hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                for (int n = 0; n < CH; ++n) {
+                    const float4 dq = *reinterpret_cast<const float4*>(dsrc + n * WS + 4 * jq);
+                    const float4 h0 = *reinterpret_cast<const float4*>(hsrc + n * WS + 8 * iq), h1 = *reinterpret_cast<const float4*>(hsrc + n * WS + 8 * iq + 4);
+                    const float dd[4] = {dq.x, dq.y, dq.z, dq.w}, hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
+                    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                    for (int ii = 0; ii < 8; ++ii) gw2p[jj][ii] = fmaf(dd[jj], hh[ii], gw2p[jj][ii]);
-            }
-#pragma unroll 4
-            for (int n = 0; n < CH; ++n) {
-                const float4 dq = *reinterpret_cast<const float4*>(d2v + n * WS + 4 * jq);
-                const float4 h0 = *reinterpret_cast<const float4*>(hav + n * WS + 8 * iq), h1 = *reinterpret_cast<const float4*>(hav + n * WS + 8 * iq + 4);
-                const float dd[4] = {dq.x, dq.y, dq.z, dq.w}, hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii < 8; ++ii) gw2v[jj][ii] = fmaf(dd[jj], hh[ii], gw2v[jj][ii]);
+                        for (int ii = 0; ii < 8; ++ii) gw2[jj][ii] = fmaf(dd[jj], hh[ii], gw2[jj][ii]);
+                }
             }
             // delta 1 = (W2^T delta 2) (1 - h1^2): the same tile as the forward pass, on the transposed weights
             float o[4][4];
@@ -403,12 +399,14 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
         __syncthreads();
         // ---- 5: gradients of layer 1 ----
         {
-            const float* d1 = t < H ? d1p : d1v;
-            const int unit = t < H ? t : t - H;
-            float sb = 0.f;
+            if (t < 2 * H) {
+                const float* d1 = t < H ? d1p : d1v;
+                const int unit = t < H ? t : t - H;
+                float sb = 0.f;
 #pragma unroll 8
-            for (int n = 0; n < CH; ++n) sb += d1[n * WS + unit];
-            gb1 += sb;
+                for (int n = 0; n < CH; ++n) sb += d1[n * WS + unit];
+                gb1 += sb;
+            }
             for (int m = 0; m < 4; ++m) {
                 const int e = t + NT * m;
                 if (e < H * D) {
@@ -427,17 +425,14 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-            out[seg.pw2 + (4 * jq + jj) * H + 8 * iq + ii] = gw2p[jj][ii];
-            out[seg.vw2 + (4 * jq + jj) * H + 8 * iq + ii] = gw2v[jj][ii];
-        }
+        for (int ii = 0; ii < 8; ++ii) out[(own_pi ? seg.pw2 : seg.vw2) + (4 * jq + jj) * H + 8 * iq + ii] = gw2[jj][ii];
     for (int m = 0; m < 4; ++m) {
         const int e = t + NT * m;
         if (e < A * H) out[seg.pw3 + e] = gw3p[m];
         if (e < H * D) { out[seg.pw1 + e] = gw1p[m]; out[seg.vw1 + e] = gw1v[m]; }
     }
     if (t < H) { out[seg.vw3 + t] = gw3v; out[seg.pb2 + t] = gb2; out[seg.pb1 + t] = gb1; }
-    else { out[seg.vb2 + (t - H)] = gb2; out[seg.vb1 + (t - H)] = gb1; }
+    else if (t < 2 * H) { out[seg.vb2 + (t - H)] = gb2; out[seg.vb1 + (t - H)] = gb1; }
     if (t < A) out[seg.pb3 + t] = gb3;
     if (t == MAXO) out[seg.vb3] = gb3;
     if (!discrete && t >= 16 && t < 16 + A) out[seg.ls + (t - 16)] = gls;
