@@ -81,6 +81,12 @@ int srl_ppo2_grad(const srl_mlp_policy* policy, const srl_mlp_grads* grads, int 
                   const void* actions, const float* adv, const float* ret, const float* old_logp, const float* old_value,
                   float cliprange, float ent_coef, float vf_coef, void* workspace, size_t workspace_bytes, void* stream);
 
+/* GAE(lambda) over one rollout (the backward recursion of stable-baselines' PPO2 runner): rew, value, done (1.0 where the episode ended at that
+ * step), adv_out, ret_out are f32[n_steps, n_envs]; last_value f32[n_envs] is the value of the observation after the last step.
+ *   delta_t = rew_t + gamma * V_{t+1} * (1 - done_t) - V_t;  adv_t = delta_t + gamma * lam * (1 - done_t) * adv_{t+1};  ret_t = adv_t + V_t */
+int srl_ppo2_gae(int n_steps, int n_envs, const float* rew, const float* value, const float* done, const float* last_value, float gamma, float lam,
+                 float* adv_out, float* ret_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,6 +438,36 @@ __global__ void __launch_bounds__(NT, 1) ppo2_grad_kernel(const __grid_constant_
     if (!discrete && t >= 16 && t < 16 + A) out[seg.ls + (t - 16)] = gls;
 }
 
+// GAE(lambda) of one rollout, the reference's backward recursion (stable-baselines PPO2 runner): one thread per env, T sequential steps,
+// eight steps' loads in flight.  Separate roundings (no FMA contraction): the same bits as the torch recursion of rl_baselines/ppo2.py.
+__global__ void __launch_bounds__(128) gae_kernel(int T, int N, const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
+                                                   const float* __restrict__ last_val, float gamma, float gl, float* __restrict__ adv, float* __restrict__ ret) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float lastgae = 0.f, nextval = last_val[n];
+    for (int t0 = T - 1; t0 >= 0; t0 -= 8) {
+        float r[8], v[8], d[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int t = t0 - k;
+            const size_t o = (size_t)(t >= 0 ? t : 0) * N + n;
+            r[k] = rew[o]; v[k] = val[o]; d[k] = done[o];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int t = t0 - k;
+            if (t >= 0) {
+                const float nonterminal = __fsub_rn(1.0f, d[k]);
+                const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(gamma, nextval), nonterminal)), v[k]);
+                lastgae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nonterminal), lastgae));
+                const size_t o = (size_t)t * N + n;
+                adv[o] = lastgae; ret[o] = __fadd_rn(lastgae, v[k]);
+                nextval = v[k];
+            }
+        }
+    }
+}
+
 struct ReduceArgs { srl_mlp_grads g; Seg seg; int nparts; const float* partial; };
 
 // sum of the per-CTA partials in CTA order (deterministic) -> the parameter's gradient tensor
@@ -521,6 +551,15 @@ int srl_ppo2_grad(const srl_mlp_policy* p, const srl_mlp_grads* grads, int minib
     ReduceArgs r;
     r.g = *grads; r.seg = seg; r.nparts = ctas; r.partial = partial;
     ppo2_reduce_kernel<<<(seg.P + 255) / 256, 256, 0, st>>>(r);
+    SRL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int srl_ppo2_gae(int n_steps, int n_envs, const float* rew, const float* value, const float* done, const float* last_value, float gamma, float lam,
+                 float* adv_out, float* ret_out, void* stream) {
+    if (!rew || !value || !done || !last_value || !adv_out || !ret_out) { srl_set_error("ppo2_gae: null argument"); return 1; }
+    if (n_steps < 1 || n_envs < 1) { srl_set_error("ppo2_gae: bad shape"); return 1; }
+    gae_kernel<<<(n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_steps, n_envs, rew, value, done, last_value, gamma, (float)((double)gamma * (double)lam), adv_out, ret_out);
     SRL_CUDA_OK(cudaGetLastError());
     return 0;
 }

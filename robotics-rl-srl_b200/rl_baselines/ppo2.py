@@ -281,6 +281,9 @@ def train(env_id, num_envs, num_timesteps, seed=0, env_kwargs=None, log_dir=None
 
     def gae():
         """GAE(lambda), the reference's backward recursion over the rollout."""
+        if fused_grad is not None:     # one launch instead of ~6 small kernels per step of the recursion
+            fused_grad.gae(buf["rew"], buf["val"], buf["done"], last_val, hp["gamma"], hp["lam"], adv, ret, stream=env.backend.stream())
+            return
         with torch.no_grad():
             lastgae = torch.zeros(N, device=dev)
             for t in reversed(range(T)):

@@ -12,7 +12,7 @@ import ctypes
 from ctypes import POINTER, Structure, byref, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
 
 HIDDEN, MAX_OBS, MAX_OUT = 64, 8, 8
-POLICY_EXPORTS = ["srl_policy_act", "srl_obs_filter", "srl_ppo2_grad", "srl_ppo2_workspace_bytes"]
+POLICY_EXPORTS = ["srl_policy_act", "srl_obs_filter", "srl_ppo2_grad", "srl_ppo2_workspace_bytes", "srl_ppo2_gae"]
 
 
 class SrlMlpPolicy(Structure):
@@ -40,6 +40,8 @@ def bind(cdll):
     cdll.srl_ppo2_grad.restype = c_int
     cdll.srl_ppo2_grad.argtypes = [POINTER(SrlMlpPolicy), POINTER(SrlMlpGrads), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]
+    cdll.srl_ppo2_gae.restype = c_int
+    cdll.srl_ppo2_gae.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]
     return cdll
 
 
@@ -133,6 +135,13 @@ class FusedPPO2Grad(object):
         if nbytes <= 0:
             raise ValueError("srl_ppo2_workspace_bytes: unsupported shape")
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+
+    def gae(self, rew, value, done, last_value, gamma, lam, adv_out, ret_out, stream=None):
+        """``srl_ppo2_gae``: GAE(lambda) of a [T, N] rollout in one launch (float32 tensors; ``done`` holds 1.0 where an episode ended)."""
+        T, N = rew.shape
+        rc = self._lib.srl_ppo2_gae(int(T), int(N), rew.data_ptr(), value.data_ptr(), done.data_ptr(), last_value.data_ptr(), float(gamma), float(lam),
+                                    adv_out.data_ptr(), ret_out.data_ptr(), stream)
+        self._library.check(rc, "srl_ppo2_gae")
 
     def __call__(self, idx, obs, actions, adv, ret, old_logp, old_value, cliprange, ent_coef, vf_coef, stream=None):
         """All arguments are CUDA tensors of the whole rollout (``idx``: int64 [minibatch] rows, or None for the first ``minibatch`` rows)."""

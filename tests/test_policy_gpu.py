@@ -241,3 +241,26 @@ def test_fused_ppo2_gradient_matches_torch_autograd(cuda_lib, discrete, obs_dim,
     for (name, p), b in zip(pol.named_parameters(), want0):
         err, scale = float((p.grad - b).abs().max()), float(b.abs().max()) + 1e-12
         assert err <= 2e-4 * scale + 2e-6, (name, err, scale)
+
+
+def test_fused_gae_matches_the_torch_recursion(cuda_lib):
+    """srl_ppo2_gae against the backward recursion of rl_baselines.ppo2 (separate roundings on both sides: the same bits)."""
+    from srl_sim.policy import FusedPPO2Grad
+    T, N, gamma, lam = 128, 1000, 0.99, 0.95
+    g = torch.Generator(device="cuda").manual_seed(2)
+    rew = torch.randn((T, N), device="cuda", generator=g); val = torch.randn((T, N), device="cuda", generator=g)
+    done = (torch.rand((T, N), device="cuda", generator=g) < 0.03).float(); last_val = torch.randn(N, device="cuda", generator=g)
+    adv = torch.zeros((T, N), device="cuda"); ret = torch.zeros((T, N), device="cuda")
+    lastgae = torch.zeros(N, device="cuda")
+    for t in reversed(range(T)):
+        nonterminal = 1.0 - done[t]
+        nextval = last_val if t == T - 1 else val[t + 1]
+        delta = rew[t] + gamma * nextval * nonterminal - val[t]
+        lastgae = delta + gamma * lam * nonterminal * lastgae
+        adv[t].copy_(lastgae)
+    torch.add(adv, val, out=ret)
+    fused = FusedPPO2Grad(cuda_lib, _policy(3, True, 6, seed=1).cuda(), 64)
+    a2 = torch.zeros_like(adv); r2 = torch.zeros_like(ret)
+    fused.gae(rew, val, done, last_val, gamma, lam, a2, r2, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (a2 - adv).abs().max().item() <= 1e-6 * adv.abs().max().item() and (r2 - ret).abs().max().item() <= 1e-6 * ret.abs().max().item()
