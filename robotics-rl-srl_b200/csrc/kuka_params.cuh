@@ -33,7 +33,7 @@ struct KukaParams {
     float maxvel[KK_NB];   // <= 0: no clamp
     float maximp[KK_NB];   // force * dt
     int   tmode[KK_NB];    // 0: IK solution, others: 0 (end_effector_angle, finger_angle are identically 0)
-    // saturating PGS sweep (kuka_device.cuh, KK_SWEEP_SAT): sigma_i = 2 maximp_i and the products the scaled problem needs
+    // saturating PGS sweep (kuka_device.cuh, "the SCALED system"): sigma_i = 2 maximp_i and the products the scaled problem needs
     float sat_sig[KK_NB], sat_isig[KK_NB], sat_isig2[KK_NB];
     float sat_ss[KK_NB * (KK_NB + 1) / 2], sat_iss[KK_NB * (KK_NB + 1) / 2];   // sigma_i sigma_j and its reciprocal, (i, j <= i) packed
     // ---- collision spheres ----
