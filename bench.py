@@ -22,6 +22,7 @@ rl_baselines/rl_algorithm/ppo2.py:58-72): a single kernel launch, 4096 x 128 env
                  plumbing_config1 = configs[0], MobileRobotGymEnv-v0, 4 env OBJECTS behind the reference-shaped
                                     (Dummy)VecEnv plumbing, random agent, 1600 steps (rank 0)
                  render_kuka      = image observations: one srl_sim_render of 4096 Kuka frames, 224 x 224 (rank 0)
+                 ppo2_config3     = configs[2], PPO2 from rl_baselines.train on 4096 Kuka envs, 14 updates (rank 0)
   --impl reference : the reference arm.  PyBullet is not installable here, so it times the oracle -- the CPU
           restatement of the reference's step -- with every host thread, on the same configs.
 """
@@ -403,6 +404,25 @@ def render_leg(be, n=4096, width=224, height=224, reps=10):
                        "l2": "256 MB flush between repetitions", "reps": reps}}
 
 
+def ppo2_leg(device_index, updates=14):
+    """BASELINE configs[2]: KukaButtonGymEnv-v0 ground_truth, PPO2 from rl_baselines.train, 4096 envs on one B200 -- the trainer's own loop (policy step,
+    lockstep simulator step with next-episode records, observation filter: three launches per env step inside a captured graph; GAE and the
+    16 minibatch gradients through srl_ppo2_gae / srl_ppo2_grad; clip + Adam in torch).  `value` = env-steps/s over the updates after the
+    first four (graph captures and warm-up excluded), `cumulative` includes them."""
+    from rl_baselines.ppo2 import train
+    n, T = 4096, 128
+    t0 = time.time()
+    hist = train("KukaButtonGymEnv-v0", n, n * T * updates, seed=0, verbose=0, device=device_index)
+    wall = time.time() - t0
+    times = [st / fps for st, _, fps in hist]                  # seconds since the training loop started, per update
+    k = min(4, len(hist) - 2)
+    steady = (hist[-1][0] - hist[k][0]) / max(times[-1] - times[k], 1e-9)
+    return {"metric": "env-steps/sec PPO2 training KukaButtonGymEnv-v0 ground_truth @4096 envs (rl_baselines.train --algo ppo2)", "value": steady, "unit": "env-steps/s",
+            "cumulative_incl_graph_capture": hist[-1][2], "updates": len(hist), "steady_state_over_updates": [k + 2, len(hist)],
+            "ms_per_update": 1e3 * (times[-1] - times[k]) / (len(hist) - 1 - k), "mean_episode_return_last": hist[-1][1], "wall_s_incl_env_setup": wall,
+            "config": {"workload": "n_steps 128, nminibatches 4, noptepochs 4 (reference hyper-parameters), 524 288 samples per update", "data": "synthetic: the env's own random resets"}}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's own step on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -592,6 +612,10 @@ def run_b200(args):
             secondary["render_kuka"] = render_leg(be)
         except Exception as ex:
             secondary["render_kuka"] = {"error": repr(ex)}
+        try:
+            secondary["ppo2_config3"] = ppo2_leg(local_rank)
+        except Exception as ex:
+            secondary["ppo2_config3"] = {"error": repr(ex)}
     metric, config = metric_and_config(args.workload, world)
     line = {"metric": metric, "value": main["value"], "unit": "env-steps/s",
             "n_gpus": world, "steps": main["steps"], "warmup": main["warmup"], "ms_per_step": main["ms_per_step"],
