@@ -423,6 +423,36 @@ def ppo2_leg(device_index, updates=14):
             "config": {"workload": "n_steps 128, nminibatches 4, noptepochs 4 (reference hyper-parameters), 524 288 samples per update", "data": "synthetic: the env's own random resets"}}
 
 
+def render_reference_leg(cores, frames_per_thread=4, width=224, height=224):
+    """The render leg on the host: the CPU checker of the ray caster (oracle/liboracle_sim.so, the same primitive lists and per-pixel arithmetic
+    as the CUDA kernels, csrc/render_core.h) on every host thread, one env shard per thread, a bounded sample of the 4096-frame call.  The
+    reference itself renders with PyBullet's TinyRenderer (CPU, one 224 x 224 frame per env step: the published 250 FPS on 8 cores includes it)."""
+    from srl_sim.model import load_kuka_scene
+    from srl_sim.render import KUKA_CAMERA, camera
+    be = _oracle_backend()
+    blob = load_kuka_scene().blob
+    parts = []
+    for k in range(max(1, cores)):
+        sim = be.make_sim("KukaButtonGymEnv-v0", frames_per_thread, seed=0, model_blob=blob, global_env_offset=k * frames_per_thread, random_target=True)
+        sim.reset()
+        parts.append((sim, np.zeros((frames_per_thread, height, width, 3), np.uint8)))
+    cam = camera(**KUKA_CAMERA)
+
+    def once():
+        ths = [threading.Thread(target=lambda p=p: p[0].render(cam, width, height, p[1])) for p in parts]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+    once()
+    t = min(once() for _ in range(2))
+    n = frames_per_thread * len(parts)
+    return {"metric": "frames/sec srl_sim_render KukaButtonGymEnv-v0 %dx%d (CPU checker)" % (width, height), "value": n / t, "unit": "frames/s", "cores": len(parts),
+            "sample": "%d frames (%d per host thread) of the 4096-frame call, every pixel against every primitive (the CPU checker does not cull)" % (n, frames_per_thread)}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference's own step on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -465,6 +495,10 @@ def run_reference(args):
                                  "sample": "%d envs x %d steps per step x 3 (bounded sample of the T=1024 rollout), CPU oracle" % (mn, mT)}
         sec["plumbing_config1"] = plumbing_config1(_oracle_library(), -1)
         sec["plumbing_config1"]["impl"] = "CPU oracle behind the same Python env objects (stand-in for PyBullet + SubprocVecEnv)"
+        try:
+            sec["render_kuka"] = render_reference_leg(cores)
+        except Exception as ex:
+            sec["render_kuka"] = {"error": repr(ex)}
         line["secondary"] = sec
     print(json.dumps(line))
 
